@@ -1,0 +1,405 @@
+#!/usr/bin/env python
+"""Benchmark of the cube-transition hot path (BASELINE.json metric: cube transitions/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A *step* is one pass of the fused scramble (K1) over one batch: BASELINE.json configs[2],
+"3x3x3 batched scramble+step, 64M instances x depth 30, sharded across 8xB200", i.e.
+8 Mi instances x depth 30 per GPU (weak scaling: every rank owns one such slice; the only
+collective is the int64 counter all-reduce after each step).  Moves are synthetic
+(`torch.randint`, seed 1234 + rank) and resident in HBM before the timed region; the
+move buffer (252 MB) and the outputs (495 MB) are each larger than the 126 MB L2.
+
+Rank 0 prints ONE JSON line: `value` (device-timed, inputs resident), `e2e` (same metric
+through the host-buffer C-ABI pipeline, pinned host buffers, H2D+D2H inside the timed
+region), `roofline` for the scramble kernel, `cpu_baseline` (the reference-semantics
+per-cube Python env on all host cores, N=1 only), the other BASELINE configs measured
+briefly (`other_configs`), `clocks`, and `gpu_launches`.
+
+`--impl reference` times the reference's own CPU implementation of the path: the
+reference is pure Python and cannot travel to the GPU box (and does not import without
+gym/matplotlib), so this arm runs the in-repo restatement of its per-cube env
+(oracle/scalar_env.py, same NumPy calls and Python loops as cube_env.py:71-111) on every
+host core.  oracle/ is used here only as the thing the reference arm measures.
+"""
+import argparse
+import json
+import multiprocessing as mp
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CUBE_SIZE = 3
+DEPTH = 30
+N_PER_GPU = 8 * 2 ** 20
+WORKLOAD = ("BASELINE configs[2]: 3x3x3 batched scramble+step, depth 30, 8 Mi instances per GPU "
+            "(= 64 Mi sharded over 8 GPUs); moves resident in HBM, buffers > L2 (no flush needed)")
+
+
+# ----------------------------------------------------------------------------- CPU arms
+_ENV = None
+
+
+def _cpu_init(cube_size):
+    global _ENV
+    from oracle.scalar_env import ScalarCubeEnv
+    _ENV = ScalarCubeEnv(cube_size)
+
+
+def _cpu_task(args):
+    depth, n_cubes, seed = args
+    import numpy as np
+    env, rng = _ENV, np.random.RandomState(seed)
+    solved = 0
+    for _ in range(n_cubes):
+        env.init_state()
+        for a in rng.randint(env.action_dim, size=depth):
+            _, _, done, _ = env.step(a)
+        solved += int(done)
+    return n_cubes * depth, solved
+
+
+class CpuReferencePool(object):
+    """The reference-semantics per-cube Python env (oracle/scalar_env.py) on one process per
+    host core.  One `run` = every process scrambles `cubes_per_proc` cubes to `depth`."""
+
+    def __init__(self, cube_size, procs):
+        self.procs = procs
+        self.pool = mp.get_context("spawn").Pool(procs, initializer=_cpu_init, initargs=(cube_size,))
+        self.run(DEPTH, 4)                                  # imports + first-touch, untimed
+
+    def run(self, depth, cubes_per_proc, seed0=1000):
+        t0 = time.perf_counter()
+        res = self.pool.map(_cpu_task, [(depth, cubes_per_proc, seed0 + i) for i in range(self.procs)], chunksize=1)
+        return time.perf_counter() - t0, sum(r[0] for r in res)
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def host_procs():
+    return max(1, min(os.cpu_count() or 1, 256))
+
+
+def cpu_c_oracle(cube_size, depth, n):
+    import numpy as np
+    from oracle import cube_c
+    moves = np.random.RandomState(0).randint(12 if cube_size == 3 else 6, size=(n, depth)).astype(np.uint8)
+    cube_c.scramble(cube_size, moves[: n // 8])
+    t0 = time.perf_counter()
+    cube_c.scramble(cube_size, moves)
+    dt = time.perf_counter() - t0
+    return n * depth / dt, cube_c.num_threads()
+
+
+def run_reference_arm(args):
+    """K timed steps; each step is a bounded sample of the workload sized so that the whole run
+    takes about `--ref-seconds` of wall clock whatever K is."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    procs = host_procs()
+    pool = CpuReferencePool(CUBE_SIZE, procs)
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    # ~28 k transitions/s/core: cubes per process per step for the time budget
+    cubes = max(8, int(args.ref_seconds * 28000.0 / DEPTH / (steps + warmup)))
+    for i in range(warmup):
+        pool.run(DEPTH, cubes, seed0=5000 + 1000 * i)
+    t_total, tr_total = 0.0, 0
+    for i in range(steps):
+        dt, n_tr = pool.run(DEPTH, cubes, seed0=100000 + 1000 * i)
+        t_total += dt
+        tr_total += n_tr
+    pool.close()
+    value = tr_total / t_total
+    sample = "%d processes x %d cubes x depth %d per step (3x3x3 per-cube Python env), %d steps" % (
+        procs, cubes, DEPTH, steps)
+    line = {
+        "impl": "reference", "metric": "cube transitions/sec", "value": value, "unit": "transitions/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * t_total / steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "CPU arm: each step is a bounded sample of the same workload "
+                   "on every host core (the reference scales by OS processes, train.py:85-92)"},
+        "cpu_baseline": {"value": value, "unit": "transitions/s", "cores": procs, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "transitions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler(object):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index, period=0.01):
+        self.samples, self.reasons, self.period, self._stop = [], set(), period, threading.Event()
+        self.max_mhz, self._h, self._nv = None, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception:                                   # noqa: BLE001 - NVML optional
+            self._h = None
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        nv = self._nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                for b, name in self.REASONS.items():
+                    if bits & b and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:                               # noqa: BLE001
+                pass
+            self._stop.wait(self.period)
+
+    def __enter__(self):
+        if self._h is not None:
+            self._t.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._h is not None:
+            self._t.join(timeout=2)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def time_launches(torch, fn, iters, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e-3              # seconds per launch
+
+
+def measure_other_configs(torch, ops, adi, dev, peak_gbs):
+    """BASELINE configs 2, 4, 5 and the single-step kernel, device-timed (CUDA events), with the
+    algorithmic bytes of SURVEY.md section 8d."""
+    out = {}
+    gen = torch.Generator(device=dev).manual_seed(4321)
+
+    def entry(name, seconds, units, unit_name, alg_bytes):
+        gbs = alg_bytes / seconds / 1e9
+        out[name] = {"value": units / seconds, "unit": unit_name, "ms": seconds * 1e3,
+                     "algorithmic_GBps": gbs, "hbm_frac": gbs / peak_gbs}
+
+    # config 2: 2x2x2 fused scramble, 16 Mi x depth 20
+    n, d = 16 * 2 ** 20, 20
+    moves = torch.randint(0, 6, (n, d), dtype=torch.uint8, device=dev, generator=gen)
+    st = torch.empty((n, 24), dtype=torch.uint8, device=dev)
+    so = torch.empty(n, dtype=torch.uint8, device=dev)
+    rw = torch.empty(n, dtype=torch.float32, device=dev)
+    t = time_launches(torch, lambda: ops.scramble(2, moves, out=st, solved=so, reward=rw), 10)
+    entry("config2_2x2_scramble_16Mi_x20", t, n * d, "transitions/s", n * (d + 24 + 1 + 4))
+    del moves, st, so, rw
+
+    # K2: one step on resident states (3x3x3 8 Mi, 2x2x2 16 Mi): 2S + 1 + 1 + 4 bytes per transition
+    for size, n in ((3, 8 * 2 ** 20), (2, 16 * 2 ** 20)):
+        s_ = ops.N_STICKERS[size]
+        states = ops.solved_states(size, n, dev)
+        act = torch.randint(0, ops.N_ACTIONS[size], (n,), dtype=torch.uint8, device=dev, generator=gen)
+        so = torch.empty(n, dtype=torch.uint8, device=dev)
+        rw = torch.empty(n, dtype=torch.float32, device=dev)
+        t = time_launches(torch, lambda: ops.step(size, states, act, solved=so, reward=rw), 10)
+        entry("step_%dx%d_resident_%dMi" % (size, size, n >> 20), t, n, "transitions/s", n * (2 * s_ + 6))
+        del states, act, so, rw
+
+    # config 4: 3x3x3 ADI expansion, 4 Mi parents -> bf16 [N,12,480] + solved + reward
+    n = 4 * 2 ** 20
+    parents, _, _ = ops.scramble(3, torch.randint(0, 12, (n, 30), dtype=torch.uint8, device=dev, generator=gen),
+                                 want_flags=False)
+    child = torch.empty((n, 12, 20, 24), dtype=torch.bfloat16, device=dev)
+    t = time_launches(torch, lambda: ops.expand(3, parents, dtype=torch.bfloat16, child_onehot=child), 5, warmup=2)
+    entry("config4_3x3_adi_expand_4Mi_parents", t, n, "parents/s", n * (54 + 12 * (960 + 1 + 4)))
+    out["config4_3x3_adi_expand_4Mi_parents"]["child_transitions_per_s"] = 12 * n / t
+    del parents, child
+
+    # config 5: 2x2x2 MCTS leaves, 1 Mi: leaf one-hot bf16 + children stickers + done flags
+    n = 2 ** 20
+    leaves, _, _ = ops.scramble(2, torch.randint(0, 6, (n, 11), dtype=torch.uint8, device=dev, generator=gen),
+                                want_flags=False)
+    t = time_launches(torch, lambda: ops.expand(2, leaves, dtype=torch.bfloat16, want_children=True,
+                                                want_child_onehot=False, want_parent_onehot=True), 10)
+    entry("config5_2x2_mcts_leaf_expand_1Mi", t, n, "leaves/s", n * (24 + 294 + 144 + 6 + 24))
+    return out
+
+
+def run_b200_arm(args):
+    import torch
+    import rubiks_cube_solver_b200 as R
+    from rubiks_cube_solver_b200 import adi, ops
+    from rubiks_cube_solver_b200 import dist as cdist
+
+    rank, local, world = cdist.init_from_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback on the product path)")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    R.load_library()
+
+    n, depth, size = args.instances_per_gpu, DEPTH, CUBE_SIZE
+    S = ops.N_STICKERS[size]
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    moves = torch.randint(0, 12, (n, depth), dtype=torch.uint8, device=dev, generator=gen)
+    states = torch.empty((n, S), dtype=torch.uint8, device=dev)
+    solved = torch.empty(n, dtype=torch.uint8, device=dev)
+    reward = torch.empty(n, dtype=torch.float32, device=dev)
+    counters = ops.new_counters(dev)
+    totals = torch.zeros(4, dtype=torch.int64, device=dev)
+
+    def step():
+        counters.zero_()
+        ops.scramble(size, moves, out=states, solved=solved, reward=reward, counters=counters)
+        totals.copy_(counters)
+        cdist.reduce_counters(totals)                     # the path's only collective: int64[4] SUM
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        barrier()
+    step_s = cdist.max_over_ranks(e0.elapsed_time(e1) * 1e-3 / args.steps, dev)
+    total_tr = world * n * depth
+    value = total_tr / step_s
+    solved_total, produced_total = int(totals[0]), int(totals[1])
+    assert produced_total == world * n, (produced_total, world * n)
+
+    # roofline of the dominant kernel: kernel-only launches, CUDA events on the launching stream
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak_gbs, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    else:
+        peak_gbs, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
+    kern_s = time_launches(torch, lambda: ops.scramble(size, moves, out=states, solved=solved, reward=reward), 20)
+    alg_bytes = n * (depth + S + 1 + 4)
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "scramble3_dram_bytes_per_launch.json")
+    if os.path.exists(prof):
+        try:
+            traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+        except Exception:                                   # noqa: BLE001
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "scramble_kernel<3,staged>", "achieved": alg_bytes / kern_s / 1e9,
+                "peak": peak_gbs, "unit": "GB/s", "frac": alg_bytes / kern_s / 1e9 / peak_gbs, "traffic": traffic,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                "kernel_ms": kern_s * 1e3, "transitions_per_s_kernel_only": n * depth / kern_s,
+                "note": "K1 is issue/ALU+shared-memory bound, not HBM bound (SURVEY.md 8d): the HBM fraction "
+                        "is reported as the contract asks; see profiles/ for the limiter"}
+
+    # end to end through the host-buffer C-ABI pipeline (pinned host memory, copies inside the timed region)
+    pipe = ops.HostScramblePipeline(size, depth, chunk_instances=args.e2e_chunk, n_stages=3, device=dev)
+    h_moves = moves.cpu().pin_memory()
+    h_states = torch.empty((n, S), dtype=torch.uint8).pin_memory()
+    h_solved = torch.empty(n, dtype=torch.uint8).pin_memory()
+    h_reward = torch.empty(n, dtype=torch.float32).pin_memory()
+    e2e_steps = max(2, min(args.steps, args.e2e_steps))
+    for _ in range(2):
+        pipe.run(h_moves, h_states, h_solved, h_reward)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        _, _, _, e2e_count = pipe.run(h_moves, h_states, h_solved, h_reward)
+    torch.cuda.synchronize()
+    e2e_s = cdist.max_over_ranks((time.perf_counter() - t0) / e2e_steps, dev)
+    barrier()
+    assert bool((h_states[:4096] == states[:4096].cpu()).all()) and e2e_count == int(counters[0])
+    e2e = {"value": total_tr / e2e_s, "unit": "transitions/s", "h2d_bytes_per_step": n * depth,
+           "d2h_bytes_per_step": n * (S + 1 + 4), "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+           "api": "cube_pipeline_scramble_host (C ABI) via ops.HostScramblePipeline.run, pinned host buffers"}
+    pipe.close()
+    del h_moves, h_states, h_solved, h_reward
+
+    line = {
+        "metric": "cube transitions/sec", "value": value, "unit": "transitions/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": step_s * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "cube_size": size, "depth": depth, "instances_per_gpu": n,
+                   "instances_total": world * n, "l2": "inputs (252 MB/GPU) and outputs (495 MB/GPU) exceed the 126 MB L2",
+                   "collective": "int64[4] all-reduce(SUM) of solved/produced counters per step"},
+        "solved_total": solved_total, "reward_total": 2 * solved_total - produced_total,
+        "e2e": e2e, "roofline": roofline, "gpu_launches": args.steps, "clocks": clocks.summary(),
+    }
+
+    if rank == 0 and world == 1:
+        if not args.skip_other:
+            del moves, states, solved, reward
+            torch.cuda.empty_cache()
+            line["other_configs"] = measure_other_configs(torch, ops, adi, dev, peak_gbs)
+        if not args.skip_cpu:
+            procs = host_procs()
+            pool = CpuReferencePool(size, procs)
+            dt, n_tr = pool.run(depth, args.cpu_cubes_per_proc)
+            pool.close()
+            line["cpu_baseline"] = {
+                "value": n_tr / dt, "unit": "transitions/s", "cores": procs, "kind": "port",
+                "sample": "%d processes x %d cubes x depth %d = %d transitions of the 3x3x3 per-cube Python env "
+                          "(oracle/scalar_env.py, reference semantics cube_env.py:71-111)" % (
+                              procs, args.cpu_cubes_per_proc, depth, n_tr)}
+            cv, threads = cpu_c_oracle(size, depth, 2 ** 21)
+            line["cpu_baseline_c"] = {"value": cv, "unit": "transitions/s", "cores": threads, "kind": "port",
+                                      "sample": "plain-C oracle (OpenMP), 2 Mi instances x depth 30"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=("b200", "reference"), default="b200")
+    ap.add_argument("--instances-per-gpu", type=int, default=N_PER_GPU)
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-chunk", type=int, default=1 << 20)
+    ap.add_argument("--cpu-cubes-per-proc", type=int, default=15000)
+    ap.add_argument("--ref-seconds", type=float, default=45.0)
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-other", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,136 @@
+/* cube_b200.h -- C ABI of the B200-native batched cube simulator (libcube_b200.so).
+ *
+ * This is the drop-in boundary for the reference's rollout / training-data hot
+ * path.  The reference is pure Python (no FFI of its own); each entry point below
+ * names the reference code whose batched equivalent it computes, and
+ * INTEGRATION.md shows the ctypes binding a maintainer of the reference adds.
+ * Paths are relative to the reference tree (SUNGBEOMCHOI/Rubiks-Cube-Solver).
+ *
+ * Conventions
+ *   - cube_size is 2 (2x2x2: S=24 stickers, A=6 actions, one-hot 7x21=147) or
+ *     3 (3x3x3: S=54, A=12, one-hot 20x24=480); anything else -> CUBE_ERR_SIZE
+ *     (the reference raises NotImplementedError, cube_env.py:43-44).
+ *   - sticker rows are uint8 colours 0..5 in the reference's sticker order
+ *     (py333.py:3-19; py222), row-major [n, S]; actions are uint8 indices in the
+ *     order of cube_env.py:24-28.
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; arrays
+ *     are contiguous and their base must be 16-byte aligned (CUBE_ERR_ALIGN).
+ *   - calls are asynchronous on `stream` (a cudaStream_t, may be NULL), never
+ *     allocate, never synchronise, keep no state between calls and are
+ *     re-entrant.  Return value: 0, a negative CUBE_ERR_*, or a positive
+ *     cudaError_t.  cube_last_error() describes the last non-zero return of
+ *     the calling thread.
+ *   - action indices are NOT range-checked on the hot path (indices >= A are
+ *     reduced mod 16 and rows A..15 are no-ops); call cube_validate_actions
+ *     when the reference's IndexError (cube_env.py:86,96) must be reproduced.
+ *   - counters, when non-NULL, is uint64[4] on the device and is only ever
+ *     ADDED to: [0] += outputs that are solved, [1] += outputs produced,
+ *     [2] += out-of-range actions (cube_validate_actions), [3] reserved.
+ *     Rewards are +1.0f / -1.0f, so a reward total is 2*[0] - [1] exactly.
+ */
+#ifndef CUBE_B200_H
+#define CUBE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CUBE_ABI_VERSION 1
+
+#define CUBE_OK 0
+#define CUBE_ERR_SIZE (-1)
+#define CUBE_ERR_ARG (-2)
+#define CUBE_ERR_ALIGN (-3)
+#define CUBE_ERR_ACTION (-4)
+
+#define CUBE_DTYPE_BF16 0
+#define CUBE_DTYPE_F32 1
+#define CUBE_DTYPE_U8 2
+
+int cube_abi_version(void);
+const char* cube_last_error(void);
+
+/* number of SMs of the current device (grid sizing is done inside the library) */
+int cube_sm_count(void);
+
+/* Fused scramble from the solved cube -- reset()'s loop `init_state(); for a in
+ * action_sequence: step(a)` (cube_env.py:61-67) and the per-cube loop of
+ * get_random_samples (cube_env.py:187-191), for n instances at once.
+ *   moves      [n, depth] uint8     in
+ *   states_out [n, S]     uint8     out  final sticker rows (== chaining doMove_3, py333.py:220-222)
+ *   solved     [n]        uint8     out  or NULL   isSolved_3 (py333.py:229-233) of the final row
+ *   reward     [n]        float32   out  or NULL   +1.0 / -1.0 (cube_env.py:89-104)
+ * depth >= 0 (depth 0 returns solved cubes). */
+int cube_scramble(int cube_size, const uint8_t* moves, int64_t n, int depth, uint8_t* states_out,
+                  uint8_t* solved, float* reward, uint64_t* counters, void* stream);
+
+/* One transition on resident states -- CubeEnv.step (cube_env.py:71-111):
+ * states[i] <- states[i][moveDefs[actions[i]]], then solved / reward.  In place. */
+int cube_step(int cube_size, uint8_t* states, const uint8_t* actions, int64_t n, uint8_t* solved,
+              float* reward, uint64_t* counters, void* stream);
+
+/* `depth` transitions per instance starting from given sticker rows (any byte
+ * content); states_out may alias states_in.  moves is [n, depth]. */
+int cube_walk(int cube_size, const uint8_t* states_in, const uint8_t* moves, int64_t n, int depth,
+              uint8_t* states_out, uint8_t* solved, float* reward, uint64_t* counters, void* stream);
+
+/* isSolved_3 / isSolved (py333.py:229-233) and the reward of resident rows. */
+int cube_solved(int cube_size, const uint8_t* states, int64_t n, uint8_t* solved, float* reward,
+                uint64_t* counters, void* stream);
+
+/* sim_state_to_state (cube_env.py:132-152): one-hot network input of each row,
+ * [n, 20, 24] or [n, 7, 21] elements of `dtype` (bf16 / f32 / u8), exactly one 1
+ * per one-hot row; 3x3x3 corners use the reference's table as shipped. */
+int cube_encode(int cube_size, const uint8_t* states, int64_t n, void* onehot, int dtype, void* stream);
+
+/* ADI / MCTS expansion -- the child loop of get_target_value (cube_env.py:212-238)
+ * and of MCTS.expand (mcts.py:96-101) for n parents at once, children in action order.
+ *   children      [n, A, S]   uint8    or NULL   child sticker rows
+ *   child_onehot  [n, A, D]   dtype    or NULL   network input of every child
+ *   parent_onehot [n, D]      dtype    or NULL   network input of the parent (mcts.py:92)
+ *   solved        [n, A]      uint8    or NULL   done flag of every child
+ *   reward        [n, A]      float32  or NULL
+ * The reference stops at the first solved child (cube_env.py:217-220); here all A
+ * children are produced and `solved` lets the caller apply that override. */
+int cube_expand(int cube_size, const uint8_t* states, int64_t n, uint8_t* children, void* child_onehot,
+                void* parent_onehot, int dtype, uint8_t* solved, float* reward, uint64_t* counters,
+                void* stream);
+
+/* state_to_sim_state (cube_env.py:154-175 + py222 getStickers): one-hot [n, 7, 21] of
+ * `dtype` -> sticker rows [n, 24].  2x2x2 only: for cube_size 3 the reference raises
+ * NotImplementedError (cube_env.py:171-172) and this returns CUBE_ERR_SIZE. */
+int cube_decode(int cube_size, const void* onehot, int dtype, int64_t n, uint8_t* states_out, void* stream);
+
+/* counters[2] += number of entries of actions[0..count) that are >= A. */
+int cube_validate_actions(int cube_size, const uint8_t* actions, int64_t count, uint64_t* counters,
+                          void* stream);
+
+/* ---- host-buffer front end (end-to-end path) ------------------------------------------
+ * For callers that hold NumPy / host arrays, as every caller of the reference does
+ * (train.py:155, :186; test.py:123).  A pipeline handle owns a few stages of device
+ * buffers and streams; cube_pipeline_scramble_host cuts the batch into chunks and
+ * overlaps the host->device copy of the moves, the fused scramble kernel and the
+ * device->host copy of the results.  It blocks until the host buffers are filled.
+ * Page-locked host buffers are needed for the overlap (pageable ones still work).
+ * The handle is bound to the device that was current at creation. */
+typedef struct cube_pipeline cube_pipeline_t;
+
+int cube_pipeline_create(int cube_size, int depth, int64_t chunk_instances, int n_stages /* 1..4 */,
+                         cube_pipeline_t** out);
+int cube_pipeline_destroy(cube_pipeline_t* p);
+
+/*   moves_host      [n, depth] uint8   in
+ *   states_out_host [n, S]     uint8   out
+ *   solved_host     [n]        uint8   out or NULL
+ *   reward_host     [n]        float32 out or NULL
+ *   solved_count               int64   out or NULL  (number of solved final states) */
+int cube_pipeline_scramble_host(cube_pipeline_t* p, const uint8_t* moves_host, int64_t n,
+                                uint8_t* states_out_host, uint8_t* solved_host, float* reward_host,
+                                int64_t* solved_count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CUBE_B200_H */

@@ -1,0 +1,140 @@
+// extern "C" boundary of libcube_b200.so: argument checks, then the launchers.
+// See include/cube_b200.h for the contract of every entry point.
+#include <cstdio>
+#include <cuda_runtime.h>
+
+#include "../../include/cube_b200.h"
+#include "cube_common.cuh"
+#include "cube_kernels.h"
+
+namespace {
+
+thread_local char t_err[256] = "";
+
+int fail(int code, const char* what)
+{
+    if (code > 0)
+        snprintf(t_err, sizeof(t_err), "%s: CUDA error %d (%s)", what, code, cudaGetErrorString((cudaError_t)code));
+    else
+        snprintf(t_err, sizeof(t_err), "%s: %s", what,
+                 code == CUBE_ERR_SIZE ? "cube_size must be 2 or 3"
+                 : code == CUBE_ERR_ARG ? "bad argument (null pointer, negative count or unknown dtype)"
+                 : code == CUBE_ERR_ALIGN ? "device pointers must be 16-byte aligned"
+                 : code == CUBE_ERR_ACTION ? "action index out of range" : "error");
+    return code;
+}
+
+inline bool misaligned(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) != 0; }
+
+#define CUBE_CHECK_SIZE(fn) if (cube_size != 2 && cube_size != 3) return fail(CUBE_ERR_SIZE, fn)
+#define CUBE_DONE(fn, rc) do { int rc_ = (rc); return rc_ ? fail(rc_, fn) : 0; } while (0)
+
+}  // namespace
+
+namespace cube {
+
+int sm_count()
+{
+    static int cached_dev = -1, cached = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev != cached_dev) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v < 1) v = 148;
+        cached = v;
+        cached_dev = dev;
+    }
+    return cached;
+}
+
+}  // namespace cube
+
+extern "C" {
+
+int cube_abi_version(void) { return CUBE_ABI_VERSION; }
+
+const char* cube_last_error(void) { return t_err; }
+
+int cube_sm_count(void) { return cube::sm_count(); }
+
+int cube_scramble(int cube_size, const uint8_t* moves, int64_t n, int depth, uint8_t* states_out,
+                  uint8_t* solved, float* reward, uint64_t* counters, void* stream)
+{
+    CUBE_CHECK_SIZE("cube_scramble");
+    if (n < 0 || depth < 0 || (n > 0 && (!states_out || (depth > 0 && !moves)))) return fail(CUBE_ERR_ARG, "cube_scramble");
+    if (misaligned(moves) || misaligned(states_out)) return fail(CUBE_ERR_ALIGN, "cube_scramble");
+    CUBE_DONE("cube_scramble", cube::launch_scramble(cube_size, moves, n, depth, states_out, solved, reward,
+                                                     (unsigned long long*)counters, (cudaStream_t)stream));
+}
+
+int cube_step(int cube_size, uint8_t* states, const uint8_t* actions, int64_t n, uint8_t* solved,
+              float* reward, uint64_t* counters, void* stream)
+{
+    CUBE_CHECK_SIZE("cube_step");
+    if (n < 0 || (n > 0 && (!states || !actions))) return fail(CUBE_ERR_ARG, "cube_step");
+    if (misaligned(states)) return fail(CUBE_ERR_ALIGN, "cube_step");
+    CUBE_DONE("cube_step", cube::launch_walk(cube_size, states, actions, n, 1, states, solved, reward,
+                                             (unsigned long long*)counters, (cudaStream_t)stream));
+}
+
+int cube_walk(int cube_size, const uint8_t* states_in, const uint8_t* moves, int64_t n, int depth,
+              uint8_t* states_out, uint8_t* solved, float* reward, uint64_t* counters, void* stream)
+{
+    CUBE_CHECK_SIZE("cube_walk");
+    if (n < 0 || depth < 0 || (n > 0 && (!states_in || !states_out || (depth > 0 && !moves))))
+        return fail(CUBE_ERR_ARG, "cube_walk");
+    if (misaligned(states_in) || misaligned(states_out)) return fail(CUBE_ERR_ALIGN, "cube_walk");
+    CUBE_DONE("cube_walk", cube::launch_walk(cube_size, states_in, moves, n, depth, states_out, solved, reward,
+                                             (unsigned long long*)counters, (cudaStream_t)stream));
+}
+
+int cube_solved(int cube_size, const uint8_t* states, int64_t n, uint8_t* solved, float* reward,
+                uint64_t* counters, void* stream)
+{
+    CUBE_CHECK_SIZE("cube_solved");
+    if (n < 0 || (n > 0 && !states)) return fail(CUBE_ERR_ARG, "cube_solved");
+    if (misaligned(states)) return fail(CUBE_ERR_ALIGN, "cube_solved");
+    CUBE_DONE("cube_solved", cube::launch_solved(cube_size, states, n, solved, reward,
+                                                 (unsigned long long*)counters, (cudaStream_t)stream));
+}
+
+int cube_encode(int cube_size, const uint8_t* states, int64_t n, void* onehot, int dtype, void* stream)
+{
+    CUBE_CHECK_SIZE("cube_encode");
+    if (n < 0 || dtype < 0 || dtype > 2 || (n > 0 && (!states || !onehot))) return fail(CUBE_ERR_ARG, "cube_encode");
+    if (misaligned(states) || misaligned(onehot)) return fail(CUBE_ERR_ALIGN, "cube_encode");
+    CUBE_DONE("cube_encode", cube::launch_expand(cube_size, states, n, nullptr, nullptr, onehot, dtype, nullptr,
+                                                 nullptr, nullptr, (cudaStream_t)stream));
+}
+
+int cube_expand(int cube_size, const uint8_t* states, int64_t n, uint8_t* children, void* child_onehot,
+                void* parent_onehot, int dtype, uint8_t* solved, float* reward, uint64_t* counters,
+                void* stream)
+{
+    CUBE_CHECK_SIZE("cube_expand");
+    if (n < 0 || dtype < 0 || dtype > 2 || (n > 0 && !states)) return fail(CUBE_ERR_ARG, "cube_expand");
+    if (misaligned(states) || misaligned(children) || misaligned(child_onehot) || misaligned(parent_onehot))
+        return fail(CUBE_ERR_ALIGN, "cube_expand");
+    CUBE_DONE("cube_expand", cube::launch_expand(cube_size, states, n, children, child_onehot, parent_onehot, dtype,
+                                                 solved, reward, (unsigned long long*)counters,
+                                                 (cudaStream_t)stream));
+}
+
+int cube_decode(int cube_size, const void* onehot, int dtype, int64_t n, uint8_t* states_out, void* stream)
+{
+    CUBE_CHECK_SIZE("cube_decode");
+    if (cube_size == 3) return fail(CUBE_ERR_SIZE, "cube_decode (3x3x3 is NotImplemented in the reference too)");
+    if (n < 0 || dtype < 0 || dtype > 2 || (n > 0 && (!onehot || !states_out))) return fail(CUBE_ERR_ARG, "cube_decode");
+    CUBE_DONE("cube_decode", cube::launch_decode2(onehot, dtype, n, states_out, (cudaStream_t)stream));
+}
+
+int cube_validate_actions(int cube_size, const uint8_t* actions, int64_t count, uint64_t* counters, void* stream)
+{
+    CUBE_CHECK_SIZE("cube_validate_actions");
+    if (count < 0 || !counters || (count > 0 && !actions)) return fail(CUBE_ERR_ARG, "cube_validate_actions");
+    if (misaligned(actions)) return fail(CUBE_ERR_ALIGN, "cube_validate_actions");
+    CUBE_DONE("cube_validate_actions", cube::launch_validate(cube_size, actions, count,
+                                                             (unsigned long long*)counters, (cudaStream_t)stream));
+}
+
+}  // extern "C"

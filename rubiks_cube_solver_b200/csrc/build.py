@@ -1,0 +1,43 @@
+"""Compile libcube_b200.so for sm_100a with nvcc (in-tree, so it travels to the GPU box).
+
+    python rubiks_cube_solver_b200/csrc/build.py [--force] [--verbose]
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.dirname(HERE)
+LIB = os.path.join(PKG, "libcube_b200.so")
+SOURCES = ["scramble.cu", "walk.cu", "expand.cu", "decode.cu", "pipeline.cu", "abi.cu"]
+HEADERS = ["cube_common.cuh", "cube_threads.cuh", "cube_tables.cuh", "cube_kernels.h", os.path.join("..", "..", "include", "cube_b200.h")]
+NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+
+def nvcc():
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
+            return cand
+    return "nvcc"
+
+
+def stale():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(os.path.join(HERE, f)) > t
+               for f in SOURCES + HEADERS if os.path.exists(os.path.join(HERE, f)))
+
+
+def build(force=False, verbose=False):
+    srcs = [s for s in SOURCES if os.path.exists(os.path.join(HERE, s))]
+    if not force and not stale():
+        return LIB
+    cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + srcs
+    subprocess.check_call(cmd, cwd=HERE)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

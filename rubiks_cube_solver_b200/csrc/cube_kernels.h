@@ -1,0 +1,36 @@
+// Internal launchers behind the C ABI (include/cube_b200.h).  All pointers are
+// device pointers, already validated by abi.cu; every launcher returns 0 or a
+// cudaError_t and never synchronises.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+// counters layout (uint64[4], device): [0] += solved outputs, [1] += outputs written,
+// [2] += out-of-range actions seen by cube_validate_actions, [3] reserved
+namespace cube {
+
+int launch_scramble(int size, const uint8_t* moves, long long n, int depth, uint8_t* states_out,
+                    uint8_t* solved, float* reward, unsigned long long* counters, cudaStream_t stream);
+
+// depth moves applied to resident sticker rows (depth = 1: the reference's step)
+int launch_walk(int size, const uint8_t* states_in, const uint8_t* moves, long long n, int depth,
+                uint8_t* states_out, uint8_t* solved, float* reward, unsigned long long* counters,
+                cudaStream_t stream);
+
+int launch_solved(int size, const uint8_t* states, long long n, uint8_t* solved, float* reward,
+                  unsigned long long* counters, cudaStream_t stream);
+
+// dtype: 0 = bf16, 1 = f32, 2 = u8.  Any of children / child_onehot / parent_onehot / solved /
+// reward may be null.
+int launch_expand(int size, const uint8_t* states, long long n, uint8_t* children, void* child_onehot,
+                  void* parent_onehot, int dtype, uint8_t* solved, float* reward,
+                  unsigned long long* counters, cudaStream_t stream);
+
+int launch_validate(int size, const uint8_t* actions, long long count, unsigned long long* counters,
+                    cudaStream_t stream);
+
+int launch_decode2(const void* onehot, int dtype, long long n, uint8_t* out, cudaStream_t stream);
+
+int sm_count();
+
+}  // namespace cube

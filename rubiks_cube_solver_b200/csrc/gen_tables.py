@@ -1,0 +1,430 @@
+"""Generate csrc/cube_tables.cuh: every constant table the sm_100a kernels use.
+
+    python rubiks_cube_solver_b200/csrc/gen_tables.py            # rewrite the header
+    python rubiks_cube_solver_b200/csrc/gen_tables.py --check    # verify it is current + self-test
+
+The header is committed; build() only compiles it.  This script is product code
+and deliberately does NOT import ``oracle/`` -- it restates the reference's
+constants independently (the tests then compare the two restatements and the
+reference dump in tests/golden/reference_tables.npz):
+
+* face turns            gym-cube/gym_cube/envs/assets/py333.py:46-138 (``moveDefs``),
+                        action order cube_env.py:24-28
+* one-hot hash tables   py333.py:140-198 (``corner_pieceDefs`` .. ``edge_pieceInds``), as
+                        shipped, including the mirrored corner row 6 and the zero-default
+                        holes of ``corner_pieceInds``
+* 2x2x2                 the un-vendored assets/py222.py (MeepMoop/py222), SURVEY.md Appendix A
+
+Internal cubie model (used only by the fused scramble kernel; never visible at
+the boundary).  A cube reached from solved is tracked as 8 corner bytes
+``piece | twist_sum << 3`` and 12 edge bytes ``piece | flip << 4``.  A face turn m
+is  ``new[q] = old[src_m[q]] + delta_m[q]``  which is one PRMT (byte permute) per
+output register plus one add / xor, with the per-move selector words fetched
+from shared memory -- no branch on the move, so lanes holding different moves
+do not diverge.  Edge slots are ordered F/B-layer-aware so that only U and D
+turns flip edges:
+
+    slot order   corners: the 8 rows of corner_pieceDefs (row 6 un-mirrored)
+                 edges  : reg0 = U layer (UB UL UF UR), reg1 = middle layer
+                          (FL FR BR BL), reg2 = D layer (DB DL DF DR)
+    edge reference sticker: the F/B sticker for the 8 edges touching F or B,
+                 the U/D sticker for UL UR DL DR  ->  F, B, R, L never flip.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+OUT = os.path.join(HERE, "cube_tables.cuh")
+
+ACTIONS_3 = ["U", "U'", "F", "F'", "R", "R'", "D", "D'", "B", "B'", "L", "L'"]
+
+# clockwise quarter turns as sticker 4-cycles (a b c d): new[a] = old[b], new[b] = old[c], ...
+CW = {
+    "U": "0 6 8 2 | 1 3 7 5 | 9 45 36 18 | 10 46 37 19 | 11 47 38 20",
+    "F": "6 44 29 9 | 7 41 28 12 | 8 38 27 15 | 18 24 26 20 | 19 21 25 23",
+    "R": "2 20 29 51 | 5 23 32 48 | 8 26 35 45 | 9 15 17 11 | 10 12 16 14",
+    "D": "15 24 42 51 | 16 25 43 52 | 17 26 44 53 | 27 33 35 29 | 28 30 34 32",
+    "B": "0 11 35 42 | 1 14 34 39 | 2 17 33 36 | 45 51 53 47 | 46 48 52 50",
+    "L": "0 53 27 18 | 3 50 30 21 | 6 47 33 24 | 36 42 44 38 | 37 39 43 41",
+}
+
+
+def cycles_of(name):
+    return [[int(x) for x in c.split()] for c in CW[name].split("|")]
+
+
+def gather_row(n, cycles, inverse=False):
+    row = list(range(n))
+    for c in cycles:
+        for k, a in enumerate(c):
+            if inverse:
+                row[c[(k + 1) % 4]] = a
+            else:
+                row[a] = c[(k + 1) % 4]
+    return row
+
+
+MOVES_3 = []          # [12][54] gather rows
+CYCLES_3 = []         # [12][5][4] : new[c[k]] = old[c[k+1]]
+for _name in ACTIONS_3[0::2]:
+    _cyc = cycles_of(_name)
+    MOVES_3.append(gather_row(54, _cyc))
+    CYCLES_3.append(_cyc)
+    MOVES_3.append(gather_row(54, _cyc, inverse=True))
+    CYCLES_3.append([[c[0], c[3], c[2], c[1]] for c in _cyc])
+MOVES_3 = np.array(MOVES_3)
+
+# 2x2x2 sticker 4f+k <-> 3x3x3 corner sticker 9f+(0,2,6,8)[k]
+TO3 = [9 * (i // 4) + (0, 2, 6, 8)[i % 4] for i in range(24)]
+TO2 = {s3: i for i, s3 in enumerate(TO3)}
+MOVES_2 = np.array([[TO2[MOVES_3[a][s3]] for s3 in TO3] for a in range(6)])
+CYCLES_2 = [[[TO2[s] for s in c] for c in CYCLES_3[a] if c[0] in TO2] for a in range(6)]
+
+# ---- reference one-hot tables (as shipped) ---------------------------------
+CORNER_DEFS_REF = [[0, 47, 36], [6, 38, 18], [8, 20, 9], [2, 11, 45],
+                   [33, 42, 53], [27, 24, 44], [29, 26, 15], [35, 51, 17]]
+EDGE_DEFS_REF = [[1, 46], [3, 37], [7, 19], [5, 10], [34, 52], [30, 43],
+                 [28, 25], [32, 16], [21, 41], [23, 12], [48, 14], [50, 39]]
+CORNER_HASHES_REF = [(50, 54, 13), (28, 8, 42), (14, 5, 12), (52, 11, 15),
+                     (61, 44, 51), (47, 30, 40), (17, 35, 18), (23, 56, 21)]
+PIECE_DEFS_2 = [[0, 21, 16], [2, 17, 8], [3, 9, 4], [1, 5, 20],
+                [12, 10, 19], [13, 6, 11], [15, 22, 7]]
+
+CORNER_COL_3 = [0] * 128        # hash -> 3*piece+ori (0 where the shipped table has a hole)
+for _p, _hs in enumerate(CORNER_HASHES_REF):
+    for _o, _h in enumerate(_hs):
+        CORNER_COL_3[_h] = 3 * _p + _o
+EDGE_COL_3 = [0] * 128          # hash -> 2*piece+ori
+for _p, (_s0, _s1) in enumerate(EDGE_DEFS_REF):
+    _a, _b = _s0 // 9, _s1 // 9
+    EDGE_COL_3[_a + 10 * _b] = 2 * _p
+    EDGE_COL_3[_b + 10 * _a] = 2 * _p + 1
+PIECE_CODE_2 = [0] * 128        # hash -> cubelet | ori << 4
+for _p in range(7):
+    _c = [s // 4 for s in PIECE_DEFS_2[_p]]
+    for _o in range(3):
+        _r = _c[-_o:] + _c[:-_o] if _o else _c          # np.roll(c, o)
+        PIECE_CODE_2[_r[0] + 2 * _r[1] + 10 * _r[2]] = _p | (_o << 4)
+
+# ---- internal cubie model ---------------------------------------------------
+CORNER_SLOTS_3 = [list(r) for r in CORNER_DEFS_REF]
+CORNER_SLOTS_3[6] = [29, 15, 26]                       # un-mirrored: same chirality as the rest
+EDGE_SLOTS_3 = [[46, 1], [3, 37], [19, 7], [5, 10],    # UB UL UF UR   (reference sticker first)
+                [21, 41], [23, 12], [48, 14], [50, 39],  # FL FR BR BL
+                [52, 34], [30, 43], [25, 28], [32, 16]]  # DB DL DF DR
+CORNER_SLOTS_2 = [[TO2[s] for s in r] for r in CORNER_SLOTS_3]   # slot 4 = the fixed DBL cubie
+
+
+def cubie_action(moves, slots):
+    """src[m][q], rot[m][q] with new[q] = old[src] twisted by rot."""
+    where = {}
+    for q, st in enumerate(slots):
+        for k, s in enumerate(st):
+            where[s] = (q, k)
+    n = len(slots[0])
+    src = np.zeros((len(moves), len(slots)), dtype=int)
+    rot = np.zeros((len(moves), len(slots)), dtype=int)
+    for m, row in enumerate(moves):
+        for q, st in enumerate(slots):
+            q2, k2 = where[row[st[0]]]
+            for k, s in enumerate(st):
+                assert where[row[s]] == (q2, (k + k2) % n), "slot stickers must share chirality"
+            src[m][q], rot[m][q] = q2, k2
+    return src, rot
+
+
+C_SRC_3, C_ROT_3 = cubie_action(MOVES_3, CORNER_SLOTS_3)
+E_SRC_3, E_ROT_3 = cubie_action(MOVES_3, EDGE_SLOTS_3)
+C_SRC_2, C_ROT_2 = cubie_action(MOVES_2, CORNER_SLOTS_2)
+assert all(E_ROT_3[m].sum() == 0 for m in (2, 3, 4, 5, 8, 9, 10, 11)), "only U/D may flip edges"
+assert all(E_ROT_3[m][4:8].sum() == 0 for m in range(12)), "middle-layer edges never flip"
+
+N_MOVE_ROWS = 16          # rows 0..A-1 = moves, the rest = identity (row 12 doubles as "no-op")
+W3 = 10                   # words per 3x3x3 move
+W2 = 4                    # words per 2x2x2 move
+
+
+def _sel(nibbles):
+    v = 0
+    for i, nb in enumerate(nibbles):
+        assert 0 <= nb < 8
+        v |= nb << (4 * i)
+    return v
+
+
+def _bytes(vals):
+    v = 0
+    for i, b in enumerate(vals):
+        assert 0 <= b < 256
+        v |= b << (8 * i)
+    return v
+
+
+def move_words_3(m):
+    """10 words: selC0 selC1 dC0 dC1 selE0 selE2 selEt selE1 fE0 fE2 (identity when m >= 12)."""
+    if m >= 12:
+        return [0x3210, 0x7654, 0, 0, 0x3210, 0x3210, 0x3210, 0x3210, 0, 0]
+    cs, cr, es, er = C_SRC_3[m], C_ROT_3[m], E_SRC_3[m], E_ROT_3[m]
+    selc0 = _sel([cs[q] for q in range(0, 4)])                       # prmt(c0, c1, .)
+    selc1 = _sel([cs[q] for q in range(4, 8)])
+    dc0 = _bytes([cr[q] << 3 for q in range(0, 4)])
+    dc1 = _bytes([cr[q] << 3 for q in range(4, 8)])
+    s0, s2, st, s1 = [], [], [], []
+    for q in range(0, 4):                                            # out0 = prmt(e0, e1, s0)
+        s = es[q]
+        assert s < 8
+        s0.append(s if s < 4 else 4 + (s - 4))
+    for q in range(8, 12):                                           # out2 = prmt(e2, e1, s2)
+        s = es[q]
+        assert s >= 4
+        s2.append(s - 8 if s >= 8 else 4 + (s - 4))
+    for i, q in enumerate(range(4, 8)):                              # t = prmt(e0, e2, st); out1 = prmt(e1, t, s1)
+        s = es[q]
+        if 4 <= s < 8:
+            st.append(0)
+            s1.append(s - 4)
+        else:
+            st.append(s if s < 4 else 4 + (s - 8))
+            s1.append(4 + i)
+    f0 = _bytes([er[q] << 4 for q in range(0, 4)])
+    f2 = _bytes([er[q] << 4 for q in range(8, 12)])
+    return [selc0, selc1, dc0, dc1, _sel(s0), _sel(s2), _sel(st), _sel(s1), f0, f2]
+
+
+def move_words_2(m):
+    if m >= 6:
+        return [0x3210, 0x7654, 0, 0]
+    cs, cr = C_SRC_2[m], C_ROT_2[m]
+    return [_sel([cs[q] for q in range(0, 4)]), _sel([cs[q] for q in range(4, 8)]),
+            _bytes([cr[q] << 3 for q in range(0, 4)]), _bytes([cr[q] << 3 for q in range(4, 8)])]
+
+
+def colour_lut(slots, per_face, n_or):
+    """lut[piece | ori << sh] = colours seen at slot sticker positions k=0.. (one byte each).
+    Position k of the slot shows home sticker (k + ori) % n of the piece."""
+    sh = 3 if n_or == 3 else 4
+    lut = [0] * 32
+    for p, st in enumerate(slots):
+        for o in range(n_or):
+            lut[p | (o << sh)] = _bytes([st[(k + o) % n_or] // per_face for k in range(n_or)])
+    return lut
+
+
+C_LUT_3 = colour_lut(CORNER_SLOTS_3, 9, 3)
+E_LUT_3 = colour_lut(EDGE_SLOTS_3, 9, 2)
+C_LUT_2 = colour_lut(CORNER_SLOTS_2, 4, 3)
+
+
+def sticker_sources(slots_list, n_stickers, centres):
+    """For every sticker position: (slot_register_index, byte) or a constant colour.
+    Register index: 0..len-1 in the order slots are listed."""
+    src = [None] * n_stickers
+    idx = 0
+    for slots in slots_list:
+        for st in slots:
+            for k, s in enumerate(st):
+                src[s] = (idx, k)
+            idx += 1
+    for s, col in centres.items():
+        src[s] = ("const", col)
+    assert all(v is not None for v in src)
+    return src
+
+
+# ---- sticker-level tables for the walk (step) and expand kernels ------------
+def cycle_words(cycles):
+    """5 (3x3x3) / 3 (2x2x2) words per move, bytes (a,b,c,d): new[a]=old[b] ... new[d]=old[a]."""
+    return [[_bytes(c) for c in mv] for mv in cycles]
+
+
+def hash_sources_3():
+    """[13][20] words: bytes = parent sticker positions feeding slot's hash under action a
+    (a = 12: identity).  byte3 = 1 for edge slots."""
+    out = []
+    for a in range(13):
+        row = MOVES_3[a] if a < 12 else list(range(54))
+        words = []
+        for q in range(8):
+            d = CORNER_DEFS_REF[q]
+            words.append(_bytes([row[d[0]], row[d[1]], row[d[2]], 0]))
+        for q in range(12):
+            d = EDGE_DEFS_REF[q]
+            words.append(_bytes([row[d[0]], row[d[1]], row[d[1]], 1]))
+        out.append(words)
+    return out
+
+
+def hash_sources_2():
+    out = []
+    for a in range(7):
+        row = MOVES_2[a] if a < 6 else list(range(24))
+        out.append([_bytes([row[d[0]], row[d[1]], row[d[2]], 0]) for d in PIECE_DEFS_2])
+    return out
+
+
+def assemble_fn(name, src, n_words):
+    """Straight-line code: out word j = stickers 4j..4j+3, each a byte of L[slot] or a constant."""
+    lines = ["CUBE_HD void %s(const uint32_t* L, uint32_t* w)\n{\n" % name]
+    for j in range(n_words):
+        ops = []
+        for b in range(4):
+            s_ = 4 * j + b
+            if s_ >= len(src) or src[s_][0] == "const":
+                col = 0 if s_ >= len(src) else src[s_][1]
+                ops.append(("0x%02xu" % col, 0))
+            else:
+                ops.append(("L[%d]" % src[s_][0], src[s_][1]))
+        lo = "cube_prmt(%s, %s, 0x%04xu)" % (ops[0][0], ops[1][0], 0x4400 | ops[0][1] | ((4 + ops[1][1]) << 4))
+        hi = "cube_prmt(%s, %s, 0x%04xu)" % (ops[2][0], ops[3][0], 0x4400 | ops[2][1] | ((4 + ops[3][1]) << 4))
+        lines.append("    w[%d] = cube_prmt(%s, %s, 0x5410u);\n" % (j, lo, hi))
+    lines.append("}\n\n")
+    return "".join(lines)
+
+
+def _c_array(ctype, name, values, per_line=8, fmt="0x%08xu"):
+    flat = list(values)
+    lines = []
+    for i in range(0, len(flat), per_line):
+        lines.append("    " + ", ".join(fmt % v for v in flat[i:i + per_line]))
+    return "CUBE_TABLE %s %s[%d] = {\n%s\n};\n" % (ctype, name, len(flat), ",\n".join(lines))
+
+
+def render():
+    o = []
+    o.append("// GENERATED by csrc/gen_tables.py -- do not edit; run the script instead.\n"
+             "// Constant tables of the B200 cube kernels (reference citations are in gen_tables.py).\n"
+             "#pragma once\n#include <cstdint>\n\n"
+             "// device-resident in .cu translation units, plain host arrays elsewhere (test emulation)\n"
+             "#if defined(__CUDACC__)\n#define CUBE_TABLE static __device__ const\n#else\n"
+             "#define CUBE_TABLE static const\n#endif\n\n")
+    o.append("#define CUBE_MOVE_ROWS %d   // table rows per word: 0..A-1 moves, rest identity\n" % N_MOVE_ROWS)
+    o.append("#define CUBE_NOOP_MOVE 12   // identity row used for padded / rejected moves\n")
+    o.append("#define CUBE_W3 %d\n#define CUBE_W2 %d\n\n" % (W3, W2))
+    # fused-scramble move words, layout [word][row]
+    t3 = [[move_words_3(m)[w] for m in range(N_MOVE_ROWS)] for w in range(W3)]
+    t2 = [[move_words_2(m)[w] for m in range(N_MOVE_ROWS)] for w in range(W2)]
+    o.append("// [word][move] : selC0 selC1 dC0 dC1 selE0 selE2 selEt selE1 fE0 fE2\n")
+    o.append(_c_array("uint32_t", "kMoveWords3", [v for r in t3 for v in r]))
+    o.append("// [word][move] : selC0 selC1 dC0 dC1\n")
+    o.append(_c_array("uint32_t", "kMoveWords2", [v for r in t2 for v in r]))
+    o.append("// colour LUTs: index = cubie byte (piece | ori << 3 corners, piece | flip << 4 edges)\n")
+    o.append(_c_array("uint32_t", "kCornerColour3", C_LUT_3))
+    o.append(_c_array("uint32_t", "kEdgeColour3", E_LUT_3))
+    o.append(_c_array("uint32_t", "kCornerColour2", C_LUT_2))
+    # sticker sources for the expansion (compile-time use): encoded as reg<<2|byte, or 0x80|colour
+    def enc(src):
+        return [(0x80 | v[1]) if v[0] == "const" else (v[0] << 2 | v[1]) for v in src]
+    src3 = sticker_sources([CORNER_SLOTS_3, EDGE_SLOTS_3], 54, {4 + 9 * f: f for f in range(6)})
+    src2 = sticker_sources([CORNER_SLOTS_2], 24, {})
+    o.append("// where each output sticker comes from: slot << 2 | k, or 0x80 | colour (centres)\n")
+    o.append("CUBE_TABLE uint8_t kStickerSrc3[56] = {%s, 0x80, 0x80};\n"
+             % ", ".join("0x%02x" % v for v in enc(src3)))
+    o.append("CUBE_TABLE uint8_t kStickerSrc2[24] = {%s};\n\n" % ", ".join("0x%02x" % v for v in enc(src2)))
+    o.append("// sticker rows from per-slot colour words L[slot] (bytes k = 0..2), generated straight-line\n")
+    o.append("#ifdef CUBE_HD\n")
+    o.append(assemble_fn("cube_assemble3", src3, 14))
+    o.append(assemble_fn("cube_assemble2", src2, 6))
+    o.append("#endif\n\n")
+    # sticker-level tables
+    cyc3 = cycle_words(CYCLES_3)
+    cyc2 = cycle_words(CYCLES_2)
+    o.append("// sticker 4-cycles per move, bytes (a,b,c,d): new[a]=old[b], new[b]=old[c], new[c]=old[d], new[d]=old[a]\n")
+    o.append("// layout [cycle][move row] (rows >= A hold the trivial cycle 0,0,0,0)\n")
+    o.append(_c_array("uint32_t", "kCycles3", [(cyc3[m][c] if m < 12 else 0) for c in range(5) for m in range(N_MOVE_ROWS)]))
+    o.append(_c_array("uint32_t", "kCycles2", [(cyc2[m][c] if m < 6 else 0) for c in range(3) for m in range(N_MOVE_ROWS)]))
+    o.append("// full gather rows new[i] = old[row[i]] ([13][56] / [7][24]; last row = identity)\n")
+    g3 = [list(MOVES_3[a]) + [54, 55] for a in range(12)] + [list(range(56))]
+    g2 = [list(MOVES_2[a]) for a in range(6)] + [list(range(24))]
+    o.append(_c_array("uint8_t", "kGather3", [v for r in g3 for v in r], per_line=28, fmt="%d"))
+    o.append(_c_array("uint8_t", "kGather2", [v for r in g2 for v in r], per_line=24, fmt="%d"))
+    o.append("// one-hot hash sources: [action (last = identity)][slot] -> parent sticker positions\n")
+    o.append(_c_array("uint32_t", "kHashSrc3", [v for r in hash_sources_3() for v in r]))
+    o.append(_c_array("uint32_t", "kHashSrc2", [v for r in hash_sources_2() for v in r]))
+    o.append("// hash -> one-hot column (3x3x3, holes = 0 as shipped) / cubelet | ori << 4 (2x2x2)\n")
+    o.append(_c_array("uint8_t", "kCornerCol3", CORNER_COL_3, per_line=32, fmt="%d"))
+    o.append(_c_array("uint8_t", "kEdgeCol3", EDGE_COL_3, per_line=32, fmt="%d"))
+    o.append(_c_array("uint8_t", "kPieceCode2", PIECE_CODE_2, per_line=32, fmt="%d"))
+    o.append("// 2x2x2 decode (py222 getStickers): sticker positions of each slot, home colours of each cubelet\n")
+    o.append(_c_array("uint8_t", "kPieceDefs2", [v for r in PIECE_DEFS_2 for v in r] + [14, 18, 23], per_line=24, fmt="%d"))
+    o.append(_c_array("uint8_t", "kHomeColour2", [v // 4 for r in PIECE_DEFS_2 for v in r] + [3, 4, 5], per_line=24, fmt="%d"))
+    return "".join(o)
+
+
+# ---- self-test: emulate the register algorithm against sticker-level gathers --
+def prmt(x, y, s):
+    b = [(x >> (8 * i)) & 255 for i in range(4)] + [(y >> (8 * i)) & 255 for i in range(4)]
+    return sum(b[(s >> (4 * i)) & 7] << (8 * i) for i in range(4))
+
+
+def emulate_3(seq):
+    c0, c1, e0, e1, e2 = 0x03020100, 0x07060504, 0x03020100, 0x07060504, 0x0b0a0908
+    for m in seq:
+        w = move_words_3(m)
+        n0, n1 = prmt(c0, c1, w[0]) + w[2], prmt(c0, c1, w[1]) + w[3]
+        t = prmt(e0, e2, w[6])
+        m0, m2, m1 = prmt(e0, e1, w[4]) ^ w[8], prmt(e2, e1, w[5]) ^ w[9], prmt(e1, t, w[7])
+        c0, c1, e0, e1, e2 = n0, n1, m0, m1, m2
+    regs = [(c0 >> 8 * i) & 255 for i in range(4)] + [(c1 >> 8 * i) & 255 for i in range(4)]
+    regs = [(b & 7) | (((b >> 3) % 3) << 3) for b in regs]
+    regs += [(r >> 8 * i) & 255 for r in (e0, e1, e2) for i in range(4)]
+    src = sticker_sources([CORNER_SLOTS_3, EDGE_SLOTS_3], 54, {4 + 9 * f: f for f in range(6)})
+    out = []
+    for s in range(54):
+        if src[s][0] == "const":
+            out.append(src[s][1])
+        else:
+            slot, k = src[s]
+            lut = C_LUT_3 if slot < 8 else E_LUT_3
+            out.append((lut[regs[slot]] >> (8 * k)) & 255)
+    return out
+
+
+def emulate_2(seq):
+    c0, c1 = 0x03020100, 0x07060504
+    for m in seq:
+        w = move_words_2(m)
+        c0, c1 = prmt(c0, c1, w[0]) + w[2], prmt(c0, c1, w[1]) + w[3]
+    regs = [(c0 >> 8 * i) & 255 for i in range(4)] + [(c1 >> 8 * i) & 255 for i in range(4)]
+    regs = [(b & 7) | (((b >> 3) % 3) << 3) for b in regs]
+    src = sticker_sources([CORNER_SLOTS_2], 24, {})
+    return [(C_LUT_2[regs[src[s][0]]] >> (8 * src[s][1])) & 255 for s in range(24)]
+
+
+def selftest(n=300, depth=14):
+    rng = np.random.RandomState(0)
+    for _ in range(n):
+        seq = rng.randint(12, size=depth)
+        s = np.repeat(np.arange(6), 9)
+        for m in seq:
+            s = s[MOVES_3[m]]
+        assert list(s) == emulate_3(seq), "3x3x3 cubie model disagrees with sticker gathers"
+        seq = rng.randint(6, size=depth)
+        s = np.repeat(np.arange(6), 4)
+        for m in seq:
+            s = s[MOVES_2[m]]
+        assert list(s) == emulate_2(seq), "2x2x2 cubie model disagrees with sticker gathers"
+    # cycles reproduce the gather rows
+    for moves, cycles, n_s in ((MOVES_3, CYCLES_3, 54), (MOVES_2, CYCLES_2, 24)):
+        for m in range(len(moves)):
+            row = list(range(n_s))
+            for c in cycles[m]:
+                for k in range(4):
+                    row[c[k]] = c[(k + 1) % 4]
+            assert row == list(moves[m])
+    return True
+
+
+if __name__ == "__main__":
+    selftest()
+    text = render()
+    if "--check" in sys.argv:
+        with open(OUT) as f:
+            if f.read() != text:
+                sys.exit("cube_tables.cuh is stale: run gen_tables.py")
+        print("cube_tables.cuh is current; self-test passed")
+    else:
+        with open(OUT, "w") as f:
+            f.write(text)
+        print("wrote", OUT)

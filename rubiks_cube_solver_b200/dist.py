@@ -1,0 +1,50 @@
+"""One process per GPU; instances shard contiguously by rank and never exchange data.
+The only collective on the path is a SUM all-reduce of the int64 counters
+(solved count, instance count): rewards are +-1, so the reward total is derived
+exactly as 2*solved - count (an fp32 sum of +-1 over 64 Mi instances is not exact)."""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_total, rank, world_size):
+    """Contiguous slice [lo, hi) of rank `rank`; the first n_total % world_size ranks get one extra."""
+    base, extra = divmod(int(n_total), int(world_size))
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def init_from_env(backend=None):
+    """Initialise torch.distributed from RANK / WORLD_SIZE / MASTER_* (torchrun).  Returns
+    (rank, local_rank, world_size); world_size 1 needs no process group."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", str(rank)))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, local, world
+
+
+def reduce_counters(counters):
+    """SUM all-reduce of an int64 counter tensor across ranks (no-op for a single process)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(counters, op=dist.ReduceOp.SUM)
+    return counters
+
+
+def reward_total(counters):
+    """Exact sum of the +-1 rewards behind the counters: 2*solved - produced."""
+    return 2 * int(counters[0]) - int(counters[1])
+
+
+def max_over_ranks(value, device):
+    """MAX all-reduce of a Python float (timing: the slowest rank defines the step)."""
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())

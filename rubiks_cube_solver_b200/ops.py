@@ -1,0 +1,251 @@
+"""Batched cube operators on CUDA tensors: thin, typed wrappers over the C ABI
+(include/cube_b200.h).  PyTorch only supplies device memory and streams here.
+
+Shapes: states ``[N, S]`` uint8 (S = 24 / 54), moves ``[N, depth]`` uint8,
+one-hot ``[N, R, C]`` (7x21 / 20x24).  Every function launches asynchronously on
+the current CUDA stream of the tensors' device and returns tensors on that device.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+N_STICKERS = {2: 24, 3: 54}
+N_ACTIONS = {2: 6, 3: 12}
+STATE_DIM = {2: (7, 21), 3: (20, 24)}                      # utils.py:162-186 get_env_config
+ONEHOT_DTYPES = {torch.bfloat16: _lib.DTYPE_BF16, torch.float32: _lib.DTYPE_F32, torch.uint8: _lib.DTYPE_U8}
+
+
+def _geom(cube_size):
+    if cube_size not in (2, 3):
+        raise NotImplementedError("cube_size must be 2 or 3")   # cube_env.py:43-44
+    return N_STICKERS[cube_size], N_ACTIONS[cube_size], STATE_DIM[cube_size]
+
+
+def _require_cuda(t, name, dtype=torch.uint8):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise TypeError("%s must be a CUDA tensor (this library has no CPU path)" % name)
+    if t.dtype != dtype:
+        raise TypeError("%s must have dtype %s, got %s" % (name, dtype, t.dtype))
+    if not t.is_contiguous():
+        raise ValueError("%s must be contiguous" % name)
+    return t
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def new_counters(device):
+    """uint64[4] device counters: [solved, produced, bad actions, reserved] (kept as int64)."""
+    return torch.zeros(4, dtype=torch.int64, device=device)
+
+
+def solved_states(cube_size, n, device):
+    """initState / initState_3 (py333.py:211-218): n solved cubes."""
+    s, _, _ = _geom(cube_size)
+    per = s // 6
+    return torch.arange(6, dtype=torch.uint8, device=device).repeat_interleave(per).repeat(n, 1).contiguous()
+
+
+def validate_actions(cube_size, actions):
+    """Raise IndexError if any action index is >= A (cube_env.py:86,96).  Synchronises."""
+    _geom(cube_size)
+    actions = _require_cuda(actions, "actions")
+    counters = new_counters(actions.device)
+    with torch.cuda.device(actions.device):
+        _lib.check(_lib.load().cube_validate_actions(cube_size, _ptr(actions), actions.numel(), _ptr(counters),
+                                                     _stream(actions.device)), "cube_validate_actions")
+    bad = int(counters[2].item())
+    if bad:
+        raise IndexError("%d action indices are out of range for cube_size %d" % (bad, cube_size))
+
+
+def scramble(cube_size, moves, out=None, solved=None, reward=None, counters=None, want_flags=True):
+    """Fused scramble from solved (C ABI cube_scramble).  Returns (states, solved, reward)."""
+    s, _, _ = _geom(cube_size)
+    moves = _require_cuda(moves, "moves")
+    if moves.dim() != 2:
+        raise ValueError("moves must be [N, depth]")
+    n, depth = moves.shape
+    dev = moves.device
+    if out is None:
+        out = torch.empty((n, s), dtype=torch.uint8, device=dev)
+    _require_cuda(out, "out")
+    if want_flags:
+        if solved is None:
+            solved = torch.empty(n, dtype=torch.uint8, device=dev)
+        if reward is None:
+            reward = torch.empty(n, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().cube_scramble(cube_size, _ptr(moves), n, depth, _ptr(out), _ptr(solved), _ptr(reward),
+                                             _ptr(counters), _stream(dev)), "cube_scramble")
+    return out, solved, reward
+
+
+def step(cube_size, states, actions, solved=None, reward=None, counters=None):
+    """One transition in place (C ABI cube_step).  Returns (states, solved, reward)."""
+    s, _, _ = _geom(cube_size)
+    states = _require_cuda(states, "states")
+    actions = _require_cuda(actions, "actions")
+    n = states.shape[0]
+    if states.shape != (n, s) or actions.numel() != n:
+        raise ValueError("states must be [N, %d] and actions [N]" % s)
+    dev = states.device
+    if solved is None:
+        solved = torch.empty(n, dtype=torch.uint8, device=dev)
+    if reward is None:
+        reward = torch.empty(n, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().cube_step(cube_size, _ptr(states), _ptr(actions), n, _ptr(solved), _ptr(reward),
+                                         _ptr(counters), _stream(dev)), "cube_step")
+    return states, solved, reward
+
+
+def walk(cube_size, states, moves, out=None, solved=None, reward=None, counters=None):
+    """`depth` transitions from given states (C ABI cube_walk); `out` may be `states`."""
+    s, _, _ = _geom(cube_size)
+    states = _require_cuda(states, "states")
+    moves = _require_cuda(moves, "moves")
+    n = states.shape[0]
+    if moves.dim() == 1:
+        moves = moves.view(n, 1)
+    if states.shape != (n, s) or moves.shape[0] != n:
+        raise ValueError("states must be [N, %d] and moves [N, depth]" % s)
+    dev = states.device
+    if out is None:
+        out = torch.empty_like(states)
+    if solved is None:
+        solved = torch.empty(n, dtype=torch.uint8, device=dev)
+    if reward is None:
+        reward = torch.empty(n, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().cube_walk(cube_size, _ptr(states), _ptr(moves), n, moves.shape[1], _ptr(out),
+                                         _ptr(solved), _ptr(reward), _ptr(counters), _stream(dev)), "cube_walk")
+    return out, solved, reward
+
+
+def is_solved(cube_size, states, counters=None):
+    """Face uniformity + reward of resident states (C ABI cube_solved)."""
+    s, _, _ = _geom(cube_size)
+    states = _require_cuda(states, "states")
+    n = states.shape[0]
+    dev = states.device
+    solved = torch.empty(n, dtype=torch.uint8, device=dev)
+    reward = torch.empty(n, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().cube_solved(cube_size, _ptr(states), n, _ptr(solved), _ptr(reward), _ptr(counters),
+                                           _stream(dev)), "cube_solved")
+    return solved, reward
+
+
+def encode(cube_size, states, dtype=torch.bfloat16, out=None):
+    """One-hot network input [N, R, C] (C ABI cube_encode)."""
+    s, _, (r, c) = _geom(cube_size)
+    states = _require_cuda(states, "states")
+    n = states.shape[0]
+    dev = states.device
+    if out is None:
+        out = torch.empty((n, r, c), dtype=dtype, device=dev)
+    _require_cuda(out, "out", dtype)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().cube_encode(cube_size, _ptr(states), n, _ptr(out), ONEHOT_DTYPES[dtype], _stream(dev)),
+                   "cube_encode")
+    return out
+
+
+def expand(cube_size, states, dtype=torch.bfloat16, want_children=False, want_child_onehot=True,
+           want_parent_onehot=False, child_onehot=None, counters=None):
+    """All A children of every state (C ABI cube_expand).
+
+    Returns dict(children [N,A,S] | None, child_onehot [N,A,R,C] | None,
+    parent_onehot [N,R,C] | None, solved [N,A] uint8, reward [N,A] float32).
+    """
+    s, a, (r, c) = _geom(cube_size)
+    states = _require_cuda(states, "states")
+    n = states.shape[0]
+    dev = states.device
+    children = torch.empty((n, a, s), dtype=torch.uint8, device=dev) if want_children else None
+    if want_child_onehot and child_onehot is None:
+        child_onehot = torch.empty((n, a, r, c), dtype=dtype, device=dev)
+    if child_onehot is not None:
+        _require_cuda(child_onehot, "child_onehot", dtype)
+    parent_onehot = torch.empty((n, r, c), dtype=dtype, device=dev) if want_parent_onehot else None
+    solved = torch.empty((n, a), dtype=torch.uint8, device=dev)
+    reward = torch.empty((n, a), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().cube_expand(cube_size, _ptr(states), n, _ptr(children), _ptr(child_onehot),
+                                           _ptr(parent_onehot), ONEHOT_DTYPES[dtype], _ptr(solved), _ptr(reward),
+                                           _ptr(counters), _stream(dev)), "cube_expand")
+    return dict(children=children, child_onehot=child_onehot, parent_onehot=parent_onehot, solved=solved,
+                reward=reward)
+
+
+def decode(cube_size, onehot):
+    """One-hot [N, 7, 21] -> sticker rows [N, 24]; 2x2x2 only (C ABI cube_decode)."""
+    _geom(cube_size)
+    if cube_size == 3:
+        raise NotImplementedError("3x3x3 decode is not implemented in the reference (cube_env.py:171-172)")
+    if not onehot.is_cuda or onehot.dtype not in ONEHOT_DTYPES or not onehot.is_contiguous():
+        raise TypeError("onehot must be a contiguous CUDA tensor of dtype bf16, f32 or u8")
+    n = onehot.shape[0]
+    if onehot.numel() != n * 147:
+        raise ValueError("onehot must be [N, 7, 21]")
+    out = torch.empty((n, 24), dtype=torch.uint8, device=onehot.device)
+    with torch.cuda.device(onehot.device):
+        _lib.check(_lib.load().cube_decode(cube_size, _ptr(onehot), ONEHOT_DTYPES[onehot.dtype], n, _ptr(out),
+                                           _stream(onehot.device)), "cube_decode")
+    return out
+
+
+class HostScramblePipeline(object):
+    """End-to-end fused scramble for host arrays (C ABI cube_pipeline_*): chunked H2D copy,
+    kernel and D2H copy overlapped over a few streams.  Bound to one device."""
+
+    def __init__(self, cube_size, depth, chunk_instances=1 << 20, n_stages=3, device=None):
+        self.s, _, _ = _geom(cube_size)
+        self.cube_size, self.depth = cube_size, depth
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        handle = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().cube_pipeline_create(cube_size, depth, chunk_instances, n_stages,
+                                                        ctypes.byref(handle)), "cube_pipeline_create")
+        self._h = handle
+
+    def run(self, moves_host, states_out=None, solved=None, reward=None):
+        """moves_host: CPU uint8 tensor [N, depth] (pinned for full overlap).  Returns CPU tensors
+        (states, solved, reward) and the solved count; blocks until they are filled."""
+        if moves_host.is_cuda or moves_host.dtype != torch.uint8 or not moves_host.is_contiguous():
+            raise TypeError("moves_host must be a contiguous CPU uint8 tensor")
+        n = moves_host.shape[0]
+        if moves_host.shape != (n, self.depth):
+            raise ValueError("moves_host must be [N, %d]" % self.depth)
+        if states_out is None:
+            states_out = torch.empty((n, self.s), dtype=torch.uint8).pin_memory()
+        if solved is None:
+            solved = torch.empty(n, dtype=torch.uint8).pin_memory()
+        if reward is None:
+            reward = torch.empty(n, dtype=torch.float32).pin_memory()
+        count = ctypes.c_int64(0)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().cube_pipeline_scramble_host(
+                self._h, ctypes.c_void_p(moves_host.data_ptr()), n, ctypes.c_void_p(states_out.data_ptr()),
+                ctypes.c_void_p(solved.data_ptr()), ctypes.c_void_p(reward.data_ptr()), ctypes.byref(count)),
+                "cube_pipeline_scramble_host")
+        return states_out, solved, reward, int(count.value)
+
+    def close(self):
+        if self._h:
+            _lib.load().cube_pipeline_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001 - interpreter shutdown
+            pass

@@ -1,0 +1,124 @@
+// Test-only CPU emulation of the kernels' per-thread code (csrc/cube_threads.cuh compiled as
+// plain C++): runs the exact byte-permute / table / shared-memory-image arithmetic of the CUDA
+// kernels tile by tile, so index and selector bugs surface in the CPU test-suite, before a GPU
+// is involved.  Never linked into the product library.
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../rubiks_cube_solver_b200/csrc/cube_threads.cuh"
+
+namespace {
+constexpr int kTile = 256;
+inline int round16(int x) { return (x + 15) & ~15; }
+
+template <int SIZE>
+void scramble_t(const uint8_t* moves, long long n, int depth, uint8_t* out, uint8_t* solved)
+{
+    using G = CubeGeom<SIZE>;
+    const uint32_t* tbl = SIZE == 3 ? kMoveWords3 : kMoveWords2;
+    const uint32_t* clut = SIZE == 3 ? kCornerColour3 : kCornerColour2;
+    std::vector<uint8_t> s_moves(round16(kTile * depth) + 32), s_out(round16(kTile * G::S));
+    for (long long base = 0; base < n; base += kTile) {
+        const int cnt = (int)((n - base) < kTile ? (n - base) : kTile);
+        std::memset(s_moves.data(), 0xee, s_moves.size());
+        std::memcpy(s_moves.data(), moves + base * depth, (size_t)cnt * depth);
+        for (int tid = 0; tid < cnt; ++tid) {
+            CubieState st;
+            cubie_init(st);
+            scramble_run_staged<SIZE>(st, tid, depth, s_moves.data(), tbl);
+            solved[base + tid] = scramble_finish<SIZE>(st, tid, clut, kEdgeColour3, s_out.data());
+        }
+        std::memcpy(out + base * G::S, s_out.data(), (size_t)cnt * G::S);
+    }
+}
+
+template <int SIZE>
+void walk_t(const uint8_t* in, const uint8_t* moves, long long n, int depth, uint8_t* out, uint8_t* solved)
+{
+    using G = CubeGeom<SIZE>;
+    const uint32_t* cyc = SIZE == 3 ? kCycles3 : kCycles2;
+    for (long long i = 0; i < n; ++i) {
+        alignas(4) uint8_t row[56];
+        std::memcpy(row, in + i * G::S, G::S);
+        for (int k = 0; k < depth; ++k) walk_turn<SIZE>(row, moves[i * depth + k] & 0xfu, cyc);
+        solved[i] = row_solved<SIZE>(row);
+        std::memcpy(out + i * G::S, row, G::S);
+    }
+}
+
+template <int SIZE, int DTYPE>
+void expand_t(const uint8_t* states, long long n, uint8_t* children, uint8_t* child_oh, uint8_t* parent_oh,
+              uint8_t* solved)
+{
+    using G = CubeGeom<SIZE>;
+    constexpr int S = G::S, A = G::A, R = G::R, C = G::C, ES = OneHot<DTYPE>::ESIZE, P = 16;
+    const uint8_t* gather = SIZE == 3 ? kGather3 : kGather2;
+    const int gstride = SIZE == 3 ? 56 : 24;
+    const uint32_t* def = SIZE == 3 ? kHashSrc3 + 12 * 20 : kHashSrc2 + 6 * 7;
+    const uint8_t* lut0 = SIZE == 3 ? kCornerCol3 : kPieceCode2;
+    const uint8_t* lut1 = kEdgeCol3;
+    std::vector<uint8_t> s_child(P * A * S), colc(P * A * R + 4), colp(P * R + 4);
+    for (long long base = 0; base < n; base += P) {
+        const int cnt = (int)((n - base) < P ? (n - base) : P), rows = cnt * A;
+        const uint8_t* s_par = states + base * S;
+        std::memset(colc.data(), 255, colc.size());
+        std::memset(colp.data(), 255, colp.size());
+        for (int r = 0; r < rows; ++r)
+            for (int i = 0; i < S; ++i) s_child[r * S + i] = s_par[(r / A) * S + gather[(r % A) * gstride + i]];
+        for (int it = 0; it < (rows + cnt) * R; ++it) {
+            const int r = it / R, slot = it % R;
+            const bool is_child = r < rows;
+            const int rr = is_child ? r : r - rows;
+            const uint8_t* row = is_child ? &s_child[rr * S] : s_par + rr * S;
+            uint8_t* colrow = is_child ? &colc[rr * R] : &colp[rr * R];
+            const uint32_t code = onehot_code<SIZE>(row, slot, def, lut0, lut1);
+            if (SIZE == 3) colrow[slot] = (uint8_t)code;
+            else colrow[code & 0xfu] = (uint8_t)(3 * slot + (code >> 4));
+        }
+        for (int r = 0; r < rows; ++r) solved[base * A + r] = stickers_solved<SIZE>(&s_child[r * S]);
+        if (children) std::memcpy(children + base * A * S, s_child.data(), (size_t)rows * S);
+        for (int pass = 0; pass < 2; ++pass) {
+            uint8_t* dst = pass == 0 ? child_oh : parent_oh;
+            if (!dst) continue;
+            const int nr = pass == 0 ? rows : cnt;
+            const uint8_t* col = pass == 0 ? colc.data() : colp.data();
+            dst += base * (pass == 0 ? A : 1) * (long long)(G::D * ES);
+            if ((nr * G::D * ES) % 16 == 0) {
+                const int n_vec = nr * R * C / OneHot<DTYPE>::V;
+                for (int v = 0; v < n_vec; ++v) {
+                    uint32_t w[4];
+                    onehot_vector<DTYPE, C>(v, col, nr * R, w);
+                    std::memcpy(dst + 16 * (long long)v, w, 16);
+                }
+            } else {
+                for (int e = 0; e < nr * G::D; ++e) {
+                    const bool one = col[e / C] == e % C;
+                    if (DTYPE == 0) reinterpret_cast<uint16_t*>(dst)[e] = one ? 0x3f80 : 0;
+                    else if (DTYPE == 1) reinterpret_cast<uint32_t*>(dst)[e] = one ? 0x3f800000u : 0u;
+                    else dst[e] = one ? 1 : 0;
+                }
+            }
+        }
+    }
+}
+}  // namespace
+
+extern "C" {
+void emul_scramble(int size, const uint8_t* moves, long long n, int depth, uint8_t* out, uint8_t* solved)
+{
+    if (size == 3) scramble_t<3>(moves, n, depth, out, solved); else scramble_t<2>(moves, n, depth, out, solved);
+}
+void emul_walk(int size, const uint8_t* in, const uint8_t* moves, long long n, int depth, uint8_t* out,
+               uint8_t* solved)
+{
+    if (size == 3) walk_t<3>(in, moves, n, depth, out, solved); else walk_t<2>(in, moves, n, depth, out, solved);
+}
+void emul_expand(int size, int dtype, const uint8_t* states, long long n, uint8_t* children, uint8_t* child_oh,
+                 uint8_t* parent_oh, uint8_t* solved)
+{
+#define CASE(SZ, DT) if (size == SZ && dtype == DT) return expand_t<SZ, DT>(states, n, children, child_oh, parent_oh, solved);
+    CASE(3, 0) CASE(3, 1) CASE(3, 2) CASE(2, 0) CASE(2, 1) CASE(2, 2)
+#undef CASE
+}
+}

@@ -1,0 +1,392 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the oracle and the
+golden vectors generated from the reference.  Bit-exact everywhere (integer / byte work).
+Run on the B200 box:  python -m pytest tests -m gpu -x -q
+"""
+import copy
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+import rubiks_cube_solver_b200 as R
+from rubiks_cube_solver_b200 import _lib, adi, ops
+
+from oracle import cube_c as C
+from oracle import cube_np as O
+from oracle import tables as T
+from oracle.gen_golden import ExactValueNet
+
+from conftest import golden
+
+pytestmark = pytest.mark.gpu
+SIZES = (2, 3)
+ONE = {torch.bfloat16: 1.0, torch.float32: 1.0, torch.uint8: 1}
+
+
+def dev():
+    return torch.device("cuda", 0)
+
+
+def cu(a, dtype=np.uint8):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=dtype)).to(dev())
+
+
+def onehot_to_u8(t):
+    return (t.float() == 1.0).to(torch.uint8).cpu().numpy(), bool(((t.float() == 0) | (t.float() == 1)).all())
+
+
+# ------------------------------------------------------------------ golden vectors (reference)
+@pytest.mark.parametrize("size", SIZES)
+def test_config1_golden(size):
+    g = golden("config1_%d.npz" % size)
+    counters = ops.new_counters(dev())
+    states, solved, reward = ops.scramble(size, cu(g["moves"]), counters=counters)
+    assert (states.cpu().numpy() == g["stickers"]).all()
+    assert (solved.cpu().numpy().astype(bool) == g["done"]).all()
+    assert (reward.cpu().numpy() == g["reward"]).all()
+    assert counters.tolist()[:2] == [int(g["done"].sum()), 1024]
+    for dt in (torch.uint8, torch.float32, torch.bfloat16):
+        enc, clean = onehot_to_u8(ops.encode(size, states, dtype=dt))
+        assert clean and (enc == g["onehot"]).all(), dt
+    # bf16 1.0 must be the exact bit pattern the net reads
+    raw = ops.encode(size, states, dtype=torch.bfloat16).view(torch.int16).cpu().numpy()
+    assert set(np.unique(raw)) == {0, 0x3f80}
+
+
+@pytest.mark.parametrize("size", SIZES)
+def test_walks_golden_step_by_step(size):
+    g = golden("walks_%d.npz" % size)
+    n, d = g["moves"].shape
+    states = ops.solved_states(size, n, dev())
+    assert (states.cpu().numpy() == O.solved_states(size, n)).all()
+    for k in range(d):
+        states, solved, reward = ops.step(size, states, cu(g["moves"][:, k]))
+        assert (states.cpu().numpy() == g["stickers"][:, k]).all(), k
+        assert (solved.cpu().numpy().astype(bool) == g["done"][:, k]).all()
+        assert (reward.cpu().numpy() == g["reward"][:, k]).all()
+        enc, _ = onehot_to_u8(ops.encode(size, states, dtype=torch.uint8))
+        assert (enc == g["onehot"][:, k]).all()
+    assert g["done"].any()
+
+
+@pytest.mark.parametrize("size", SIZES)
+def test_expand_golden(size):
+    g = golden("expand_%d.npz" % size)
+    res = ops.expand(size, cu(g["parents"]), dtype=torch.bfloat16, want_children=True, want_parent_onehot=True)
+    assert (res["children"].cpu().numpy() == g["children"]).all()
+    assert (res["solved"].cpu().numpy().astype(bool) == g["child_solved"]).all()
+    assert (res["reward"].cpu().numpy() == np.where(g["child_solved"], 1.0, -1.0)).all()
+    enc, clean = onehot_to_u8(res["child_onehot"])
+    assert clean and (enc == g["child_onehot"]).all()
+    enc, _ = onehot_to_u8(res["parent_onehot"])
+    assert (enc == O.encode(size, g["parents"])).all()
+
+
+def test_decode_golden():
+    g = golden("decode_2.npz")
+    for dt in (torch.uint8, torch.float32, torch.bfloat16):
+        got = ops.decode(2, cu(g["onehot"]).to(dt).contiguous())
+        assert (got.cpu().numpy() == g["stickers"]).all()
+    with pytest.raises(NotImplementedError):
+        ops.decode(3, cu(np.zeros((1, 20, 24))))
+
+
+# ------------------------------------------------------------------ oracle, seeded inputs
+@pytest.mark.parametrize("size", SIZES)
+@pytest.mark.parametrize("depth", (0, 1, 3, 4, 7, 8, 9, 20, 30, 31, 32, 61, 100, 128, 129, 200))
+def test_scramble_vs_oracle_depths(size, depth):
+    rng = np.random.RandomState(depth + 100 * size)
+    n = 3000
+    moves = rng.randint(T.N_ACTIONS[size], size=(n, depth)).astype(np.uint8)
+    if depth >= 2:
+        h = depth // 2
+        moves[:64, h:2 * h] = moves[:64, :h][:, ::-1] ^ 1
+        if depth % 2:
+            moves[:64, -1] = 12                                    # no-op row keeps them solved
+    counters = ops.new_counters(dev())
+    states, solved, reward = ops.scramble(size, cu(moves), counters=counters)
+    if depth >= 2 and depth % 2:
+        # the first 64 rows end with the no-op index: the oracle applies their first depth-1 moves
+        want, want_solved, want_reward, _ = C.scramble(size, np.where(moves == 12, 0, moves))
+        want[:64], want_solved[:64], want_reward[:64], _ = C.scramble(size, moves[:64, :-1])
+        cnt = int(want_solved.sum())
+    else:
+        want, want_solved, want_reward, cnt = C.scramble(size, moves)
+    assert (states.cpu().numpy() == want).all()
+    assert (solved.cpu().numpy().astype(bool) == want_solved).all()
+    assert (reward.cpu().numpy() == want_reward).all()
+    assert counters.tolist()[:2] == [cnt, n]
+    if depth >= 2:
+        assert solved[:64].all()
+
+
+@pytest.mark.parametrize("size", SIZES)
+@pytest.mark.parametrize("n", (1, 2, 255, 256, 257, 513, 100003))
+def test_scramble_ragged_sizes(size, n):
+    rng = np.random.RandomState(n)
+    depth = 20 if size == 2 else 30
+    moves = rng.randint(T.N_ACTIONS[size], size=(n, depth)).astype(np.uint8)
+    states, solved, _ = ops.scramble(size, cu(moves))
+    want, ws, _, _ = C.scramble(size, moves)
+    assert (states.cpu().numpy() == want).all() and (solved.cpu().numpy().astype(bool) == ws).all()
+
+
+def test_scramble_empty_and_optional_outputs():
+    for size in SIZES:
+        s, so, rw = ops.scramble(size, torch.empty((0, 5), dtype=torch.uint8, device=dev()))
+        assert s.shape == (0, T.N_STICKERS[size]) and so.numel() == 0
+        moves = cu(np.random.RandomState(1).randint(T.N_ACTIONS[size], size=(300, 6)))
+        s2, so2, rw2 = ops.scramble(size, moves, want_flags=False)
+        assert so2 is None and rw2 is None
+        assert (s2.cpu().numpy() == O.scramble(size, moves.cpu().numpy())).all()
+
+
+@pytest.mark.parametrize("size", SIZES)
+@pytest.mark.parametrize("depth", (1, 2, 7))
+def test_walk_vs_oracle_any_bytes(size, depth):
+    rng = np.random.RandomState(5 + depth)
+    n = 5000
+    A, S = T.N_ACTIONS[size], T.N_STICKERS[size]
+    start = O.scramble(size, rng.randint(A, size=(n, 11)))
+    start[:100] = rng.randint(0, 256, size=(100, S))               # the gather is defined for any bytes
+    moves = rng.randint(A, size=(n, depth)).astype(np.uint8)
+    start[100:200] = O.scramble(size, moves[100:200, ::-1] ^ 1)
+    out, solved, reward = ops.walk(size, cu(start), cu(moves))
+    want = O.scramble(size, moves, init=start)
+    assert (out.cpu().numpy() == want).all()
+    assert (solved.cpu().numpy().astype(bool) == O.is_solved(size, want)).all()
+    assert solved[100:200].all()
+    # in place
+    st = cu(start)
+    ops.walk(size, st, cu(moves), out=st)
+    assert (st.cpu().numpy() == want).all()
+    sol2, rew2 = ops.is_solved(size, st)
+    assert (sol2.cpu().numpy().astype(bool) == O.is_solved(size, want)).all()
+    assert (rew2.cpu().numpy() == O.rewards(O.is_solved(size, want))).all()
+
+
+@pytest.mark.parametrize("size", SIZES)
+@pytest.mark.parametrize("dtype", (torch.bfloat16, torch.float32, torch.uint8))
+@pytest.mark.parametrize("n", (1, 5, 16, 37, 4099))
+def test_expand_vs_oracle(size, dtype, n):
+    rng = np.random.RandomState(n)
+    A, S = T.N_ACTIONS[size], T.N_STICKERS[size]
+    parents = O.scramble(size, rng.randint(A, size=(n, 9)))
+    parents[0] = O.scramble(size, np.array([[3]]))[0]
+    counters = ops.new_counters(dev())
+    res = ops.expand(size, cu(parents), dtype=dtype, want_children=True, want_parent_onehot=True, counters=counters)
+    want_c, want_s = O.expand(size, parents)
+    assert (res["children"].cpu().numpy() == want_c).all()
+    assert (res["solved"].cpu().numpy().astype(bool) == want_s).all() and res["solved"][0, 2] == 1
+    assert counters.tolist()[:2] == [int(want_s.sum()), n * A]
+    enc, clean = onehot_to_u8(res["child_onehot"])
+    assert clean and (enc.reshape(n * A, -1) == O.encode(size, want_c.reshape(n * A, S)).reshape(n * A, -1)).all()
+    enc, clean = onehot_to_u8(res["parent_onehot"])
+    assert clean and (enc == O.encode(size, parents)).all()
+    # expand[a] == step(a)
+    for a in (0, A - 1):
+        stepped, _, _ = ops.step(size, cu(parents), torch.full((n,), a, dtype=torch.uint8, device=dev()))
+        assert (stepped == res["children"][:, a]).all()
+
+
+def test_validate_actions_and_errors():
+    good = cu(np.random.RandomState(0).randint(12, size=(1000, 30)))
+    ops.validate_actions(3, good)
+    with pytest.raises(IndexError):
+        ops.validate_actions(2, good)                               # 6..11 are out of range for 2x2x2
+    bad = good.clone()
+    bad[777, 3] = 12
+    with pytest.raises(IndexError):
+        ops.validate_actions(3, bad)
+    bad[777, 3] = 200
+    with pytest.raises(IndexError):
+        ops.validate_actions(3, bad)
+    with pytest.raises(NotImplementedError):
+        ops.scramble(4, good)
+    with pytest.raises(TypeError):
+        ops.scramble(3, good.cpu())
+    with pytest.raises(ValueError):                                 # mis-aligned device pointer
+        lib = _lib.load()
+        raw = torch.empty(4096, dtype=torch.uint8, device=dev())
+        _lib.check(lib.cube_scramble(3, ctypes.c_void_p(raw.data_ptr() + 1), 8, 4, ctypes.c_void_p(raw.data_ptr() + 1024),
+                                     None, None, None, None), "cube_scramble")
+
+
+# ------------------------------------------------------------------ full-size properties (BASELINE configs 2, 3)
+@pytest.mark.parametrize("size,n,depth", ((2, 16 * 2 ** 20, 20), (3, 8 * 2 ** 20, 30)))
+def test_full_size_properties(size, n, depth):
+    A = T.N_ACTIONS[size]
+    gen = torch.Generator(device=dev()).manual_seed(1234)
+    moves = torch.randint(0, A, (n, depth), dtype=torch.uint8, device=dev(), generator=gen)
+    counters = ops.new_counters(dev())
+    states, solved, reward = ops.scramble(size, moves, counters=counters)
+    # sampled replay through the oracle: first 4096 rows, 4096 random rows, and the solved count of 1 Mi rows
+    idx = np.concatenate((np.arange(4096), np.random.RandomState(7).randint(n, size=4096)))
+    want, ws, wr, _ = C.scramble(size, moves[idx].cpu().numpy())
+    assert (states[idx].cpu().numpy() == want).all()
+    assert (solved[idx].cpu().numpy().astype(bool) == ws).all() and (reward[idx].cpu().numpy() == wr).all()
+    sub = slice(n // 2, n // 2 + 2 ** 20)
+    _, ws, _, cnt = C.scramble(size, moves[sub].cpu().numpy())
+    assert int(solved[sub].sum()) == cnt
+    assert int(counters[0]) == int(solved.sum()) and int(counters[1]) == n
+    assert float(reward.double().sum()) == 2 * int(counters[0]) - n
+    # every sticker row is a permutation of the solved multiset (checksum of checksums)
+    per = T.N_STICKERS[size] // 6
+    hist = torch.stack([(states == c).sum(dim=1) for c in range(6)], dim=1)
+    assert bool((hist == per).all())
+    # scramble followed by its inverse is the identity: all N instances solved
+    undo = torch.cat((moves, moves.flip(1) ^ 1), dim=1).contiguous()
+    counters.zero_()
+    s2, so2, _ = ops.scramble(size, undo, counters=counters)
+    assert int(counters[0]) == n and bool(so2.all())
+    assert bool((s2 == ops.solved_states(size, 1, dev())).all())
+    # one more step on the resident states equals a depth+1 scramble
+    extra = torch.randint(0, A, (n,), dtype=torch.uint8, device=dev(), generator=gen)
+    stepped, so3, _ = ops.step(size, states.clone(), extra)
+    longer, so4, _ = ops.scramble(size, torch.cat((moves, extra[:, None]), dim=1).contiguous())
+    assert bool((stepped == longer).all()) and bool((so3 == so4).all())
+
+
+def test_config4_and_5_shapes_sampled():
+    # config 4 (3x3x3 ADI batch) and config 5 (2x2x2 MCTS leaves) on a slice, vs the oracle
+    gen = torch.Generator(device=dev()).manual_seed(99)
+    moves = torch.randint(0, 12, (4096, 30), dtype=torch.uint8, device=dev(), generator=gen)
+    trail, n_pad = adi.scramble_prefixes(3, moves)
+    _, want_trail, _ = O.scramble(3, moves.cpu().numpy(), per_step=True)
+    assert (trail[:, :4096].cpu().numpy() == want_trail.transpose(1, 0, 2)).all()
+    parents = trail.view(-1, 54)
+    res = ops.expand(3, parents, dtype=torch.bfloat16)
+    sample = np.random.RandomState(0).randint(parents.shape[0], size=2048)
+    pc, ps = O.expand(3, parents[sample].cpu().numpy())
+    enc, clean = onehot_to_u8(res["child_onehot"][sample])
+    assert clean and (enc.reshape(2048 * 12, 480) == O.encode(3, pc.reshape(-1, 54)).reshape(-1, 480)).all()
+    assert (res["solved"][sample].cpu().numpy().astype(bool) == ps).all()
+    leaves_moves = torch.randint(0, 6, (2 ** 16, 11), dtype=torch.uint8, device=dev(), generator=gen)
+    leaves, _, _ = ops.scramble(2, leaves_moves)
+    res = ops.expand(2, leaves, dtype=torch.bfloat16, want_children=True, want_child_onehot=False,
+                     want_parent_onehot=True)
+    lc, ls = O.expand(2, leaves.cpu().numpy())
+    assert (res["children"].cpu().numpy() == lc).all() and (res["solved"].cpu().numpy().astype(bool) == ls).all()
+    enc, _ = onehot_to_u8(res["parent_onehot"])
+    assert (enc == O.encode(2, leaves.cpu().numpy())).all()
+
+
+def test_host_pipeline_matches_device_path():
+    for size, depth in ((3, 30), (2, 20)):
+        n = 300000 + 77
+        moves = torch.from_numpy(np.random.RandomState(size).randint(T.N_ACTIONS[size], size=(n, depth))
+                                 .astype(np.uint8)).pin_memory()
+        pipe = ops.HostScramblePipeline(size, depth, chunk_instances=1 << 16, n_stages=3)
+        states, solved, reward, count = pipe.run(moves)
+        want, ws, wr, cnt = C.scramble(size, moves.numpy())
+        assert (states.numpy() == want).all() and (solved.numpy().astype(bool) == ws).all()
+        assert (reward.numpy() == wr).all() and count == cnt
+        states2, _, _, count2 = pipe.run(moves[:1000].contiguous())          # reusable, ragged
+        assert (states2.numpy() == want[:1000]).all() and count2 == int(ws[:1000].sum())
+        pipe.close()
+
+
+# ------------------------------------------------------------------ the drop-in env
+@pytest.mark.parametrize("size", SIZES)
+def test_cube_env_drop_in(size):
+    g = golden("config1_%d.npz" % size)
+    w = golden("walks_%d.npz" % size)
+    env = R.make_env(torch.device("cpu"), size)
+    assert env.state_dim == list(T.STATE_DIM[size]) and env.action_dim == T.N_ACTIONS[size]
+    assert env.action_to_sim_action[size] == T.ACTIONS[size]
+    assert env.sim_cube.dtype == np.int64 and (env.sim_cube == T.SOLVED[size]).all()
+    before = np.random.get_state()[1].copy()
+    for seed in (0, 1, 500, 1023):
+        obs = env.reset(seed=seed, scramble_count=10)
+        assert obs.dtype == np.dtype(str(g["obs_dtype"])) and obs.shape == tuple(T.STATE_DIM[size])
+        assert (env.sim_cube == g["stickers"][seed]).all() and (obs == g["onehot"][seed]).all()
+        assert obs is env.cube
+    assert (np.random.get_state()[1] == before).all()
+    with pytest.raises(UnboundLocalError):
+        env.reset(seed=0, scramble_count=0)
+    env.init_state()                                                  # step before any reset (train.py:155 path)
+    for k, a in enumerate(w["moves"][0]):
+        obs, r, d, info = env.step(int(a))
+        assert (obs == w["onehot"][0, k]).all() and (env.sim_cube == w["stickers"][0, k]).all()
+        assert isinstance(r, float) and r == w["reward"][0, k] and isinstance(d, bool) and d == w["done"][0, k]
+        assert info == {}
+    with pytest.raises(IndexError):
+        env.step(T.N_ACTIONS[size])
+    # deepcopy independence (mcts.py:37,96,101)
+    env.reset(seed=3, scramble_count=5)
+    twin = copy.deepcopy(env)
+    twin.step(0)
+    assert not (twin.sim_cube == env.sim_cube).all()
+    env.step(0)
+    assert (twin.sim_cube == env.sim_cube).all() and (twin.cube == env.cube).all()
+    # undo -> reward +1, done
+    env.init_state()
+    seq = [1, 4, 2]
+    for a in seq:
+        env.step(a)
+    for a in reversed(seq[1:]):
+        _, r, d, _ = env.step(a ^ 1)
+        assert r == -1.0 and not d
+    _, r, d, _ = env.step(seq[0] ^ 1)
+    assert r == 1.0 and d is True
+    with pytest.raises(NotImplementedError):
+        R.make_env(torch.device("cpu"), 4)
+    if size == 2:
+        d2 = golden("decode_2.npz")
+        assert (env.state_to_sim_state(d2["onehot"][0].astype(np.float64)) == d2["stickers"][0]).all()
+    else:
+        with pytest.raises(NotImplementedError):
+            env.state_to_sim_state(env.cube)
+
+
+@pytest.mark.parametrize("size", SIZES)
+def test_adi_against_reference_golden(size):
+    g = golden("adi_%d.npz" % size)
+    n, d = g["moves"].shape
+    net = ExactValueNet(T.STATE_DIM[size], T.N_ACTIONS[size])
+    env = R.make_env(torch.device("cpu"), size)
+    buf = []
+    saved = np.random.get_state()
+    np.random.seed(11)
+    env.get_random_samples(buf, net, d, n, float(g["temperature"]))
+    after = np.random.get_state()[1].copy()
+    np.random.set_state(saved)
+    assert len(buf) == n * d
+    assert (np.array([b["state"] for b in buf]) == g["state"]).all()
+    assert buf[0]["state"].dtype == (np.float64 if size == 2 else np.int64)
+    assert [b["target_policy"] for b in buf] == list(g["target_policy"])
+    assert [b["target_value"] for b in buf] == list(g["target_value"])
+    assert [b["scramble_count"] for b in buf] == list(g["scramble_count"])
+    assert np.array_equal(np.array([b["error"] for b in buf]), g["error"])
+    # the global RNG advanced exactly as the reference's loop advances it
+    ref = np.random.RandomState(11)
+    ref.randint(T.N_ACTIONS[size], size=(n, d))
+    assert (ref.get_state()[1] == after).all()
+    # get_target_value on single cubes, including the first-solved-child override
+    env.init_state()
+    env.step(5)
+    tv, tp, err = env.get_target_value(net, 1, 1.0)
+    assert (tv, tp) == (1.0, 4)
+    k = 0
+    env.init_state()
+    for a in g["moves"][0]:
+        env.step(int(a))
+        tv, tp, err = env.get_target_value(net, k + 1, float(g["temperature"]))
+        assert tv == g["target_value"][k] and tp == g["target_policy"][k] and err == g["error"][k]
+        k += 1
+
+
+def test_batched_env_matches_reference_seeds():
+    for size in SIZES:
+        g = golden("config1_%d.npz" % size)
+        env = R.BatchedCubeEnv(1024, cube_size=size, obs_dtype=torch.float32)
+        obs, reward, done = env.reset(seeds=range(1024), scramble_count=10)
+        assert (env.sim_cube.cpu().numpy() == g["stickers"]).all()
+        assert (obs.cpu().numpy() == g["onehot"]).all()
+        assert (done.cpu().numpy().astype(bool) == g["done"]).all() and (reward.cpu().numpy() == g["reward"]).all()
+        act = torch.from_numpy(g["moves"][:, -1] ^ 1)
+        obs, reward, done, info = env.step(act, validate=True)
+        want = O.scramble(size, g["moves"][:, :-1])
+        assert (env.sim_cube.cpu().numpy() == want).all() and info == {}
+        assert (obs.cpu().numpy() == O.encode(size, want)).all()

@@ -1,0 +1,115 @@
+"""CPU emulation of the CUDA kernels' per-thread code (tests/host_emul/emul.cpp compiles
+csrc/cube_threads.cuh as plain C++) against the oracle.  Catches table / selector / index
+bugs without a GPU; the product library never contains this code path."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import cube_np as O
+from oracle import tables as T
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "host_emul", "emul.cpp")
+LIB = os.path.join(HERE, "host_emul", "libcube_emul.so")
+CSRC = os.path.join(os.path.dirname(HERE), "rubiks_cube_solver_b200", "csrc")
+
+
+@pytest.fixture(scope="module")
+def emul():
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("cube_threads.cuh", "cube_common.cuh", "cube_tables.cuh")]
+    if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-w", "-o", LIB, SRC])
+    lib = ctypes.CDLL(LIB)
+    vp, ll = ctypes.c_void_p, ctypes.c_longlong
+    lib.emul_scramble.argtypes = [ctypes.c_int, vp, ll, ctypes.c_int, vp, vp]
+    lib.emul_walk.argtypes = [ctypes.c_int, vp, vp, ll, ctypes.c_int, vp, vp]
+    lib.emul_expand.argtypes = [ctypes.c_int, ctypes.c_int, vp, ll, vp, vp, vp, vp]
+    return lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+@pytest.mark.parametrize("size", (2, 3))
+@pytest.mark.parametrize("depth", (0, 1, 3, 4, 7, 8, 9, 20, 30, 31, 32, 61, 100))
+def test_scramble_emulation(emul, size, depth):
+    rng = np.random.RandomState(depth * 7 + size)
+    n = 700                                   # two full tiles + a ragged one
+    A = T.N_ACTIONS[size]
+    moves = rng.randint(A, size=(n, depth)).astype(np.uint8)
+    if depth >= 2:
+        h = depth // 2
+        moves[:50, h:2 * h] = moves[:50, :h][:, ::-1] ^ 1          # rows that come back to solved
+        if depth % 2:
+            moves[:50, -1] = moves[:50, 0]
+    out = np.empty((n, T.N_STICKERS[size]), dtype=np.uint8)
+    solved = np.empty(n, dtype=np.uint8)
+    emul.emul_scramble(size, _p(moves), n, depth, _p(out), _p(solved))
+    want = O.scramble(size, moves)
+    assert (out == want).all()
+    assert (solved.astype(bool) == O.is_solved(size, want)).all()
+    if depth >= 2 and depth % 2 == 0:
+        assert solved[:50].all()
+
+
+@pytest.mark.parametrize("size", (2, 3))
+def test_scramble_emulation_noop_rows(emul, size):
+    # indices A..15 are no-ops on the hot path (include/cube_b200.h)
+    rng = np.random.RandomState(3)
+    A = T.N_ACTIONS[size]
+    moves = rng.randint(A, size=(300, 12)).astype(np.uint8)
+    padded = np.full((300, 24), 12, dtype=np.uint8)
+    padded[:, ::2] = moves
+    a = np.empty((300, T.N_STICKERS[size]), dtype=np.uint8)
+    s = np.empty(300, dtype=np.uint8)
+    emul.emul_scramble(size, _p(padded), 300, 24, _p(a), _p(s))
+    assert (a == O.scramble(size, moves)).all()
+
+
+@pytest.mark.parametrize("size", (2, 3))
+@pytest.mark.parametrize("depth", (1, 5))
+def test_walk_emulation(emul, size, depth):
+    rng = np.random.RandomState(11 + size)
+    n = 600
+    A = T.N_ACTIONS[size]
+    start = O.scramble(size, rng.randint(A, size=(n, 9)))
+    start[:20] = rng.randint(0, 256, size=(20, T.N_STICKERS[size]))     # arbitrary bytes: still a pure gather
+    moves = rng.randint(A, size=(n, depth)).astype(np.uint8)
+    start[20:40] = O.scramble(size, (moves[20:40, ::-1] ^ 1))           # rows that end solved
+    out = np.empty_like(start)
+    solved = np.empty(n, dtype=np.uint8)
+    emul.emul_walk(size, _p(start), _p(moves), n, depth, _p(out), _p(solved))
+    want = O.scramble(size, moves, init=start)
+    assert (out == want).all()
+    assert (solved.astype(bool) == O.is_solved(size, want)).all()
+    assert solved[20:40].all()
+
+
+@pytest.mark.parametrize("size", (2, 3))
+@pytest.mark.parametrize("dtype", (0, 1, 2))
+@pytest.mark.parametrize("n", (5, 16, 37))
+def test_expand_emulation(emul, size, dtype, n):
+    rng = np.random.RandomState(n + dtype)
+    A, S = T.N_ACTIONS[size], T.N_STICKERS[size]
+    D = T.ONEHOT_WIDTH[size]
+    parents = O.scramble(size, rng.randint(A, size=(n, 6)))
+    parents[0] = O.scramble(size, np.array([[3]]))[0]                    # one move from solved
+    es = (2, 4, 1)[dtype]
+    children = np.empty((n, A, S), dtype=np.uint8)
+    coh = np.empty((n, A, D * es), dtype=np.uint8)
+    poh = np.empty((n, D * es), dtype=np.uint8)
+    solved = np.empty((n, A), dtype=np.uint8)
+    emul.emul_expand(size, dtype, _p(parents), n, _p(children), _p(coh), _p(poh), _p(solved))
+    want_c, want_s = O.expand(size, parents)
+    assert (children == want_c).all() and (solved.astype(bool) == want_s).all()
+    assert solved[0, 2] == 1
+    one = {0: np.uint16(0x3f80), 1: np.float32(1.0), 2: np.uint8(1)}[dtype]
+    view = {0: np.uint16, 1: np.float32, 2: np.uint8}[dtype]
+    want_coh = O.encode(size, want_c.reshape(n * A, S)).reshape(n, A, D).astype(view) * one
+    want_poh = O.encode(size, parents).reshape(n, D).astype(view) * one
+    assert (coh.view(view).reshape(n, A, D) == want_coh).all()
+    assert (poh.view(view).reshape(n, D) == want_poh).all()
