@@ -18,7 +18,11 @@
 CUBE_HD uint32_t cube_prmt(uint32_t x, uint32_t y, uint32_t sel)
 {
 #if defined(__CUDA_ARCH__)
-    return __byte_perm(x, y, sel);
+    // raw PRMT: __byte_perm() masks the selector with 0x7777 first (one extra LOP3 per permute);
+    // every selector in this library keeps the sign-replicate bits clear by construction
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(y), "r"(sel));
+    return r;
 #else
     uint64_t v = (uint64_t)x | ((uint64_t)y << 32);
     uint32_t r = 0;
@@ -62,21 +66,30 @@ CUBE_HD void cubie_init(CubieState& s)
     s.e0 = 0x03020100u; s.e1 = 0x07060504u; s.e2 = 0x0b0a0908u;
 }
 
-// one face turn; tbl is the [word][CUBE_MOVE_ROWS] move-word table, m < CUBE_MOVE_ROWS
+// one face turn; tbl is the [word][CUBE_MOVE_ROWS] move-word table, byte_off = 4 * move row
 template <int SIZE>
-CUBE_HD void cubie_move(CubieState& s, const uint32_t* tbl, uint32_t m)
+CUBE_HD void cubie_move_at(CubieState& s, const uint32_t* tbl, uint32_t byte_off)
 {
-    const uint32_t* t = tbl + m;
-    uint32_t n0 = cube_prmt(s.c0, s.c1, t[0 * CUBE_MOVE_ROWS]) + t[2 * CUBE_MOVE_ROWS];
-    uint32_t n1 = cube_prmt(s.c0, s.c1, t[1 * CUBE_MOVE_ROWS]) + t[3 * CUBE_MOVE_ROWS];
+    const uint32_t* t = reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(tbl) + byte_off);
+    // packed move words (gen_tables.py packed_words_3): PRMT only reads selector bits 15:0
+    const uint32_t A = t[0 * CUBE_MOVE_ROWS], B = t[1 * CUBE_MOVE_ROWS], C = t[2 * CUBE_MOVE_ROWS];
+    const uint32_t n0 = cube_prmt(s.c0, s.c1, A) + B;
+    const uint32_t n1 = cube_prmt(s.c0, s.c1, A >> 16) + C;
     s.c0 = n0; s.c1 = n1;
     if (SIZE == 3) {
-        uint32_t tt = cube_prmt(s.e0, s.e2, t[6 * CUBE_MOVE_ROWS]);
-        uint32_t m0 = cube_prmt(s.e0, s.e1, t[4 * CUBE_MOVE_ROWS]) ^ t[8 * CUBE_MOVE_ROWS];
-        uint32_t m2 = cube_prmt(s.e2, s.e1, t[5 * CUBE_MOVE_ROWS]) ^ t[9 * CUBE_MOVE_ROWS];
-        uint32_t m1 = cube_prmt(s.e1, tt, t[7 * CUBE_MOVE_ROWS]);
+        const uint32_t D = t[3 * CUBE_MOVE_ROWS], E = t[4 * CUBE_MOVE_ROWS], F = t[5 * CUBE_MOVE_ROWS];
+        const uint32_t tt = cube_prmt(s.e0, s.e2, E);
+        const uint32_t m0 = cube_prmt(s.e0, s.e1, D) ^ (F & 0x10101010u);
+        const uint32_t m2 = cube_prmt(s.e2, s.e1, D >> 16) ^ ((F >> 1) & 0x10101010u);
+        const uint32_t m1 = cube_prmt(s.e1, tt, E >> 16);
         s.e0 = m0; s.e1 = m1; s.e2 = m2;
     }
+}
+
+template <int SIZE>
+CUBE_HD void cubie_move(CubieState& s, const uint32_t* tbl, uint32_t m)      // m < CUBE_MOVE_ROWS
+{
+    cubie_move_at<SIZE>(s, tbl, m * 4u);
 }
 
 // The twist field (5 bits) only accumulates: every turn adds 0, 1 or 2 per corner.
@@ -98,23 +111,32 @@ CUBE_HD uint32_t cubie_reduce_twist(uint32_t c)
     return c - ge3 * 24u;                                        // 3 << 3
 }
 
+CUBE_HD uint32_t cube_lut_at(const uint32_t* lut, uint32_t byte_off)
+{
+    return *reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(lut) + byte_off);
+}
+
 // colour words (bytes k = 0..2) of every slot -> sticker rows; luts have 32 entries
 template <int SIZE>
 CUBE_HD void cubie_to_stickers(const CubieState& s, const uint32_t* corner_lut, const uint32_t* edge_lut,
                                uint32_t* words /* CubeGeom<SIZE>::WORDS */)
 {
+    // every cubie byte is < 32 here (twists reduced), so byte * 4 stays inside its byte:
+    // one multiply per register, then one byte-extract per slot gives the LUT byte offset
     uint32_t L[20];
+    const uint32_t c0 = s.c0 * 4u, c1 = s.c1 * 4u;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        L[q] = corner_lut[(s.c0 >> (8 * q)) & 0x1fu];
-        L[4 + q] = corner_lut[(s.c1 >> (8 * q)) & 0x1fu];
+        L[q] = cube_lut_at(corner_lut, cube_prmt(c0, 0u, 0x4440u + q));
+        L[4 + q] = cube_lut_at(corner_lut, cube_prmt(c1, 0u, 0x4440u + q));
     }
     if (SIZE == 3) {
+        const uint32_t e0 = s.e0 * 4u, e1 = s.e1 * 4u, e2 = s.e2 * 4u;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            L[8 + q] = edge_lut[(s.e0 >> (8 * q)) & 0x1fu];
-            L[12 + q] = edge_lut[(s.e1 >> (8 * q)) & 0x1fu];
-            L[16 + q] = edge_lut[(s.e2 >> (8 * q)) & 0x1fu];
+            L[8 + q] = cube_lut_at(edge_lut, cube_prmt(e0, 0u, 0x4440u + q));
+            L[12 + q] = cube_lut_at(edge_lut, cube_prmt(e1, 0u, 0x4440u + q));
+            L[16 + q] = cube_lut_at(edge_lut, cube_prmt(e2, 0u, 0x4440u + q));
         }
         cube_assemble3(L, words);
     } else {

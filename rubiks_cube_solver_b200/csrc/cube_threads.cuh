@@ -7,9 +7,11 @@
 template <int SIZE>
 CUBE_HD void scramble_apply_word(CubieState& st, const uint32_t* s_tbl, uint32_t w)
 {
-    w &= 0x0f0f0f0fu;                                   // rows 12..15 of the table are identity
+    // byte offsets of the four table rows: (m & 15) * 4 per byte (rows 12..15 are identity),
+    // then one byte-extract per move
+    const uint32_t w4 = (w * 4u) & 0x3c3c3c3cu;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) cubie_move<SIZE>(st, s_tbl, (w >> (8 * k)) & 0xffu);
+    for (int k = 0; k < 4; ++k) cubie_move_at<SIZE>(st, s_tbl, cube_prmt(w4, 0u, 0x4440u + k));
 }
 
 // moves of the tile are a flat byte image in s_moves (row `tid` at byte tid*depth, any alignment)
@@ -19,19 +21,19 @@ CUBE_HD void scramble_run_staged(CubieState& st, int tid, int depth, const uint8
     const uint32_t* mw = reinterpret_cast<const uint32_t*>(s_moves);
     const uint32_t r = (uint32_t)tid * (uint32_t)depth;
     const uint32_t wi = r >> 2, sh = (r & 3u) << 3;
-    const int nwords = (depth + 3) >> 2;
+    const int nfull = depth >> 2, tail = depth & 3;
     uint32_t lo = mw[wi];
-    for (int j = 0; j < nwords; ++j) {
-        const uint32_t hi = mw[wi + j + 1];             // may run <= 4 bytes past the row: padded, masked below
-        uint32_t w = cube_funnel_r(lo, hi, sh);
+    for (int j = 0; j < nfull; ++j) {
+        const uint32_t hi = mw[wi + j + 1];             // may run <= 4 bytes past the row (tile is padded)
+        const uint32_t w = cube_funnel_r(lo, hi, sh);
         lo = hi;
-        const int valid = depth - 4 * j;
-        if (valid < 4) {
-            const uint32_t keep = (1u << (8 * valid)) - 1u;
-            w = (w & keep) | (0x0c0c0c0cu & ~keep);     // pad with the no-op move
-        }
         scramble_apply_word<SIZE>(st, s_tbl, w);
         if (j & 1) { st.c0 = cubie_fold_twist(st.c0); st.c1 = cubie_fold_twist(st.c1); }
+    }
+    if (tail) {                                          // last 1..3 moves (uniform over the grid)
+        const uint32_t w = cube_funnel_r(lo, mw[wi + nfull + 1], sh);
+        const uint32_t w4 = (w * 4u) & 0x3c3c3c3cu;
+        for (int k = 0; k < tail; ++k) cubie_move_at<SIZE>(st, s_tbl, cube_prmt(w4, 0u, 0x4440u + k));
     }
 }
 

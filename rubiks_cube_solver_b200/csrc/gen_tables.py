@@ -201,6 +201,24 @@ def move_words_2(m):
             _bytes([cr[q] << 3 for q in range(0, 4)]), _bytes([cr[q] << 3 for q in range(4, 8)])]
 
 
+def packed_words_3(m):
+    """6 words the kernel actually loads: A = selC0 | selC1 << 16, B = dC0, C = dC1,
+    D = selE0 | selE2 << 16, E = selEt | selE1 << 16, F = fE0 | fE2 << 1 (flip bit 4 / bit 5 per byte).
+    PRMT reads only the low 16 bits of its selector, so A, D, E are used as they are for the
+    first permute and shifted right by 16 for the second."""
+    w = move_words_3(m)
+    return [w[0] | w[1] << 16, w[2], w[3], w[4] | w[5] << 16, w[6] | w[7] << 16, w[8] | w[9] << 1]
+
+
+def packed_words_2(m):
+    w = move_words_2(m)
+    return [w[0] | w[1] << 16, w[2], w[3]]
+
+
+PW3 = 6
+PW2 = 3
+
+
 def colour_lut(slots, per_face, n_or):
     """lut[piece | ori << sh] = colours seen at slot sticker positions k=0.. (one byte each).
     Position k of the slot shows home sticker (k + ori) % n of the piece."""
@@ -301,13 +319,14 @@ def render():
              "#define CUBE_TABLE static const\n#endif\n\n")
     o.append("#define CUBE_MOVE_ROWS %d   // table rows per word: 0..A-1 moves, rest identity\n" % N_MOVE_ROWS)
     o.append("#define CUBE_NOOP_MOVE 12   // identity row used for padded / rejected moves\n")
-    o.append("#define CUBE_W3 %d\n#define CUBE_W2 %d\n\n" % (W3, W2))
+    o.append("#define CUBE_W3 %d\n#define CUBE_W2 %d\n\n" % (PW3, PW2))
     # fused-scramble move words, layout [word][row]
-    t3 = [[move_words_3(m)[w] for m in range(N_MOVE_ROWS)] for w in range(W3)]
-    t2 = [[move_words_2(m)[w] for m in range(N_MOVE_ROWS)] for w in range(W2)]
-    o.append("// [word][move] : selC0 selC1 dC0 dC1 selE0 selE2 selEt selE1 fE0 fE2\n")
+    t3 = [[packed_words_3(m)[w] for m in range(N_MOVE_ROWS)] for w in range(PW3)]
+    t2 = [[packed_words_2(m)[w] for m in range(N_MOVE_ROWS)] for w in range(PW2)]
+    o.append("// [word][move] : A = selC0 | selC1 << 16, B = dC0, C = dC1, D = selE0 | selE2 << 16,\n"
+             "//                 E = selEt | selE1 << 16, F = fE0 | fE2 << 1\n")
     o.append(_c_array("uint32_t", "kMoveWords3", [v for r in t3 for v in r]))
-    o.append("// [word][move] : selC0 selC1 dC0 dC1\n")
+    o.append("// [word][move] : A = selC0 | selC1 << 16, B = dC0, C = dC1\n")
     o.append(_c_array("uint32_t", "kMoveWords2", [v for r in t2 for v in r]))
     o.append("// colour LUTs: index = cubie byte (piece | ori << 3 corners, piece | flip << 4 edges)\n")
     o.append(_c_array("uint32_t", "kCornerColour3", C_LUT_3))

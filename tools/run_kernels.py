@@ -1,0 +1,70 @@
+"""Launch each hot kernel a few times at its BASELINE size (for ncu captures and quick timing).
+
+    python tools/run_kernels.py [scramble3|scramble2|step3|step2|expand3|leaf2|all] [--iters N]
+"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import torch
+
+from rubiks_cube_solver_b200 import ops
+
+
+def main():
+    which = sys.argv[1] if len(sys.argv) > 1 and not sys.argv[1].startswith("--") else "all"
+    iters = int(sys.argv[sys.argv.index("--iters") + 1]) if "--iters" in sys.argv else 5
+    dev = torch.device("cuda", 0)
+    gen = torch.Generator(device=dev).manual_seed(1234)
+
+    def timed(name, fn, units):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        print("%-10s %8.4f ms  %.4g units/s" % (name, ms, units / ms * 1e3), flush=True)
+
+    if which in ("scramble3", "all"):
+        n, d = 8 * 2 ** 20, 30
+        moves = torch.randint(0, 12, (n, d), dtype=torch.uint8, device=dev, generator=gen)
+        st = torch.empty((n, 54), dtype=torch.uint8, device=dev)
+        so = torch.empty(n, dtype=torch.uint8, device=dev)
+        rw = torch.empty(n, dtype=torch.float32, device=dev)
+        timed("scramble3", lambda: ops.scramble(3, moves, out=st, solved=so, reward=rw), n * d)
+    if which in ("scramble2", "all"):
+        n, d = 16 * 2 ** 20, 20
+        moves = torch.randint(0, 6, (n, d), dtype=torch.uint8, device=dev, generator=gen)
+        st = torch.empty((n, 24), dtype=torch.uint8, device=dev)
+        so = torch.empty(n, dtype=torch.uint8, device=dev)
+        rw = torch.empty(n, dtype=torch.float32, device=dev)
+        timed("scramble2", lambda: ops.scramble(2, moves, out=st, solved=so, reward=rw), n * d)
+    for size, n, key in ((3, 8 * 2 ** 20, "step3"), (2, 16 * 2 ** 20, "step2")):
+        if which in (key, "all"):
+            states = ops.solved_states(size, n, dev)
+            act = torch.randint(0, ops.N_ACTIONS[size], (n,), dtype=torch.uint8, device=dev, generator=gen)
+            so = torch.empty(n, dtype=torch.uint8, device=dev)
+            rw = torch.empty(n, dtype=torch.float32, device=dev)
+            timed(key, lambda: ops.step(size, states, act, solved=so, reward=rw), n)
+    if which in ("expand3", "all"):
+        n = 2 ** 20
+        parents, _, _ = ops.scramble(3, torch.randint(0, 12, (n, 30), dtype=torch.uint8, device=dev, generator=gen),
+                                     want_flags=False)
+        child = torch.empty((n, 12, 20, 24), dtype=torch.bfloat16, device=dev)
+        timed("expand3", lambda: ops.expand(3, parents, dtype=torch.bfloat16, child_onehot=child), n)
+    if which in ("leaf2", "all"):
+        n = 2 ** 20
+        leaves, _, _ = ops.scramble(2, torch.randint(0, 6, (n, 11), dtype=torch.uint8, device=dev, generator=gen),
+                                    want_flags=False)
+        timed("leaf2", lambda: ops.expand(2, leaves, dtype=torch.bfloat16, want_children=True,
+                                          want_child_onehot=False, want_parent_onehot=True), n)
+
+
+if __name__ == "__main__":
+    main()
