@@ -41,6 +41,19 @@ CUBE_HD uint32_t cube_funnel_r(uint32_t lo, uint32_t hi, uint32_t shift)   // ((
 #endif
 }
 
+// x >> 16 on the FMA pipe (IMAD.HI) instead of the ALU pipe (SHF): the scramble kernel is
+// bound by the ALU pipe (PRMT / LOP3 / SHF share it) while the FMA pipe idles.
+CUBE_HD uint32_t cube_hi16(uint32_t x)
+{
+#if defined(__CUDA_ARCH__)
+    uint32_t r;
+    asm("mul.hi.u32 %0, %1, 65536;" : "=r"(r) : "r"(x));
+    return r;
+#else
+    return x >> 16;
+#endif
+}
+
 #include "cube_tables.cuh"
 
 // ---- geometry ---------------------------------------------------------------
@@ -54,7 +67,7 @@ template <> struct CubeGeom<3> {
 
 // ---- cubie state of the fused scramble kernel --------------------------------
 // corners: byte = piece | twist_sum << 3   (twist_sum reduced lazily, see below)
-// edges  : byte = piece | flip << 4
+// edges  : byte = piece | a << 4 | b << 5 with flip = a ^ b (U-layer flips toggle a, D-layer flips b)
 struct CubieState {
     uint32_t c0, c1;          // corner slots 0-3, 4-7
     uint32_t e0, e1, e2;      // edge slots 0-3 (U layer), 4-7 (middle), 8-11 (D layer); unused for 2x2x2
@@ -74,14 +87,14 @@ CUBE_HD void cubie_move_at(CubieState& s, const uint32_t* tbl, uint32_t byte_off
     // packed move words (gen_tables.py packed_words_3): PRMT only reads selector bits 15:0
     const uint32_t A = t[0 * CUBE_MOVE_ROWS], B = t[1 * CUBE_MOVE_ROWS], C = t[2 * CUBE_MOVE_ROWS];
     const uint32_t n0 = cube_prmt(s.c0, s.c1, A) + B;
-    const uint32_t n1 = cube_prmt(s.c0, s.c1, A >> 16) + C;
+    const uint32_t n1 = cube_prmt(s.c0, s.c1, cube_hi16(A)) + C;
     s.c0 = n0; s.c1 = n1;
     if (SIZE == 3) {
         const uint32_t D = t[3 * CUBE_MOVE_ROWS], E = t[4 * CUBE_MOVE_ROWS], F = t[5 * CUBE_MOVE_ROWS];
         const uint32_t tt = cube_prmt(s.e0, s.e2, E);
         const uint32_t m0 = cube_prmt(s.e0, s.e1, D) ^ (F & 0x10101010u);
-        const uint32_t m2 = cube_prmt(s.e2, s.e1, D >> 16) ^ ((F >> 1) & 0x10101010u);
-        const uint32_t m1 = cube_prmt(s.e1, tt, E >> 16);
+        const uint32_t m2 = cube_prmt(s.e2, s.e1, cube_hi16(D)) ^ (F & 0x20202020u);     // flip = bit4 ^ bit5
+        const uint32_t m1 = cube_prmt(s.e1, tt, cube_hi16(E));
         s.e0 = m0; s.e1 = m1; s.e2 = m2;
     }
 }
@@ -116,12 +129,12 @@ CUBE_HD uint32_t cube_lut_at(const uint32_t* lut, uint32_t byte_off)
     return *reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(lut) + byte_off);
 }
 
-// colour words (bytes k = 0..2) of every slot -> sticker rows; luts have 32 entries
+// colour words (bytes k = 0..2) of every slot -> sticker rows; 32 corner / 64 edge LUT entries
 template <int SIZE>
 CUBE_HD void cubie_to_stickers(const CubieState& s, const uint32_t* corner_lut, const uint32_t* edge_lut,
                                uint32_t* words /* CubeGeom<SIZE>::WORDS */)
 {
-    // every cubie byte is < 32 here (twists reduced), so byte * 4 stays inside its byte:
+    // every cubie byte is < 64 here (twists reduced), so byte * 4 stays inside its byte:
     // one multiply per register, then one byte-extract per slot gives the LUT byte offset
     uint32_t L[20];
     const uint32_t c0 = s.c0 * 4u, c1 = s.c1 * 4u;
@@ -147,8 +160,15 @@ CUBE_HD void cubie_to_stickers(const CubieState& s, const uint32_t* corner_lut, 
 template <int SIZE>
 CUBE_HD bool cubie_is_identity(const CubieState& s)     // twists must be reduced first
 {
+    // corners first: a random state passes this with probability ~1e-8, so the edge test
+    // (which has to fold the two flip bits) almost never executes
     bool ok = (s.c0 == 0x03020100u) & (s.c1 == 0x07060504u);
-    if (SIZE == 3) ok = ok & (s.e0 == 0x03020100u) & (s.e1 == 0x07060504u) & (s.e2 == 0x0b0a0908u);
+    if (SIZE == 3 && ok) {
+        const uint32_t e0 = (s.e0 ^ ((s.e0 >> 1) & 0x10101010u)) & 0x1f1f1f1fu;
+        const uint32_t e1 = (s.e1 ^ ((s.e1 >> 1) & 0x10101010u)) & 0x1f1f1f1fu;
+        const uint32_t e2 = (s.e2 ^ ((s.e2 >> 1) & 0x10101010u)) & 0x1f1f1f1fu;
+        ok = (e0 == 0x03020100u) & (e1 == 0x07060504u) & (e2 == 0x0b0a0908u);
+    }
     return ok;
 }
 

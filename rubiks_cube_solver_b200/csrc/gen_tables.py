@@ -203,7 +203,8 @@ def move_words_2(m):
 
 def packed_words_3(m):
     """6 words the kernel actually loads: A = selC0 | selC1 << 16, B = dC0, C = dC1,
-    D = selE0 | selE2 << 16, E = selEt | selE1 << 16, F = fE0 | fE2 << 1 (flip bit 4 / bit 5 per byte).
+    D = selE0 | selE2 << 16, E = selEt | selE1 << 16, F = fE0 | fE2 << 1 (bit 4 / bit 5 per byte;
+    an edge is flipped when bits 4 and 5 of its byte differ).
     PRMT reads only the low 16 bits of its selector, so A, D, E are used as they are for the
     first permute and shifted right by 16 for the second."""
     w = move_words_3(m)
@@ -231,7 +232,11 @@ def colour_lut(slots, per_face, n_or):
 
 
 C_LUT_3 = colour_lut(CORNER_SLOTS_3, 9, 3)
-E_LUT_3 = colour_lut(EDGE_SLOTS_3, 9, 2)
+# Edge flip is the PARITY of bits 4 and 5 of the edge byte: U-layer flips toggle bit 4 and
+# D-layer flips toggle bit 5, so the packed flip word F = fE0 | fE2 << 1 is applied with two fused
+# and-xor LOP3s and no shift.  The edge colour LUT therefore has 64 entries.
+_E_LUT_32 = colour_lut(EDGE_SLOTS_3, 9, 2)
+E_LUT_3 = [_E_LUT_32[(i & 15) | ((((i >> 4) ^ (i >> 5)) & 1) << 4)] for i in range(64)]
 C_LUT_2 = colour_lut(CORNER_SLOTS_2, 4, 3)
 
 
@@ -380,10 +385,10 @@ def prmt(x, y, s):
 def emulate_3(seq):
     c0, c1, e0, e1, e2 = 0x03020100, 0x07060504, 0x03020100, 0x07060504, 0x0b0a0908
     for m in seq:
-        w = move_words_3(m)
-        n0, n1 = prmt(c0, c1, w[0]) + w[2], prmt(c0, c1, w[1]) + w[3]
-        t = prmt(e0, e2, w[6])
-        m0, m2, m1 = prmt(e0, e1, w[4]) ^ w[8], prmt(e2, e1, w[5]) ^ w[9], prmt(e1, t, w[7])
+        A, B, C, D, E, F = packed_words_3(m)           # exactly what the kernel does
+        n0, n1 = prmt(c0, c1, A) + B, prmt(c0, c1, A >> 16) + C
+        t = prmt(e0, e2, E)
+        m0, m2, m1 = prmt(e0, e1, D) ^ (F & 0x10101010), prmt(e2, e1, D >> 16) ^ (F & 0x20202020), prmt(e1, t, E >> 16)
         c0, c1, e0, e1, e2 = n0, n1, m0, m1, m2
     regs = [(c0 >> 8 * i) & 255 for i in range(4)] + [(c1 >> 8 * i) & 255 for i in range(4)]
     regs = [(b & 7) | (((b >> 3) % 3) << 3) for b in regs]
@@ -403,8 +408,8 @@ def emulate_3(seq):
 def emulate_2(seq):
     c0, c1 = 0x03020100, 0x07060504
     for m in seq:
-        w = move_words_2(m)
-        c0, c1 = prmt(c0, c1, w[0]) + w[2], prmt(c0, c1, w[1]) + w[3]
+        A, B, C = packed_words_2(m)
+        c0, c1 = prmt(c0, c1, A) + B, prmt(c0, c1, A >> 16) + C
     regs = [(c0 >> 8 * i) & 255 for i in range(4)] + [(c1 >> 8 * i) & 255 for i in range(4)]
     regs = [(b & 7) | (((b >> 3) % 3) << 3) for b in regs]
     src = sticker_sources([CORNER_SLOTS_2], 24, {})
