@@ -54,6 +54,17 @@ CUBE_HD uint32_t cube_hi16(uint32_t x)
 #endif
 }
 
+CUBE_HD uint32_t cube_shr2(uint32_t x)          // x >> 2, also on the FMA pipe
+{
+#if defined(__CUDA_ARCH__)
+    uint32_t r;
+    asm("mul.hi.u32 %0, %1, 1073741824;" : "=r"(r) : "r"(x));
+    return r;
+#else
+    return x >> 2;
+#endif
+}
+
 #include "cube_tables.cuh"
 
 // ---- geometry ---------------------------------------------------------------
@@ -85,12 +96,14 @@ CUBE_HD void cubie_move_at(CubieState& s, const uint32_t* tbl, uint32_t byte_off
 {
     const uint32_t* t = reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(tbl) + byte_off);
     // packed move words (gen_tables.py packed_words_3): PRMT only reads selector bits 15:0
-    const uint32_t A = t[0 * CUBE_MOVE_ROWS], B = t[1 * CUBE_MOVE_ROWS], C = t[2 * CUBE_MOVE_ROWS];
+    // D-layer corner q+4 sits under U-layer corner q and a side-face turn twists them in opposite
+    // senses, so the D-layer twist word is 2*B (mod 3): one multiply-add, no table word
+    const uint32_t A = t[0 * CUBE_MOVE_ROWS], B = t[1 * CUBE_MOVE_ROWS];
     const uint32_t n0 = cube_prmt(s.c0, s.c1, A) + B;
-    const uint32_t n1 = cube_prmt(s.c0, s.c1, cube_hi16(A)) + C;
+    const uint32_t n1 = cube_prmt(s.c0, s.c1, cube_hi16(A)) + 2u * B;
     s.c0 = n0; s.c1 = n1;
     if (SIZE == 3) {
-        const uint32_t D = t[3 * CUBE_MOVE_ROWS], E = t[4 * CUBE_MOVE_ROWS], F = t[5 * CUBE_MOVE_ROWS];
+        const uint32_t D = t[2 * CUBE_MOVE_ROWS], E = t[3 * CUBE_MOVE_ROWS], F = t[4 * CUBE_MOVE_ROWS];
         const uint32_t tt = cube_prmt(s.e0, s.e2, E);
         const uint32_t m0 = cube_prmt(s.e0, s.e1, D) ^ (F & 0x10101010u);
         const uint32_t m2 = cube_prmt(s.e2, s.e1, cube_hi16(D)) ^ (F & 0x20202020u);     // flip = bit4 ^ bit5
@@ -105,15 +118,18 @@ CUBE_HD void cubie_move(CubieState& s, const uint32_t* tbl, uint32_t m)      // 
     cubie_move_at<SIZE>(s, tbl, m * 4u);
 }
 
-// The twist field (5 bits) only accumulates: every turn adds 0, 1 or 2 per corner.
-// Because 4 == 1 (mod 3), f -> (f & 3) + (f >> 2) preserves f mod 3 and maps
-// f <= 31 to <= 10 (and f <= 26 to <= 8), so one 4-op fold every 8 turns keeps the
-// field from overflowing: 8 + 2*8 = 24 <= 31.
-constexpr int kTwistFoldPeriod = 8;
-
+// The twist field (5 bits) only accumulates: a turn adds 0, 1 or 2 to a corner byte that ends up
+// in the U layer (c0 += B) and 0, 2 or 4 to one that ends up in the D layer (c1 += 2*B), and bytes
+// migrate between the two registers.  Because 4 == 1 (mod 3), f -> (f & 3) + (f >> 2) preserves
+// f mod 3 and maps f <= 26 to <= 8.  BOTH registers are folded after every 4 turns, so whatever
+// route a byte takes it holds <= 8 + 4*4 = 24 before a fold, and <= 8 + 3*4 = 20 after the up to
+// 3 turns that may follow the last fold.  (Folding the two registers on different schedules is
+// wrong: a byte can dodge the folds by changing layer.)
 CUBE_HD uint32_t cubie_fold_twist(uint32_t c)
 {
-    return (c & 0x1f1f1f1fu) + ((c >> 2) & 0x38383838u);
+    // f - 3 * (f >> 2) == (f & 3) + (f >> 2); t holds (f >> 2) at the field's position (bits 3..5)
+    const uint32_t t = cube_shr2(c) & 0x38383838u;
+    return c - 3u * t;
 }
 
 // exact twist mod 3 (field <= 31 on entry): two folds bring it to <= 4, then one conditional -3

@@ -23,12 +23,14 @@ CUBE_HD void scramble_run_staged(CubieState& st, int tid, int depth, const uint8
     const uint32_t wi = r >> 2, sh = (r & 3u) << 3;
     const int nfull = depth >> 2, tail = depth & 3;
     uint32_t lo = mw[wi];
+#pragma unroll 2
     for (int j = 0; j < nfull; ++j) {
         const uint32_t hi = mw[wi + j + 1];             // may run <= 4 bytes past the row (tile is padded)
         const uint32_t w = cube_funnel_r(lo, hi, sh);
         lo = hi;
         scramble_apply_word<SIZE>(st, s_tbl, w);
-        if (j & 1) { st.c0 = cubie_fold_twist(st.c0); st.c1 = cubie_fold_twist(st.c1); }
+        st.c0 = cubie_fold_twist(st.c0);                 // every 4 turns, see cubie_fold_twist
+        st.c1 = cubie_fold_twist(st.c1);
     }
     if (tail) {                                          // last 1..3 moves (uniform over the grid)
         const uint32_t w = cube_funnel_r(lo, mw[wi + nfull + 1], sh);
@@ -56,9 +58,10 @@ CUBE_HD bool scramble_finish(CubieState& st, int tid, const uint32_t* s_clut, co
         for (int j = 0; j < 13; ++j) wbase[j] = cube_prmt(words[j], words[j + 1], sel);
         *reinterpret_cast<uint16_t*>(rowp + (odd ? 0 : 52)) = (uint16_t)(odd ? words[0] : words[13]);
     } else {
-        uint32_t* rowp = reinterpret_cast<uint32_t*>(s_out + 24 * tid);
+        // 24-byte rows as three 8-byte stores: a half-warp's 16 rows hit 16 distinct bank pairs
+        uint64_t* rowp = reinterpret_cast<uint64_t*>(s_out + 24 * tid);
 #pragma unroll
-        for (int j = 0; j < 6; ++j) rowp[j] = words[j];
+        for (int j = 0; j < 3; ++j) rowp[j] = (uint64_t)words[2 * j] | ((uint64_t)words[2 * j + 1] << 32);
     }
     return ok;
 }

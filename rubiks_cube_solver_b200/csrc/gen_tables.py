@@ -202,22 +202,34 @@ def move_words_2(m):
 
 
 def packed_words_3(m):
-    """6 words the kernel actually loads: A = selC0 | selC1 << 16, B = dC0, C = dC1,
-    D = selE0 | selE2 << 16, E = selEt | selE1 << 16, F = fE0 | fE2 << 1 (bit 4 / bit 5 per byte;
-    an edge is flipped when bits 4 and 5 of its byte differ).
+    """5 words the kernel actually loads: A = selC0 | selC1 << 16, B = dC0, D = selE0 | selE2 << 16,
+    E = selEt | selE1 << 16, F = fE0 | fE2 << 1 (bit 4 / bit 5 per byte; an edge is flipped when
+    bits 4 and 5 of its byte differ).
     PRMT reads only the low 16 bits of its selector, so A, D, E are used as they are for the
-    first permute and shifted right by 16 for the second."""
+    first permute and shifted right by 16 for the second.  The D-layer corner twists need no
+    word of their own: corner slot q+4 sits directly below slot q and a side-face turn twists
+    the two in opposite senses, so dC1 == 2 * dC0 (mod 3) byte for byte (asserted here)."""
     w = move_words_3(m)
-    return [w[0] | w[1] << 16, w[2], w[3], w[4] | w[5] << 16, w[6] | w[7] << 16, w[8] | w[9] << 1]
+    for q in range(4):
+        d0, d1 = (w[2] >> (8 * q + 3)) & 3, (w[3] >> (8 * q + 3)) & 3
+        assert d1 == (2 * d0) % 3, "D-layer twist must be the negative of the U-layer twist"
+    return [w[0] | w[1] << 16, w[2], w[4] | w[5] << 16, w[6] | w[7] << 16, w[8] | w[9] << 1]
 
 
 def packed_words_2(m):
     w = move_words_2(m)
-    return [w[0] | w[1] << 16, w[2], w[3]]
+    for q in range(4):
+        d0, d1 = (w[2] >> (8 * q + 3)) & 3, (w[3] >> (8 * q + 3)) & 3
+        assert d1 == (2 * d0) % 3
+    return [w[0] | w[1] << 16, w[2]]
 
 
-PW3 = 6
-PW2 = 3
+def fold_twist(c):
+    return (c & 0x1f1f1f1f) + ((c >> 2) & 0x38383838)
+
+
+PW3 = 5
+PW2 = 2
 
 
 def colour_lut(slots, per_face, n_or):
@@ -328,10 +340,10 @@ def render():
     # fused-scramble move words, layout [word][row]
     t3 = [[packed_words_3(m)[w] for m in range(N_MOVE_ROWS)] for w in range(PW3)]
     t2 = [[packed_words_2(m)[w] for m in range(N_MOVE_ROWS)] for w in range(PW2)]
-    o.append("// [word][move] : A = selC0 | selC1 << 16, B = dC0, C = dC1, D = selE0 | selE2 << 16,\n"
+    o.append("// [word][move] : A = selC0 | selC1 << 16, B = dC0 (dC1 == 2*B mod 3), D = selE0 | selE2 << 16,\n"
              "//                 E = selEt | selE1 << 16, F = fE0 | fE2 << 1\n")
     o.append(_c_array("uint32_t", "kMoveWords3", [v for r in t3 for v in r]))
-    o.append("// [word][move] : A = selC0 | selC1 << 16, B = dC0, C = dC1\n")
+    o.append("// [word][move] : A = selC0 | selC1 << 16, B = dC0 (dC1 == 2*B mod 3)\n")
     o.append(_c_array("uint32_t", "kMoveWords2", [v for r in t2 for v in r]))
     o.append("// colour LUTs: index = cubie byte (piece | ori << 3 corners, piece | flip << 4 edges)\n")
     o.append(_c_array("uint32_t", "kCornerColour3", C_LUT_3))
@@ -384,9 +396,12 @@ def prmt(x, y, s):
 
 def emulate_3(seq):
     c0, c1, e0, e1, e2 = 0x03020100, 0x07060504, 0x03020100, 0x07060504, 0x0b0a0908
-    for m in seq:
-        A, B, C, D, E, F = packed_words_3(m)           # exactly what the kernel does
-        n0, n1 = prmt(c0, c1, A) + B, prmt(c0, c1, A >> 16) + C
+    for i, m in enumerate(seq):
+        A, B, D, E, F = packed_words_3(m)              # exactly what the kernel does
+        n0, n1 = prmt(c0, c1, A) + B, prmt(c0, c1, A >> 16) + 2 * B
+        if i % 4 == 3:
+            n0, n1 = fold_twist(n0), fold_twist(n1)
+        assert all(((n >> 8 * k) & 255) >> 3 <= 31 for n in (n0, n1) for k in range(4)) and n0 < 2 ** 32 and n1 < 2 ** 32
         t = prmt(e0, e2, E)
         m0, m2, m1 = prmt(e0, e1, D) ^ (F & 0x10101010), prmt(e2, e1, D >> 16) ^ (F & 0x20202020), prmt(e1, t, E >> 16)
         c0, c1, e0, e1, e2 = n0, n1, m0, m1, m2
@@ -407,16 +422,18 @@ def emulate_3(seq):
 
 def emulate_2(seq):
     c0, c1 = 0x03020100, 0x07060504
-    for m in seq:
-        A, B, C = packed_words_2(m)
-        c0, c1 = prmt(c0, c1, A) + B, prmt(c0, c1, A >> 16) + C
+    for i, m in enumerate(seq):
+        A, B = packed_words_2(m)
+        c0, c1 = prmt(c0, c1, A) + B, prmt(c0, c1, A >> 16) + 2 * B
+        if i % 4 == 3:
+            c0, c1 = fold_twist(c0), fold_twist(c1)
     regs = [(c0 >> 8 * i) & 255 for i in range(4)] + [(c1 >> 8 * i) & 255 for i in range(4)]
     regs = [(b & 7) | (((b >> 3) % 3) << 3) for b in regs]
     src = sticker_sources([CORNER_SLOTS_2], 24, {})
     return [(C_LUT_2[regs[src[s][0]]] >> (8 * src[s][1])) & 255 for s in range(24)]
 
 
-def selftest(n=300, depth=14):
+def selftest(n=300, depth=37):
     rng = np.random.RandomState(0)
     for _ in range(n):
         seq = rng.randint(12, size=depth)

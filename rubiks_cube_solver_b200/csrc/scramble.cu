@@ -39,7 +39,8 @@ struct ScrambleSmem {                   // carve-up of the dynamic shared memory
     static constexpr int kCornerLut = kTable + G::MW * CUBE_MOVE_ROWS * 4;
     static constexpr int kEdgeLut = kCornerLut + 32 * 4;
     static constexpr int kBarrier = kEdgeLut + 64 * 4;
-    static constexpr int kOut = round16(kBarrier + 16);
+    static constexpr int kFlags = kBarrier + 16;          // one solved byte per row of the tile
+    static constexpr int kOut = round16(kFlags + kTile);
     static constexpr int kMoves = kOut + round16(kTile * G::S);
     __host__ __device__ static constexpr int bytes(int depth, bool staged)
     {
@@ -59,11 +60,13 @@ __device__ __forceinline__ void load_tables(uint8_t* smem, int tid)
     if (tid >= 160 && tid < 224) s_elut[tid - 160] = (SIZE == 3) ? kEdgeColour3[tid - 160] : 0u;
 }
 
-// one tile per CTA; move bytes staged in shared memory
-template <int SIZE>
+// one tile per CTA; move bytes staged in shared memory.  FULL: every tile of the grid has 256
+// rows (bulk copies); !FULL: the single ragged tile at the end of a batch (plain copies).
+// `tile0` is the index of the first tile this launch handles.
+template <int SIZE, bool FULL>
 __global__ void __launch_bounds__(kTile, CUBE_SCRAMBLE_MIN_BLOCKS)
-scramble_tile_kernel(const uint8_t* __restrict__ moves, long long n, int depth, uint8_t* __restrict__ out,
-                     uint8_t* __restrict__ solved, float* __restrict__ reward,
+scramble_tile_kernel(const uint8_t* __restrict__ moves, long long n, long long tile0, int depth,
+                     uint8_t* __restrict__ out, uint8_t* __restrict__ solved, float* __restrict__ reward,
                      unsigned long long* __restrict__ counters)
 {
     using G = CubeGeom<SIZE>;
@@ -73,13 +76,20 @@ scramble_tile_kernel(const uint8_t* __restrict__ moves, long long n, int depth, 
     const uint32_t* s_clut = reinterpret_cast<const uint32_t*>(smem + L::kCornerLut);
     const uint32_t* s_elut = reinterpret_cast<const uint32_t*>(smem + L::kEdgeLut);
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + L::kBarrier);
+    uint8_t* s_flags = smem + L::kFlags;
     uint8_t* s_out = smem + L::kOut;
     uint8_t* s_moves = smem + L::kMoves;
 
     const int tid = threadIdx.x;
-    const long long base = (long long)blockIdx.x * kTile;
-    const int cnt = (int)((n - base) < (long long)kTile ? (n - base) : (long long)kTile);
-    const bool full = cnt == kTile;                       // bulk copies need 16-byte multiples: full tiles only
+    // Row of the tile this thread computes.  3x3x3 rows are 54 bytes = 13.5 words, so rows of
+    // different parity sit differently on the word grid: warps 0-3 take the even rows, warps 4-7
+    // the odd ones.  Within a warp consecutive lanes are then 27 words apart (odd), which makes
+    // every per-lane shared-memory access of the row (14 stores) and of the moves (60-byte
+    // stride at depth 30) bank-conflict free, and the row's alignment is warp-uniform.
+    const int row = (SIZE == 3) ? 2 * (((tid >> 5) & 3) * 32 + (tid & 31)) + (tid >> 7) : tid;
+    const long long base = (tile0 + blockIdx.x) * kTile;
+    const int cnt = FULL ? kTile : (int)(n - base);       // bulk copies need 16-byte multiples: full tiles only
+    constexpr bool full = FULL;
     const uint32_t move_bytes = (uint32_t)(kTile * depth);
 
     if (full && depth > 0 && tid == 0) {
@@ -97,32 +107,35 @@ scramble_tile_kernel(const uint8_t* __restrict__ moves, long long n, int depth, 
     if (full && depth > 0) bulk::mbar_wait(s_bar, 0);
 
     bool ok = false;
-    if (tid < cnt) {
+    if (row < cnt) {
         CubieState st;
         cubie_init(st);
-        scramble_run_staged<SIZE>(st, tid, depth, s_moves, s_tbl);
-        ok = scramble_finish<SIZE>(st, tid, s_clut, s_elut, s_out);
-        if (solved) solved[base + tid] = ok ? 1 : 0;
-        if (reward) reward[base + tid] = ok ? 1.0f : -1.0f;
+        scramble_run_staged<SIZE>(st, row, depth, s_moves, s_tbl);
+        ok = scramble_finish<SIZE>(st, row, s_clut, s_elut, s_out);
+        s_flags[row] = ok ? 1 : 0;
     }
     const unsigned bal = __ballot_sync(0xffffffffu, ok);
     if ((tid & 31) == 0 && bal && counters) atomicAdd(&counters[0], (unsigned long long)__popc(bal));
-    if (blockIdx.x == 0 && tid == 0 && counters) atomicAdd(&counters[1], (unsigned long long)n);
+    if (blockIdx.x == 0 && tid == 0 && counters) atomicAdd(&counters[1], (unsigned long long)(FULL ? (long long)gridDim.x * kTile : (long long)cnt));
 
+    if (full) bulk::fence_smem_writes();                  // rows written above -> visible to the copy engine
+    __syncthreads();
     if (full) {
-        bulk::fence_smem_writes();                        // rows written above -> visible to the copy engine
-        __syncthreads();
         if (tid == 0) {
             bulk::store(out + base * G::S, s_out, (uint32_t)(kTile * G::S));
             bulk::commit();
-            bulk::wait_read_all();                        // shared memory must outlive the copy's reads
         }
     } else {
-        __syncthreads();
         const long long byte0 = base * G::S;
         const int nbytes = cnt * G::S;
         for (int i = tid; i < nbytes; i += kTile) out[byte0 + i] = s_out[i];
     }
+    if (tid < cnt) {                                      // verdicts leave in row order, coalesced
+        const bool row_ok = s_flags[tid] != 0;
+        if (solved) solved[base + tid] = row_ok ? 1 : 0;
+        if (reward) reward[base + tid] = row_ok ? 1.0f : -1.0f;
+    }
+    if (full && tid == 0) bulk::wait_read_all();          // shared memory must outlive the copy's reads
 }
 
 // deep sequences (depth > kMaxStagedDepth): persistent CTAs, moves read straight from global
@@ -154,7 +167,7 @@ scramble_deep_kernel(const uint8_t* __restrict__ moves, long long n, int depth, 
             const uint8_t* row = moves + (base + tid) * depth;
             for (int k = 0; k < depth; ++k) {
                 cubie_move<SIZE>(st, s_tbl, (uint32_t)__ldg(row + k) & 0xfu);
-                if ((k & 7) == 7) { st.c0 = cubie_fold_twist(st.c0); st.c1 = cubie_fold_twist(st.c1); }
+                if ((k & 3) == 3) { st.c0 = cubie_fold_twist(st.c0); st.c1 = cubie_fold_twist(st.c1); }
             }
             ok = scramble_finish<SIZE>(st, tid, s_clut, s_elut, s_out);
             if (solved) solved[base + tid] = ok ? 1 : 0;
@@ -181,16 +194,22 @@ int launch_one(const uint8_t* moves, long long n, int depth, uint8_t* out, uint8
     const int smem = ScrambleSmem<SIZE>::bytes(depth, staged);
     const long long n_tiles = (n + kTile - 1) / kTile;
     if (staged) {
-        auto kern = scramble_tile_kernel<SIZE>;
+        auto kern_full = scramble_tile_kernel<SIZE, true>;
+        auto kern_tail = scramble_tile_kernel<SIZE, false>;
         static int configured_smem = -1;
         if (smem > configured_smem) {
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            cudaError_t e = cudaFuncSetAttribute(kern_full, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(kern_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
             if (e != cudaSuccess) return (int)e;
             // largest shared-memory carve-out, so occupancy is set by registers, not by the default split
-            cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(kern_full, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             configured_smem = smem;
         }
-        kern<<<(unsigned)n_tiles, kTile, smem, stream>>>(moves, n, depth, out, solved, reward, counters);
+        const long long full_tiles = n / kTile;
+        if (full_tiles > 0)
+            kern_full<<<(unsigned)full_tiles, kTile, smem, stream>>>(moves, n, 0, depth, out, solved, reward, counters);
+        if (full_tiles < n_tiles)
+            kern_tail<<<1, kTile, smem, stream>>>(moves, n, full_tiles, depth, out, solved, reward, counters);
     } else {
         auto kern = scramble_deep_kernel<SIZE>;
         int per_sm = 0;

@@ -113,3 +113,48 @@ def test_expand_emulation(emul, size, dtype, n):
     want_poh = O.encode(size, parents).reshape(n, D).astype(view) * one
     assert (coh.view(view).reshape(n, A, D) == want_coh).all()
     assert (poh.view(view).reshape(n, D) == want_poh).all()
+
+
+def _gen_tables():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_gen_t", os.path.join(CSRC, "gen_tables.py"))
+    g = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(g)
+    return g
+
+
+@pytest.mark.parametrize("size", (2, 3))
+def test_lazy_twist_field_never_overflows(size):
+    """The scramble kernel accumulates corner twists un-reduced in a 5-bit field and folds it
+    every 4 turns.  Exact integer model of that schedule: random walks plus a greedy adversary
+    that always plays the turn maximising the largest field must stay below 32."""
+    g = _gen_tables()
+    src, rot = (g.C_SRC_3, g.C_ROT_3) if size == 3 else (g.C_SRC_2, g.C_ROT_2)
+    n_moves = len(src)
+
+    def gain(m, q):                         # c0 += B, c1 += 2*B (cube_common.cuh cubie_move_at)
+        return int(rot[m][q]) if q < 4 else 2 * int(rot[m][q - 4])
+
+    def turn(field, m):
+        return [field[src[m][q]] + gain(m, q) for q in range(8)]
+
+    def fold(field):
+        return [(f & 3) + (f >> 2) for f in field]
+
+    rng = np.random.RandomState(0)
+    worst = 0
+    for trial in range(400):
+        field = [0] * 8
+        for k in range(64):
+            if trial < 200:
+                m = int(rng.randint(n_moves))
+            else:                            # greedy adversary with random tie-breaks
+                cands = [(max(turn(field, mm)), rng.rand(), mm) for mm in range(n_moves)]
+                m = max(cands)[2]
+            field = turn(field, m)
+            worst = max(worst, max(field))
+            assert max(field) < 32, (trial, k, field)
+            if k % 4 == 3:
+                field = fold(field)
+                assert max(field) <= 8
+    assert worst <= 24
