@@ -141,7 +141,7 @@ class ClockSampler(object):
                0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
                0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
 
-    def __init__(self, index, period=0.01):
+    def __init__(self, index, period=0.004):
         self.samples, self.reasons, self.period, self._stop = [], set(), period, threading.Event()
         self.max_mhz, self._h, self._nv = None, None, None
         try:
@@ -245,7 +245,7 @@ def measure_other_configs(torch, ops, adi, dev, peak_gbs):
                                 want_flags=False)
     t = time_launches(torch, lambda: ops.expand(2, leaves, dtype=torch.bfloat16, want_children=True,
                                                 want_child_onehot=False, want_parent_onehot=True), 10)
-    entry("config5_2x2_mcts_leaf_expand_1Mi", t, n, "leaves/s", n * (24 + 294 + 144 + 6 + 24))
+    entry("config5_2x2_mcts_leaf_expand_1Mi", t, n, "leaves/s", n * (24 + 294 + 144 + 6 + 24))   # + reward f32 x6
     return out
 
 
@@ -315,12 +315,12 @@ def run_b200_arm(args):
             traffic = json.load(open(prof)).get("dram_bytes_per_launch")
         except Exception:                                   # noqa: BLE001
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "scramble_kernel<3,staged>", "achieved": alg_bytes / kern_s / 1e9,
+    roofline = {"bound": "hbm", "kernel": "scramble_tile_kernel<3,true>", "achieved": alg_bytes / kern_s / 1e9,
                 "peak": peak_gbs, "unit": "GB/s", "frac": alg_bytes / kern_s / 1e9 / peak_gbs, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                 "kernel_ms": kern_s * 1e3, "transitions_per_s_kernel_only": n * depth / kern_s,
-                "note": "K1 is issue/ALU+shared-memory bound, not HBM bound (SURVEY.md 8d): the HBM fraction "
-                        "is reported as the contract asks; see profiles/ for the limiter"}
+                "note": "K1 is bound by instruction issue / the ALU pipe (PRMT, LOP3), not by HBM (SURVEY.md 8d, "
+                        "DESIGN.md): the HBM fraction is reported as the contract asks; see profiles/"}
 
     # end to end through the host-buffer C-ABI pipeline (pinned host memory, copies inside the timed region)
     pipe = ops.HostScramblePipeline(size, depth, chunk_instances=args.e2e_chunk, n_stages=3, device=dev)
@@ -385,7 +385,7 @@ def run_b200_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=("b200", "reference"), default="b200")
     ap.add_argument("--instances-per-gpu", type=int, default=N_PER_GPU)

@@ -22,7 +22,9 @@
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kParents = 16;            // parents per tile; a multiple of 16 keeps every stream 16-byte aligned
+// parents per tile; a multiple of 16 keeps every stream 16-byte aligned.  2x2x2 parents are
+// small (6 children of 24 bytes), so a tile takes 64 of them to keep all 256 threads busy.
+template <int SIZE> struct ExpandTile { static constexpr int kParents = (SIZE == 3) ? 16 : 64; };
 
 __host__ __device__ constexpr int round16(int x) { return (x + 15) & ~15; }
 
@@ -43,7 +45,7 @@ __device__ __forceinline__ void emit_onehot(uint8_t* __restrict__ dst, const uin
 }
 
 template <int SIZE, int DTYPE>
-__global__ void __launch_bounds__(kThreads, 4)
+__global__ void __launch_bounds__(kThreads, 6)
 expand_kernel(const uint8_t* __restrict__ states, long long n, uint8_t* __restrict__ children,
               uint8_t* __restrict__ child_onehot, uint8_t* __restrict__ parent_onehot,
               uint8_t* __restrict__ solved, float* __restrict__ reward,
@@ -52,6 +54,7 @@ expand_kernel(const uint8_t* __restrict__ states, long long n, uint8_t* __restri
     using G = CubeGeom<SIZE>;
     constexpr int S = G::S, A = G::A, R = G::R, C = G::C;
     constexpr int ESIZE = OneHot<DTYPE>::ESIZE;
+    constexpr int kParents = ExpandTile<SIZE>::kParents;
     constexpr int kRows = kParents * A;
 
     __shared__ __align__(16) uint8_t s_par[round16(kParents * S)];
@@ -122,14 +125,19 @@ expand_kernel(const uint8_t* __restrict__ states, long long n, uint8_t* __restri
         }
 
         // verdicts of the children
-        bool ok = false;
-        if (need_children && tid < rows) {
-            ok = stickers_solved<SIZE>(s_child + tid * S);
-            if (solved) solved[base * A + tid] = ok ? 1 : 0;
-            if (reward) reward[base * A + tid] = ok ? 1.0f : -1.0f;
+        if (need_children) {
+            for (int r0 = 0; r0 < rows; r0 += kThreads) {     // warp-uniform trip count
+                const int r = r0 + tid;
+                bool ok = false;
+                if (r < rows) {
+                    ok = stickers_solved<SIZE>(s_child + r * S);
+                    if (solved) solved[base * A + r] = ok ? 1 : 0;
+                    if (reward) reward[base * A + r] = ok ? 1.0f : -1.0f;
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, ok);
+                if ((tid & 31) == 0 && bal) atomicAdd(&s_solved_count, (unsigned)__popc(bal));
+            }
         }
-        const unsigned bal = __ballot_sync(0xffffffffu, ok);
-        if ((tid & 31) == 0 && bal) atomicAdd(&s_solved_count, (unsigned)__popc(bal));
         __syncthreads();
 
         if (children) {
@@ -181,12 +189,17 @@ int launch_one(const uint8_t* states, long long n, uint8_t* children, void* chil
                uint8_t* solved, float* reward, unsigned long long* counters, cudaStream_t stream)
 {
     auto kern = expand_kernel<SIZE, DTYPE>;
-    int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, 0) != cudaSuccess || per_sm < 1)
-        per_sm = 1;
+    constexpr int kParents = ExpandTile<SIZE>::kParents;
     const long long n_tiles = (n + kParents - 1) / kParents;
-    long long grid = (long long)cube::sm_count() * per_sm;
-    if (grid > n_tiles) grid = n_tiles;
+    // one tile per CTA (the in-kernel tile loop only runs more than once for gigantic batches):
+    // the phases of a tile are separated by barriers, so overlap comes from having many CTAs
+    // per SM in different phases, scheduled by the hardware
+    const long long grid = n_tiles < 0x7fffffffLL ? n_tiles : 0x7fffffffLL;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        configured = true;
+    }
     kern<<<(unsigned)grid, kThreads, 0, stream>>>(states, n, children, (uint8_t*)child_onehot,
                                                   (uint8_t*)parent_onehot, solved, reward, counters);
     return (int)cudaGetLastError();

@@ -52,7 +52,7 @@ void expand_t(const uint8_t* states, long long n, uint8_t* children, uint8_t* ch
               uint8_t* solved)
 {
     using G = CubeGeom<SIZE>;
-    constexpr int S = G::S, A = G::A, R = G::R, C = G::C, ES = OneHot<DTYPE>::ESIZE, P = 16;
+    constexpr int S = G::S, A = G::A, R = G::R, C = G::C, ES = OneHot<DTYPE>::ESIZE, P = (SIZE == 3) ? 16 : 64;
     const uint8_t* gather = SIZE == 3 ? kGather3 : kGather2;
     const int gstride = SIZE == 3 ? 56 : 24;
     const uint32_t* def = SIZE == 3 ? kHashSrc3 + 12 * 20 : kHashSrc2 + 6 * 7;
