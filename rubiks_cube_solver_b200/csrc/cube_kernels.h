@@ -29,6 +29,11 @@ int launch_expand(int size, const uint8_t* states, long long n, uint8_t* childre
 int launch_validate(int size, const uint8_t* actions, long long count, unsigned long long* counters,
                     cudaStream_t stream);
 
+// 2x2x2 leaf expansion (children + parent one-hot, no child one-hot): handles the leading
+// multiple-of-tile parents and returns how many; *rc is 0 or a cudaError_t
+long long launch_leaf2(const uint8_t* states, long long n, uint8_t* children, void* parent_onehot, int dtype,
+                       uint8_t* solved, float* reward, unsigned long long* counters, cudaStream_t stream, int* rc);
+
 int launch_decode2(const void* onehot, int dtype, long long n, uint8_t* out, cudaStream_t stream);
 
 int sm_count();

@@ -318,6 +318,46 @@ def assemble_fn(name, src, n_words):
     return "".join(lines)
 
 
+def gather_words_fn(name, moves, n_words):
+    """Straight-line code: c = child `a` of the parent row held as words p[]; every child word is a
+    byte gather from at most four parent words (compile-time PRMT selectors)."""
+    lines = ["template <int A> CUBE_HD void %s(const uint32_t* p, uint32_t* c)\n{\n" % name]
+    for a, row in enumerate(moves):
+        lines.append("    if (A == %d) {\n" % a)
+        for j in range(n_words):
+            srcs = [int(row[4 * j + b]) if 4 * j + b < len(row) else 4 * j + b for b in range(4)]
+            if srcs == [4 * j + b for b in range(4)]:
+                lines.append("        c[%d] = p[%d];\n" % (j, j))
+                continue
+            words = []
+            for s_ in srcs:
+                if s_ // 4 not in words:
+                    words.append(s_ // 4)
+            def pick(pair, want):
+                # selector over (pair[0], pair[1]) giving `want` = list of (word, byte) or None per output byte
+                sel = 0
+                for i, wb in enumerate(want):
+                    if wb is None:
+                        continue
+                    w_, b_ = wb
+                    sel |= ((0 if w_ == pair[0] else 4) + b_) << (4 * i)
+                return sel
+            want = [(s_ // 4, s_ % 4) for s_ in srcs]
+            if len(words) <= 2:
+                pair = (words + words)[:2]
+                lines.append("        c[%d] = cube_prmt(p[%d], p[%d], 0x%04xu);\n" % (j, pair[0], pair[1], pick(pair, want)))
+            else:
+                lo_pair, hi_pair = words[:2], (words[2:] + words[2:])[:2]
+                lo = [wb if wb[0] in lo_pair else None for wb in want]
+                hi = [wb if wb[0] not in lo_pair else None for wb in want]
+                final = sum(((i if lo[i] is not None else 4 + i) << (4 * i)) for i in range(4))
+                lines.append("        c[%d] = cube_prmt(cube_prmt(p[%d], p[%d], 0x%04xu), cube_prmt(p[%d], p[%d], 0x%04xu), 0x%04xu);\n"
+                             % (j, lo_pair[0], lo_pair[1], pick(lo_pair, lo), hi_pair[0], hi_pair[1], pick(hi_pair, hi), final))
+        lines.append("    }\n")
+    lines.append("}\n\n")
+    return "".join(lines)
+
+
 def _c_array(ctype, name, values, per_line=8, fmt="0x%08xu"):
     flat = list(values)
     lines = []
@@ -362,6 +402,11 @@ def render():
     o.append("#ifdef CUBE_HD\n")
     o.append(assemble_fn("cube_assemble3", src3, 14))
     o.append(assemble_fn("cube_assemble2", src2, 6))
+    o.append("// sticker positions of 2x2x2 slot `pos` (py222 pieceDefs), usable as compile-time constants\n")
+    o.append("CUBE_HD constexpr int cube_piece_def2(int pos, int k)\n{\n    constexpr int t[21] = {%s};\n"
+             "    return t[pos * 3 + k];\n}\n\n" % ", ".join(str(v) for r in PIECE_DEFS_2 for v in r))
+    o.append("// child A of a 2x2x2 parent row held as six words (new[i] = old[moveDefs[A][i]])\n")
+    o.append(gather_words_fn("cube_child2", MOVES_2, 6))
     o.append("#endif\n\n")
     # sticker-level tables
     cyc3 = cycle_words(CYCLES_3)

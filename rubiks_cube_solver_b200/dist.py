@@ -37,6 +37,15 @@ def reduce_counters(counters):
     return counters
 
 
+def reduce_counters_async(counters):
+    """Start the SUM all-reduce and return a handle whose `.wait()` orders the current stream after
+    it (None for a single process).  The collective runs on NCCL's own stream, so the next step's
+    kernel -- which does not depend on it -- overlaps the reduction."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist.all_reduce(counters, op=dist.ReduceOp.SUM, async_op=True)
+    return None
+
+
 def reward_total(counters):
     """Exact sum of the +-1 rewards behind the counters: 2*solved - produced."""
     return 2 * int(counters[0]) - int(counters[1])

@@ -190,6 +190,31 @@ def test_expand_vs_oracle(size, dtype, n):
         assert (stepped == res["children"][:, a]).all()
 
 
+@pytest.mark.parametrize("dtype", (torch.bfloat16, torch.float32, torch.uint8))
+@pytest.mark.parametrize("n", (1, 63, 64, 128, 129, 1000, 70001))
+@pytest.mark.parametrize("want_children,want_parent", ((True, True), (True, False), (False, True)))
+def test_leaf_expand_vs_oracle(dtype, n, want_children, want_parent):
+    # the MCTS-leaf shape of cube_expand for 2x2x2 (register-resident kernel + generic remainder)
+    rng = np.random.RandomState(n)
+    parents = O.scramble(2, rng.randint(6, size=(n, 9)))
+    parents[0] = O.scramble(2, np.array([[3]]))[0]
+    if n > 1:
+        parents[n // 2] = O.solved_states(2, 1)[0]
+    counters = ops.new_counters(dev())
+    res = ops.expand(2, cu(parents), dtype=dtype, want_children=want_children, want_child_onehot=False,
+                     want_parent_onehot=want_parent, counters=counters)
+    want_c, want_s = O.expand(2, parents)
+    assert res["child_onehot"] is None
+    assert (res["solved"].cpu().numpy().astype(bool) == want_s).all() and res["solved"][0, 2] == 1
+    assert (res["reward"].cpu().numpy() == np.where(want_s, 1.0, -1.0)).all()
+    assert counters.tolist()[:2] == [int(want_s.sum()), n * 6]
+    if want_children:
+        assert (res["children"].cpu().numpy() == want_c).all()
+    if want_parent:
+        enc, clean = onehot_to_u8(res["parent_onehot"])
+        assert clean and (enc == O.encode(2, parents)).all()
+
+
 def test_validate_actions_and_errors():
     good = cu(np.random.RandomState(0).randint(12, size=(1000, 30)))
     ops.validate_actions(3, good)
