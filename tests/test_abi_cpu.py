@@ -156,3 +156,20 @@ def test_two_rank_counter_reduction_gloo():
         assert counters[:2] == [want_solved, 1001]
         assert total == 2 * want_solved - 1001
         assert t == 2.0
+
+
+def test_rollout_host_helpers():
+    import torch
+    from rubiks_cube_solver_b200 import rollout
+    from oracle import cube_np as O
+    m = rollout.reference_scrambles(3, seeds=[0, 10, 20], depths=[1, 4, 7])
+    assert m.shape == (9, 7) and m.dtype == np.uint8
+    for i, d in enumerate((1, 4, 7)):
+        for j, s in enumerate((0, 10, 20)):
+            row = m[i * 3 + j]
+            assert (row[:d] == O.reference_moves(3, s, d)).all() and (row[d:] == rollout.NOOP).all()
+    logits = torch.tensor([[0.1, 0.9, 0.3, 0.2], [0.8, 0.1, 0.7, 0.0], [0.0, 0.2, 0.1, 0.9]])
+    assert rollout.greedy_actions(logits).tolist() == [1, 0, 3]
+    # best action is the inverse of the previous one -> second best (model.py:60-74)
+    pre = torch.tensor([0, 1, -1])
+    assert rollout.greedy_actions(logits, pre).tolist() == [2, 2, 3]

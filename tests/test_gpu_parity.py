@@ -415,3 +415,55 @@ def test_batched_env_matches_reference_seeds():
         want = O.scramble(size, g["moves"][:, :-1])
         assert (env.sim_cube.cpu().numpy() == want).all() and info == {}
         assert (obs.cpu().numpy() == O.encode(size, want)).all()
+
+
+class ExactPolicyNet(torch.nn.Module):
+    """DeepCube-shaped net (model.py:31-45) whose outputs are exact in fp32 on any device."""
+
+    def __init__(self, state_dim, action_dim, seed=3):
+        super().__init__()
+        r = np.random.RandomState(seed)
+        d = state_dim[0] * state_dim[1]
+        self.w = torch.nn.Parameter(torch.tensor(r.randint(-512, 513, size=(d, action_dim)).astype(np.float32) / 1024.0),
+                                    requires_grad=False)
+
+    def forward(self, x):
+        if x.dim() == 2:
+            x = x.unsqueeze(0)
+        logits = x.reshape(x.shape[0], -1).float() @ self.w
+        return logits.sum(dim=1, keepdim=True), logits
+
+
+@pytest.mark.parametrize("size", SIZES)
+@pytest.mark.parametrize("mask", (False, True))
+def test_greedy_rollout_matches_scalar_env(size, mask):
+    from rubiks_cube_solver_b200 import rollout
+    from oracle.scalar_env import ScalarCubeEnv
+    net = ExactPolicyNet(T.STATE_DIM[size], T.N_ACTIONS[size])
+    seeds, depths, horizon = [0, 10, 20, 30], [1, 2, 3, 5], 12
+    moves = rollout.reference_scrambles(size, seeds, depths)
+    res = rollout.greedy_solve(net.to(dev()), size, moves, max_timesteps=horizon, mask_inverse=mask)
+    env = ScalarCubeEnv(size)
+    cpu_net = ExactPolicyNet(T.STATE_DIM[size], T.N_ACTIONS[size])
+    k = 0
+    for d in depths:
+        for s in seeds:
+            state = env.reset(seed=s, scramble_count=d)
+            first, pre = 0, None
+            for t in range(1, horizon + 1):
+                _, logits = cpu_net(torch.tensor(state).float())
+                order = logits[0].argsort(descending=True, stable=True)
+                a = int(order[0])
+                if mask and pre is not None and a == (pre ^ 1):
+                    a = int(order[1])
+                state, _, done, _ = env.step(a)
+                pre = a
+                if done:
+                    first = t
+                    break
+            assert int(res["steps"][k]) == first and bool(res["solved"][k]) == (first > 0), (d, s)
+            if first == 0:
+                assert (res["states"][k].cpu().numpy() == env.sim_cube).all()
+            k += 1
+    pct = rollout.validation(net.to(dev()), size, sample_scramble_count=3, sample_cube_count=4, max_timesteps=6)
+    assert len(pct) == 3 and all(0.0 <= p <= 100.0 for p in pct)
