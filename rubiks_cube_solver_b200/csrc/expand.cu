@@ -184,10 +184,70 @@ expand_kernel(const uint8_t* __restrict__ states, long long n, uint8_t* __restri
     }
 }
 
+// encode only (`cube_encode`, sim_state_to_state cube_env.py:132-152): no children to build, so a
+// tile is 128 rows -- enough output (123 KB for 3x3x3 bf16) per CTA to amortise the table loads
+constexpr int kEncodeRows = 128;
+
+template <int SIZE, int DTYPE>
+__global__ void __launch_bounds__(kThreads, 6)
+encode_kernel(const uint8_t* __restrict__ states, long long n, uint8_t* __restrict__ onehot)
+{
+    using G = CubeGeom<SIZE>;
+    constexpr int S = G::S, R = G::R, C = G::C, ESIZE = OneHot<DTYPE>::ESIZE;
+    __shared__ __align__(16) uint8_t s_rows[round16(kEncodeRows * S)];
+    __shared__ uint8_t s_col[kEncodeRows * R + 4];
+    __shared__ uint32_t s_def[R];
+    __shared__ uint8_t s_lut[2][128];
+
+    const int tid = threadIdx.x;
+    if (tid < R) s_def[tid] = (SIZE == 3) ? kHashSrc3[12 * 20 + tid] : kHashSrc2[6 * 7 + tid];
+    if (tid < 128) {
+        s_lut[0][tid] = (SIZE == 3) ? kCornerCol3[tid] : kPieceCode2[tid];
+        s_lut[1][tid] = (SIZE == 3) ? kEdgeCol3[tid] : 0;
+    }
+    const long long base = (long long)blockIdx.x * kEncodeRows;
+    const int cnt = (int)((n - base) < (long long)kEncodeRows ? (n - base) : (long long)kEncodeRows);
+    {
+        const long long byte0 = base * S;                  // multiple of 16
+        const int nbytes = cnt * S;
+        const int nvec = nbytes >> 4;
+        const int4* src = reinterpret_cast<const int4*>(states + byte0);
+        for (int i = tid; i < nvec; i += kThreads) reinterpret_cast<int4*>(s_rows)[i] = __ldcs(src + i);
+        for (int i = (nvec << 4) + tid; i < nbytes; i += kThreads) s_rows[i] = states[byte0 + i];
+    }
+    if (SIZE == 2) for (int i = tid; i < kEncodeRows * R; i += kThreads) s_col[i] = 255;
+    __syncthreads();
+    for (int it = tid; it < cnt * R; it += kThreads) {
+        const int r = it / R, slot = it - r * R;
+        const uint32_t code = onehot_code<SIZE>(s_rows + r * S, slot, s_def, s_lut[0], s_lut[1]);
+        if (SIZE == 3) s_col[it] = (uint8_t)code;
+        else s_col[r * R + (code & 0xfu)] = (uint8_t)(3 * slot + (code >> 4));
+    }
+    __syncthreads();
+    uint8_t* dst = onehot + base * (long long)(G::D * ESIZE);
+    if ((cnt * G::D * ESIZE) % 16 == 0) {
+        emit_onehot<DTYPE, C>(dst, s_col, cnt * R, tid);
+    } else {
+        for (int e = tid; e < cnt * G::D; e += kThreads) {
+            const int seg = e / C, off = e - seg * C;
+            const bool one = s_col[seg] == off;
+            if (DTYPE == 0) reinterpret_cast<uint16_t*>(dst)[e] = one ? 0x3f80 : 0;
+            else if (DTYPE == 1) reinterpret_cast<uint32_t*>(dst)[e] = one ? 0x3f800000u : 0u;
+            else dst[e] = one ? 1 : 0;
+        }
+    }
+}
+
 template <int SIZE, int DTYPE>
 int launch_one(const uint8_t* states, long long n, uint8_t* children, void* child_onehot, void* parent_onehot,
                uint8_t* solved, float* reward, unsigned long long* counters, cudaStream_t stream)
 {
+    if (!children && !child_onehot && !solved && !reward && !counters) {
+        if (!parent_onehot) return 0;
+        const long long tiles = (n + kEncodeRows - 1) / kEncodeRows;
+        encode_kernel<SIZE, DTYPE><<<(unsigned)tiles, kThreads, 0, stream>>>(states, n, (uint8_t*)parent_onehot);
+        return (int)cudaGetLastError();
+    }
     auto kern = expand_kernel<SIZE, DTYPE>;
     constexpr int kParents = ExpandTile<SIZE>::kParents;
     const long long n_tiles = (n + kParents - 1) / kParents;

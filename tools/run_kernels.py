@@ -64,6 +64,22 @@ def main():
                                     want_flags=False)
         timed("leaf2", lambda: ops.expand(2, leaves, dtype=torch.bfloat16, want_children=True,
                                           want_child_onehot=False, want_parent_onehot=True), n)
+    for size, n, key in ((3, 4 * 2 ** 20, "encode3"), (2, 8 * 2 ** 20, "encode2")):
+        if which in (key, "all"):
+            a = ops.N_ACTIONS[size]
+            st, _, _ = ops.scramble(size, torch.randint(0, a, (n, 15), dtype=torch.uint8, device=dev, generator=gen),
+                                    want_flags=False)
+            obs = torch.empty((n,) + ops.STATE_DIM[size], dtype=torch.bfloat16, device=dev)
+            timed(key, lambda: ops.encode(size, st, dtype=torch.bfloat16, out=obs), n)
+            d = ops.STATE_DIM[size][0] * ops.STATE_DIM[size][1]
+            print("   %s algorithmic bytes/row %d" % (key, ops.N_STICKERS[size] + 2 * d))
+    if which in ("expand2", "all"):
+        n = 4 * 2 ** 20
+        parents, _, _ = ops.scramble(2, torch.randint(0, 6, (n, 14), dtype=torch.uint8, device=dev, generator=gen),
+                                     want_flags=False)
+        child = torch.empty((n, 6, 7, 21), dtype=torch.bfloat16, device=dev)
+        timed("expand2", lambda: ops.expand(2, parents, dtype=torch.bfloat16, child_onehot=child), n)
+        print("   expand2 algorithmic bytes/parent %d" % (24 + 6 * (294 + 5)))
 
 
 if __name__ == "__main__":
