@@ -237,7 +237,31 @@ def measure_other_configs(torch, ops, adi, dev, peak_gbs):
     t = time_launches(torch, lambda: ops.expand(3, parents, dtype=torch.bfloat16, child_onehot=child), 5, warmup=2)
     entry("config4_3x3_adi_expand_4Mi_parents", t, n, "parents/s", n * (54 + 12 * (960 + 1 + 4)))
     out["config4_3x3_adi_expand_4Mi_parents"]["child_transitions_per_s"] = 12 * n / t
-    del parents, child
+    del parents
+
+    # config 4 end to end on the device: 139 810 cubes x 30 scramble prefixes (cube_env.py:187-194:
+    # every prefix is a sample) -> 4 194 300 parents -> 12 children + bf16 one-hot each
+    cubes = n // 30 // 16 * 16
+    adi_moves = torch.randint(0, 12, (cubes, 30), dtype=torch.uint8, device=dev, generator=gen)
+
+    def adi_batch():
+        trail, n_pad = adi.scramble_prefixes(3, adi_moves)
+        ops.expand(3, trail.view(-1, 54), dtype=torch.bfloat16, child_onehot=child[: 30 * n_pad])
+
+    t = time_launches(torch, adi_batch, 3, warmup=1)
+    n_par = 30 * ((cubes + 15) // 16 * 16)
+    entry("config4_3x3_adi_prefixes_plus_expand", t, n_par, "parents/s",
+          n_par * (54 + 12 * (960 + 1 + 4)) + 30 * cubes * (2 * 54 + 6))
+    del child, adi_moves
+
+    # sim_state_to_state for a resident batch (cube_encode), 3x3x3 bf16
+    n = 4 * 2 ** 20
+    st, _, _ = ops.scramble(3, torch.randint(0, 12, (n, 15), dtype=torch.uint8, device=dev, generator=gen),
+                            want_flags=False)
+    obs = torch.empty((n, 20, 24), dtype=torch.bfloat16, device=dev)
+    t = time_launches(torch, lambda: ops.encode(3, st, dtype=torch.bfloat16, out=obs), 5, warmup=2)
+    entry("encode_3x3_bf16_4Mi", t, n, "states/s", n * (54 + 960))
+    del st, obs
 
     # config 5: 2x2x2 MCTS leaves, 1 Mi: leaf one-hot bf16 + children stickers + done flags
     n = 2 ** 20

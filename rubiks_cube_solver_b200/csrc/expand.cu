@@ -71,7 +71,7 @@ expand_kernel(const uint8_t* __restrict__ states, long long n, uint8_t* __restri
         const int a = i / S, k = i - a * S;
         s_gather[i] = (SIZE == 3) ? kGather3[a * 56 + k] : kGather2[a * 24 + k];
     }
-    if (tid < R) s_def[tid] = (SIZE == 3) ? kHashSrc3[12 * 20 + tid] : kHashSrc2[6 * 7 + tid];   // identity rows
+    if (tid < R) s_def[tid] = (SIZE == 3) ? kHashDef3[tid] : kHashDef2[tid];
     if (tid < 128) {
         s_lut[0][tid] = (SIZE == 3) ? kCornerCol3[tid] : kPieceCode2[tid];
         s_lut[1][tid] = (SIZE == 3) ? kEdgeCol3[tid] : 0;
@@ -200,7 +200,7 @@ encode_kernel(const uint8_t* __restrict__ states, long long n, uint8_t* __restri
     __shared__ uint8_t s_lut[2][128];
 
     const int tid = threadIdx.x;
-    if (tid < R) s_def[tid] = (SIZE == 3) ? kHashSrc3[12 * 20 + tid] : kHashSrc2[6 * 7 + tid];
+    if (tid < R) s_def[tid] = (SIZE == 3) ? kHashDef3[tid] : kHashDef2[tid];
     if (tid < 128) {
         s_lut[0][tid] = (SIZE == 3) ? kCornerCol3[tid] : kPieceCode2[tid];
         s_lut[1][tid] = (SIZE == 3) ? kEdgeCol3[tid] : 0;

@@ -274,29 +274,16 @@ def cycle_words(cycles):
     return [[_bytes(c) for c in mv] for mv in cycles]
 
 
-def hash_sources_3():
-    """[13][20] words: bytes = parent sticker positions feeding slot's hash under action a
-    (a = 12: identity).  byte3 = 1 for edge slots."""
-    out = []
-    for a in range(13):
-        row = MOVES_3[a] if a < 12 else list(range(54))
-        words = []
-        for q in range(8):
-            d = CORNER_DEFS_REF[q]
-            words.append(_bytes([row[d[0]], row[d[1]], row[d[2]], 0]))
-        for q in range(12):
-            d = EDGE_DEFS_REF[q]
-            words.append(_bytes([row[d[0]], row[d[1]], row[d[1]], 1]))
-        out.append(words)
-    return out
+def hash_defs_3():
+    """[20] words: bytes = the sticker positions feeding each slot's hash (corner_pieceDefs /
+    edge_pieceDefs as shipped); byte 3 = 1 for edge slots."""
+    words = [_bytes([d[0], d[1], d[2], 0]) for d in CORNER_DEFS_REF]
+    words += [_bytes([d[0], d[1], d[1], 1]) for d in EDGE_DEFS_REF]
+    return words
 
 
-def hash_sources_2():
-    out = []
-    for a in range(7):
-        row = MOVES_2[a] if a < 6 else list(range(24))
-        out.append([_bytes([row[d[0]], row[d[1]], row[d[2]], 0]) for d in PIECE_DEFS_2])
-    return out
+def hash_defs_2():
+    return [_bytes([d[0], d[1], d[2], 0]) for d in PIECE_DEFS_2]
 
 
 def assemble_fn(name, src, n_words):
@@ -385,19 +372,12 @@ def render():
     o.append(_c_array("uint32_t", "kMoveWords3", [v for r in t3 for v in r]))
     o.append("// [word][move] : A = selC0 | selC1 << 16, B = dC0 (dC1 == 2*B mod 3)\n")
     o.append(_c_array("uint32_t", "kMoveWords2", [v for r in t2 for v in r]))
-    o.append("// colour LUTs: index = cubie byte (piece | ori << 3 corners, piece | flip << 4 edges)\n")
+    o.append("// colour LUTs: index = cubie byte (piece | twist << 3 corners; piece | a << 4 | b << 5 edges, flip = a ^ b)\n")
     o.append(_c_array("uint32_t", "kCornerColour3", C_LUT_3))
     o.append(_c_array("uint32_t", "kEdgeColour3", E_LUT_3))
     o.append(_c_array("uint32_t", "kCornerColour2", C_LUT_2))
-    # sticker sources for the expansion (compile-time use): encoded as reg<<2|byte, or 0x80|colour
-    def enc(src):
-        return [(0x80 | v[1]) if v[0] == "const" else (v[0] << 2 | v[1]) for v in src]
     src3 = sticker_sources([CORNER_SLOTS_3, EDGE_SLOTS_3], 54, {4 + 9 * f: f for f in range(6)})
     src2 = sticker_sources([CORNER_SLOTS_2], 24, {})
-    o.append("// where each output sticker comes from: slot << 2 | k, or 0x80 | colour (centres)\n")
-    o.append("CUBE_TABLE uint8_t kStickerSrc3[56] = {%s, 0x80, 0x80};\n"
-             % ", ".join("0x%02x" % v for v in enc(src3)))
-    o.append("CUBE_TABLE uint8_t kStickerSrc2[24] = {%s};\n\n" % ", ".join("0x%02x" % v for v in enc(src2)))
     o.append("// sticker rows from per-slot colour words L[slot] (bytes k = 0..2), generated straight-line\n")
     o.append("#ifdef CUBE_HD\n")
     o.append(assemble_fn("cube_assemble3", src3, 14))
@@ -415,14 +395,14 @@ def render():
     o.append("// layout [cycle][move row] (rows >= A hold the trivial cycle 0,0,0,0)\n")
     o.append(_c_array("uint32_t", "kCycles3", [(cyc3[m][c] if m < 12 else 0) for c in range(5) for m in range(N_MOVE_ROWS)]))
     o.append(_c_array("uint32_t", "kCycles2", [(cyc2[m][c] if m < 6 else 0) for c in range(3) for m in range(N_MOVE_ROWS)]))
-    o.append("// full gather rows new[i] = old[row[i]] ([13][56] / [7][24]; last row = identity)\n")
-    g3 = [list(MOVES_3[a]) + [54, 55] for a in range(12)] + [list(range(56))]
-    g2 = [list(MOVES_2[a]) for a in range(6)] + [list(range(24))]
+    o.append("// full gather rows new[i] = old[row[i]] ([12][56] / [6][24])\n")
+    g3 = [list(MOVES_3[a]) + [54, 55] for a in range(12)]
+    g2 = [list(MOVES_2[a]) for a in range(6)]
     o.append(_c_array("uint8_t", "kGather3", [v for r in g3 for v in r], per_line=28, fmt="%d"))
     o.append(_c_array("uint8_t", "kGather2", [v for r in g2 for v in r], per_line=24, fmt="%d"))
-    o.append("// one-hot hash sources: [action (last = identity)][slot] -> parent sticker positions\n")
-    o.append(_c_array("uint32_t", "kHashSrc3", [v for r in hash_sources_3() for v in r]))
-    o.append(_c_array("uint32_t", "kHashSrc2", [v for r in hash_sources_2() for v in r]))
+    o.append("// one-hot hash definitions: [slot] -> the sticker positions whose colours are hashed\n")
+    o.append(_c_array("uint32_t", "kHashDef3", hash_defs_3()))
+    o.append(_c_array("uint32_t", "kHashDef2", hash_defs_2()))
     o.append("// hash -> one-hot column (3x3x3, holes = 0 as shipped) / cubelet | ori << 4 (2x2x2)\n")
     o.append(_c_array("uint8_t", "kCornerCol3", CORNER_COL_3, per_line=32, fmt="%d"))
     o.append(_c_array("uint8_t", "kEdgeCol3", EDGE_COL_3, per_line=32, fmt="%d"))

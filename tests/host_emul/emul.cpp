@@ -55,7 +55,7 @@ void expand_t(const uint8_t* states, long long n, uint8_t* children, uint8_t* ch
     constexpr int S = G::S, A = G::A, R = G::R, C = G::C, ES = OneHot<DTYPE>::ESIZE, P = (SIZE == 3) ? 16 : 64;
     const uint8_t* gather = SIZE == 3 ? kGather3 : kGather2;
     const int gstride = SIZE == 3 ? 56 : 24;
-    const uint32_t* def = SIZE == 3 ? kHashSrc3 + 12 * 20 : kHashSrc2 + 6 * 7;
+    const uint32_t* def = SIZE == 3 ? kHashDef3 : kHashDef2;
     const uint8_t* lut0 = SIZE == 3 ? kCornerCol3 : kPieceCode2;
     const uint8_t* lut1 = kEdgeCol3;
     std::vector<uint8_t> s_child(P * A * S), colc(P * A * R + 4), colp(P * R + 4);
