@@ -270,7 +270,54 @@ def measure_other_configs(torch, ops, adi, dev, peak_gbs):
     t = time_launches(torch, lambda: ops.expand(2, leaves, dtype=torch.bfloat16, want_children=True,
                                                 want_child_onehot=False, want_parent_onehot=True), 10)
     entry("config5_2x2_mcts_leaf_expand_1Mi", t, n, "leaves/s", n * (24 + 294 + 144 + 6 + 24))   # + reward f32 x6
+    out["drop_in_get_random_samples"] = measure_drop_in_adi(torch, dev)
     return out
+
+
+def measure_drop_in_adi(torch, dev):
+    """The reference's own call -- env.get_random_samples(buf, model, 30, 200, T) (train.py:155,
+    config.yaml: 200 cubes x 30 scrambles, 3x3x3, hidden [1024, 256, 128]) -- through the drop-in
+    CubeEnv (GPU inside) and through the reference-semantics per-cube env on one host core."""
+    import numpy as np
+    import rubiks_cube_solver_b200 as R
+    from oracle.scalar_env import ScalarCubeEnv
+
+    class Net(torch.nn.Module):                               # DeepCube's layer shapes (model.py:7-29)
+        def __init__(self):
+            super().__init__()
+            nn = torch.nn
+            self.enc = nn.Sequential(nn.Flatten(), nn.Linear(480, 1024), nn.ELU(), nn.Linear(1024, 256), nn.ELU())
+            self.pol = nn.Sequential(nn.Linear(256, 128), nn.ELU(), nn.Linear(128, 12))
+            self.val = nn.Sequential(nn.Linear(256, 128), nn.ELU(), nn.Linear(128, 1))
+
+        def forward(self, x):
+            if x.dim() == 2:
+                x = x.unsqueeze(0)
+            h = self.enc(x)
+            return self.val(h), self.pol(h)
+
+    torch.manual_seed(0)
+    gpu_net = Net().to(dev)
+    env = R.make_env(dev, 3)
+    np.random.seed(0)
+    env.get_random_samples([], gpu_net, 30, 200, 1.0)        # warm-up
+    buf = []
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        env.get_random_samples(buf, gpu_net, 30, 200, 1.0)
+    torch.cuda.synchronize()
+    ours = 3 * 6000 / (time.perf_counter() - t0)
+    cpu_net = Net()
+    cpu_env = ScalarCubeEnv(3, device=torch.device("cpu"))
+    torch.set_num_threads(1)
+    cpu_env.get_random_samples([], cpu_net, 30, 2, 1.0)
+    t0 = time.perf_counter()
+    cpu_env.get_random_samples([], cpu_net, 30, 20, 1.0)
+    ref = 600 / (time.perf_counter() - t0)
+    return {"samples_per_s_drop_in_gpu": ours, "samples_per_s_reference_semantics_1_core": ref,
+            "note": "one sample = one scramble prefix with its 12 children evaluated by the net and the ADI target "
+                    "(cube_env.py:177-252); 200 cubes x 30 per call; includes building the Python dicts"}
 
 
 def run_b200_arm(args):

@@ -122,24 +122,26 @@ CUBE_HD void onehot_set(uint32_t* w, int p)
     }
 }
 
-// vector v of a stream of n_seg one-hot segments of width C; col[s] = position of the 1 in
-// segment s (255 = none)
+// The 16-byte vector that starts `off` elements into segment `seg` of a stream of one-hot
+// segments of width C; col[s] = position of the 1 in segment s (255 = none).  A vector touches at
+// most two segments (V <= C).  Branch-free: onehot_set ignores positions outside [0, V), and a
+// 255 column always lands outside; col[] must be readable one entry past the last segment.
+template <int DTYPE, int C>
+CUBE_HD void onehot_vector_at(int seg, int off, const uint8_t* col, uint32_t* w)
+{
+    w[0] = w[1] = w[2] = w[3] = 0u;
+    onehot_set<DTYPE>(w, (int)col[seg] - off);
+    if (C % OneHot<DTYPE>::V != 0) onehot_set<DTYPE>(w, C - off + (int)col[seg + 1]);   // segments straddle vectors
+}
+
+// vector number v of the stream
 template <int DTYPE, int C>
 CUBE_HD void onehot_vector(int v, const uint8_t* col, int n_seg, uint32_t* w)
 {
-    constexpr int V = OneHot<DTYPE>::V;
-    const int e0 = v * V;
+    (void)n_seg;
+    const int e0 = v * OneHot<DTYPE>::V;
     const int seg = e0 / C;
-    const int off = e0 - seg * C;
-    w[0] = w[1] = w[2] = w[3] = 0u;
-    const int c0 = col[seg];
-    const int p0 = c0 - off;
-    if (c0 != 255 && p0 >= 0 && p0 < V) onehot_set<DTYPE>(w, p0);
-    if (off + V > C && seg + 1 < n_seg) {               // the vector runs into the next segment
-        const int c1 = col[seg + 1];
-        const int p1 = C - off + c1;
-        if (c1 != 255 && p1 < V) onehot_set<DTYPE>(w, p1);
-    }
+    onehot_vector_at<DTYPE, C>(seg, e0 - seg * C, col, w);
 }
 
 // column of the 1 for one (row, slot): 3x3x3 returns the column, 2x2x2 returns cubelet | ori << 4

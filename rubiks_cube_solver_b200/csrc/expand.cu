@@ -35,12 +35,18 @@ template <int DTYPE, int C>
 __device__ __forceinline__ void emit_onehot(uint8_t* __restrict__ dst, const uint8_t* col, int n_seg, int tid)
 {
     constexpr int V = OneHot<DTYPE>::V;
+    constexpr int kSegStep = (kThreads * V) / C, kOffStep = (kThreads * V) % C;   // advance per iteration
     const int n_vec = n_seg * C / V;
     int4* out = reinterpret_cast<int4*>(dst);
+    int seg = (tid * V) / C;
+    int off = tid * V - seg * C;
     for (int v = tid; v < n_vec; v += kThreads) {
         uint32_t w[4];
-        onehot_vector<DTYPE, C>(v, col, n_seg, w);
+        onehot_vector_at<DTYPE, C>(seg, off, col, w);
         __stcs(out + v, make_int4((int)w[0], (int)w[1], (int)w[2], (int)w[3]));
+        seg += kSegStep;
+        off += kOffStep;
+        if (off >= C) { off -= C; ++seg; }
     }
 }
 
@@ -100,12 +106,14 @@ expand_kernel(const uint8_t* __restrict__ states, long long n, uint8_t* __restri
         __syncthreads();
 
         if (need_children) {
-            // children[p][a][i] = parent[p][moveDefs[a][i]]: 64 lanes per row, 4 rows in flight
-            const int lane64 = tid & 63;
-            if (lane64 < S) {
-                for (int r = tid >> 6; r < rows; r += kThreads / 64) {
+            // children[p][a][i] = parent[p][moveDefs[a][i]]: one sticker per lane, 64 (3x3x3) or 32
+            // (2x2x2) lanes per row, so 4 / 8 rows are in flight
+            constexpr int kLanes = (S > 32) ? 64 : 32;
+            const int lane = tid & (kLanes - 1);
+            if (lane < S) {
+                for (int r = tid / kLanes; r < rows; r += kThreads / kLanes) {
                     const int p = r / A, a = r - p * A;
-                    s_child[r * S + lane64] = s_par[p * S + s_gather[a * S + lane64]];
+                    s_child[r * S + lane] = s_par[p * S + s_gather[a * S + lane]];
                 }
             }
         }

@@ -467,3 +467,32 @@ def test_greedy_rollout_matches_scalar_env(size, mask):
             k += 1
     pct = rollout.validation(net.to(dev()), size, sample_scramble_count=3, sample_cube_count=4, max_timesteps=6)
     assert len(pct) == 3 and all(0.0 <= p <= 100.0 for p in pct)
+
+
+@pytest.mark.parametrize("size", SIZES)
+def test_mcts_leaf_batch_matches_per_leaf_expand(size):
+    # MCTS.expand (mcts.py:83-113) per leaf with the scalar env vs one batched call
+    import copy as _copy
+    from rubiks_cube_solver_b200 import mcts_batch
+    from oracle.scalar_env import ScalarCubeEnv
+    net = ExactPolicyNet(T.STATE_DIM[size], T.N_ACTIONS[size])
+    rng = np.random.RandomState(4)
+    A = T.N_ACTIONS[size]
+    n = 200
+    leaves = O.scramble(size, rng.randint(A, size=(n, 6)))
+    leaves[0] = O.scramble(size, np.array([[2]]))[0]
+    out = mcts_batch.expand_leaves(net.to(dev()), size, cu(leaves), obs_dtype=torch.float32)
+    cpu_net = ExactPolicyNet(T.STATE_DIM[size], T.N_ACTIONS[size])
+    env = ScalarCubeEnv(size)
+    for i in range(0, n, 7):
+        env.sim_cube = leaves[i].astype(np.int64)
+        env.cube = env._observe(env.sim_cube)
+        value, logits = cpu_net(torch.tensor(env.cube).float())
+        policy = torch.nn.functional.softmax(logits, dim=-1)[0]
+        assert float(out["value"][i]) == float(value[0, 0])
+        assert torch.allclose(out["policy"][i].cpu(), policy, atol=1e-6)
+        for a in range(A):
+            child = _copy.deepcopy(env)
+            _, _, done, _ = child.step(a)
+            assert (out["children"][i, a].cpu().numpy() == child.sim_cube).all() and bool(out["done"][i, a]) == done
+    assert bool(out["done"][0, 3])
