@@ -66,6 +66,156 @@ CUBE_HD bool scramble_finish(CubieState& st, int tid, const uint32_t* s_clut, co
     return ok;
 }
 
+
+// ---- K1p: fused scramble, two moves per table row --------------------------------------------
+// The pair table lives in shared memory as [row][vec][lane slot] 16-byte vectors, 256 bytes per
+// row: 3x3x3 rows are two vectors (P, Q) x 8 lane slots, 2x2x2 rows one vector x 16 lane slots.
+// A lane only ever reads its own slot, so the 128-bit loads of a quarter warp touch eight
+// different 16-byte bank groups whatever rows the lanes ask for: no bank conflicts by construction.
+// `lanereg` = the lane's slot offset in byte 0 (bytes 1..3 zero); a row address is then ONE byte
+// permute: byte 1 <- the pair index, byte 0 <- the slot offset.
+struct CubeVec4 { uint32_t x, y, z, w; };
+
+CUBE_HD CubeVec4 cube_ld128(const uint8_t* p)
+{
+#if defined(__CUDA_ARCH__)
+    const uint4 v = *reinterpret_cast<const uint4*>(p);
+    return CubeVec4{v.x, v.y, v.z, v.w};
+#else
+    CubeVec4 v;
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(p);
+    v.x = q[0]; v.y = q[1]; v.z = q[2]; v.w = q[3];
+    return v;
+#endif
+}
+
+template <int SIZE>
+CUBE_HD uint32_t pair_lanereg(int lane)
+{
+    return (uint32_t)(lane & (SIZE == 3 ? 7 : 15)) << 4;
+}
+
+// fill the shared-memory image from kPairWords{3,2}; thread `t` of `nthreads`
+template <int SIZE>
+CUBE_HD void pair_table_fill(uint8_t* s_ptbl, int t, int nthreads)
+{
+    const uint32_t* src = (SIZE == 3) ? kPairWords3 : kPairWords2;
+    for (int i = t; i < CUBE_PAIR_ROWS * 16; i += nthreads) {
+        const int row = i >> 4, slot = i & 15;
+        const uint32_t* v = src + ((SIZE == 3) ? (row * 2 + (slot >> 3)) * 4 : row * 4);
+        uint32_t* d = reinterpret_cast<uint32_t*>(s_ptbl) + i * 4;
+        d[0] = v[0]; d[1] = v[1]; d[2] = v[2]; d[3] = v[3];
+    }
+}
+
+// two face turns: one row of the pair table (gen_tables.py pair_words_3 / pair_words_2)
+template <int SIZE>
+CUBE_HD void pair_apply(CubieState& s, const uint8_t* s_ptbl, uint32_t addr)
+{
+    const CubeVec4 P = cube_ld128(s_ptbl + addr);
+    const uint32_t n0 = cube_prmt(s.c0, s.c1, P.x) + P.y;
+    const uint32_t n1 = cube_prmt(s.c0, s.c1, cube_hi16(P.x)) + P.z;
+    s.c0 = n0; s.c1 = n1;
+    if (SIZE == 3) {
+        const CubeVec4 Q = cube_ld128(s_ptbl + addr + 128);
+        const uint32_t t0 = cube_prmt(s.e1, s.e2, Q.x);
+        const uint32_t t1 = cube_prmt(s.e0, s.e2, Q.y);
+        const uint32_t t2 = cube_prmt(s.e0, s.e1, Q.z);
+        const uint32_t m0 = cube_prmt(s.e0, t0, cube_hi16(Q.x)) ^ (P.w & 0x10101010u);
+        const uint32_t m1 = cube_prmt(s.e1, t1, cube_hi16(Q.y)) ^ Q.w;
+        const uint32_t m2 = cube_prmt(s.e2, t2, cube_hi16(Q.z)) ^ (P.w & 0x20202020u);
+        s.e0 = m0; s.e1 = m1; s.e2 = m2;
+    }
+}
+
+// Moves of the tile are a flat byte image (row `row` at byte row*depth, any alignment; readable
+// up to 8 bytes past the last row).  A pair adds at most 2 to a twist field, so 15 pairs
+// (depth <= 30) never need a fold; deeper sequences fold every 10 pairs (<= 10 + 20 stays < 32).
+template <int SIZE>
+CUBE_HD void scramble_pairs_run(CubieState& st, int row, int depth, const uint8_t* s_moves, const uint8_t* s_ptbl,
+                                uint32_t lanereg)
+{
+    const uint32_t* mw = reinterpret_cast<const uint32_t*>(s_moves);
+    const uint32_t r = (uint32_t)row * (uint32_t)depth;
+    const uint32_t wi = r >> 2, sh = (r & 3u) << 3;
+    const int nfull = depth >> 2, tail = depth & 3;
+    uint32_t lo = mw[wi];
+    auto word = [&](int j) {
+        const uint32_t hi = mw[wi + j + 1];
+        const uint32_t y = cube_funnel_r(lo, hi, sh) * (uint32_t)(CUBE_PAIR_BASE + 256);   // bytes 1, 3 = pair rows
+        lo = hi;
+        pair_apply<SIZE>(st, s_ptbl, cube_prmt(y, lanereg, 0x5514u));
+        pair_apply<SIZE>(st, s_ptbl, cube_prmt(y, lanereg, 0x5534u));
+    };
+    if (depth <= 30) {                                   // uniform over the grid
+#pragma unroll 2
+        for (int j = 0; j < nfull; ++j) word(j);
+    } else {
+        for (int j0 = 0; j0 < nfull; j0 += 5) {
+            const int j1 = (j0 + 5 < nfull) ? j0 + 5 : nfull;
+            for (int j = j0; j < j1; ++j) word(j);
+            st.c0 = cubie_fold_twist(st.c0);
+            st.c1 = cubie_fold_twist(st.c1);
+        }
+    }
+    if (tail) {                                          // last 1..3 moves, padded with the no-move index
+        const uint32_t keep = (1u << (8 * tail)) - 1u;
+        const uint32_t w = (cube_funnel_r(lo, mw[wi + nfull + 1], sh) & keep) | (0x0c0c0c0cu & ~keep);
+        const uint32_t y = w * (uint32_t)(CUBE_PAIR_BASE + 256);
+        pair_apply<SIZE>(st, s_ptbl, cube_prmt(y, lanereg, 0x5514u));
+        if (tail == 3) pair_apply<SIZE>(st, s_ptbl, cube_prmt(y, lanereg, 0x5534u));
+    }
+}
+
+// reduce, judge, expand to stickers and store the row into a 64-row shared output tile.
+// 3x3x3: `row`'s parity must be uniform over the warp (odd rows sit two bytes off the word grid
+// and use the pre-shifted assembly), so the two warps of a pair take the even and the odd rows.
+template <int SIZE>
+CUBE_HD bool scramble_pairs_finish(CubieState& st, int row, const uint32_t* s_clut, const uint32_t* s_elut, uint8_t* s_out)
+{
+    st.c0 = cubie_reduce_twist(st.c0);
+    st.c1 = cubie_reduce_twist(st.c1);
+    const bool ok = cubie_is_identity<SIZE>(st);
+    uint32_t L[20];
+    const uint32_t c0 = st.c0 * 4u, c1 = st.c1 * 4u;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        L[q] = cube_lut_at(s_clut, cube_prmt(c0, 0u, 0x4440u + q));
+        L[4 + q] = cube_lut_at(s_clut, cube_prmt(c1, 0u, 0x4440u + q));
+    }
+    if (SIZE == 3) {
+        const uint32_t e0 = st.e0 * 4u, e1 = st.e1 * 4u, e2 = st.e2 * 4u;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            L[8 + q] = cube_lut_at(s_elut, cube_prmt(e0, 0u, 0x4440u + q));
+            L[12 + q] = cube_lut_at(s_elut, cube_prmt(e1, 0u, 0x4440u + q));
+            L[16 + q] = cube_lut_at(s_elut, cube_prmt(e2, 0u, 0x4440u + q));
+        }
+        uint32_t w[13], h;
+        uint8_t* rowp = s_out + 54 * row;
+        if (row & 1) {
+            cube_assemble3_odd(L, w, &h);
+            *reinterpret_cast<uint16_t*>(rowp) = (uint16_t)h;
+            uint32_t* wb = reinterpret_cast<uint32_t*>(rowp + 2);
+#pragma unroll
+            for (int j = 0; j < 13; ++j) wb[j] = w[j];
+        } else {
+            cube_assemble3_even(L, w, &h);
+            uint32_t* wb = reinterpret_cast<uint32_t*>(rowp);
+#pragma unroll
+            for (int j = 0; j < 13; ++j) wb[j] = w[j];
+            *reinterpret_cast<uint16_t*>(rowp + 52) = (uint16_t)h;
+        }
+    } else {
+        uint32_t w[6];
+        cube_assemble2(L, w);
+        uint64_t* rowp = reinterpret_cast<uint64_t*>(s_out + 24 * row);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) rowp[j] = (uint64_t)w[2 * j] | ((uint64_t)w[2 * j + 1] << 32);
+    }
+    return ok;
+}
+
 // ---- K2: one face turn of a sticker row in shared memory ------------------------------------
 template <int SIZE>
 CUBE_HD void walk_turn(uint8_t* row, uint32_t m, const uint32_t* s_cyc)

@@ -224,6 +224,67 @@ def packed_words_2(m):
     return [w[0] | w[1] << 16, w[2]]
 
 
+
+# ---- pair tables: two face turns per table row (fused scramble kernel K1p) ---------------
+# Row p = m0 + 13 * m1 applies m0 and then m1 (index 12 = no move), so a byte pair of the move
+# stream is one table lookup:  new[q] = old[src[q]] + delta[q]  with src = src_m0 o src_m1 and
+# delta[q] = delta_m0[src_m1[q]] + delta_m1[q] (twists mod 3, flips mod 2).
+PAIR_BASE = 13
+PAIR_ROWS = PAIR_BASE * PAIR_BASE
+
+
+def _ident_or(table, m, n):
+    return list(table[m]) if m < len(table) else list(range(n))
+
+
+def _zero_or(table, m, n):
+    return list(table[m]) if m < len(table) else [0] * n
+
+
+def compose(src_t, rot_t, m0, m1, n, mod):
+    s0, r0 = _ident_or(src_t, m0, n), _zero_or(rot_t, m0, n)
+    s1, r1 = _ident_or(src_t, m1, n), _zero_or(rot_t, m1, n)
+    return [s0[s1[q]] for q in range(n)], [(r0[s1[q]] + r1[q]) % mod for q in range(n)]
+
+
+def pair_words_3(p):
+    """8 words of one 3x3x3 pair row, as the kernel loads them (two 16-byte vectors):
+    P = [selC0 | selC1 << 16, T0, T1, F]      c0' = prmt(c0, c1, selC0) + T0, c1' likewise with T1;
+                                              F = flips of e0 at bit 4 | flips of e2 at bit 5
+    Q = [st0 | so0 << 16, st1 | so1 << 16, st2 | so2 << 16, F1]
+        t_k = prmt(e_x, e_y, st_k) gathers the bytes output register k takes from the two OTHER
+        registers ((x, y) = (1,2), (0,2), (0,1)); e_k' = prmt(e_k, t_k, so_k) ^ flips; F1 = flips of
+        e1 at bit 4.  An edge is flipped when bits 4 and 5 of its byte differ."""
+    m0, m1 = p % PAIR_BASE, p // PAIR_BASE
+    cs, cr = compose(C_SRC_3, C_ROT_3, m0, m1, 8, 3)
+    es, er = compose(E_SRC_3, E_ROT_3, m0, m1, 12, 2)
+    P = [_sel(cs[0:4]) | _sel(cs[4:8]) << 16,
+         _bytes([r << 3 for r in cr[0:4]]), _bytes([r << 3 for r in cr[4:8]]),
+         _bytes([r << 4 for r in er[0:4]]) | _bytes([r << 5 for r in er[8:12]])]
+    Q = []
+    for k, (x, y) in enumerate(((1, 2), (0, 2), (0, 1))):
+        st, so = [], []
+        for i in range(4):
+            s = es[4 * k + i]
+            if s // 4 == k:
+                st.append(0)
+                so.append(s - 4 * k)
+            else:
+                st.append(s - 4 * x if s // 4 == x else 4 + s - 4 * y)
+                so.append(4 + i)
+        Q.append(_sel(st) | _sel(so) << 16)
+    Q.append(_bytes([r << 4 for r in er[4:8]]))
+    return P + Q
+
+
+def pair_words_2(p):
+    """4 words of one 2x2x2 pair row: [selC0 | selC1 << 16, T0, T1, 0]; indices 6..12 = no move."""
+    m0, m1 = p % PAIR_BASE, p // PAIR_BASE
+    cs, cr = compose(C_SRC_2, C_ROT_2, m0, m1, 8, 3)
+    return [_sel(cs[0:4]) | _sel(cs[4:8]) << 16,
+            _bytes([r << 3 for r in cr[0:4]]), _bytes([r << 3 for r in cr[4:8]]), 0]
+
+
 def fold_twist(c):
     return (c & 0x1f1f1f1f) + ((c >> 2) & 0x38383838)
 
@@ -305,6 +366,66 @@ def assemble_fn(name, src, n_words):
     return "".join(lines)
 
 
+
+def _prmt_expr(ops):
+    """Fewest byte permutes that put ops[i] = (operand, byte) into output byte i (None = don't care).
+    Operands are C expressions (L[slot] or an immediate); at most four distinct ones."""
+    regs = []
+    for o in ops:
+        if o is not None and o[0] not in regs:
+            regs.append(o[0])
+
+    def sel(pair, want, passthrough=None):
+        v = 0
+        for i, o in enumerate(want):
+            if o is None:
+                nb = 0
+            elif passthrough is not None and o[0] not in pair:
+                nb = passthrough[i]
+            else:
+                nb = (0 if o[0] == pair[0] else 4) + o[1]
+            v |= nb << (4 * i)
+        return v
+
+    if len(regs) <= 2:
+        pair = (regs + regs + ["0u"])[:2]
+        return "cube_prmt(%s, %s, 0x%04xu)" % (pair[0], pair[1], sel(pair, ops)), 1
+    if len(regs) == 3:
+        # t holds the bytes of regs[0:2] in place, then regs[2] fills the rest
+        pair = regs[:2]
+        lo = [o if (o is not None and o[0] in pair) else None for o in ops]
+        t = "cube_prmt(%s, %s, 0x%04xu)" % (pair[0], pair[1], sel(pair, lo))
+        final = 0
+        for i, o in enumerate(ops):
+            final |= (i if (o is None or o[0] in pair) else 4 + o[1]) << (4 * i)
+        return "cube_prmt(%s, %s, 0x%04xu)" % (t, regs[2], final), 2
+    lo_pair, hi_pair = regs[:2], regs[2:]
+    lo = [o if (o is not None and o[0] in lo_pair) else None for o in ops]
+    hi = [o if (o is not None and o[0] in hi_pair) else None for o in ops]
+    final = sum(((i if (ops[i] is None or ops[i][0] in lo_pair) else 4 + i) << (4 * i)) for i in range(4))
+    return ("cube_prmt(cube_prmt(%s, %s, 0x%04xu), cube_prmt(%s, %s, 0x%04xu), 0x%04xu)"
+            % (lo_pair[0], lo_pair[1], sel(lo_pair, lo), hi_pair[0], hi_pair[1], sel(hi_pair, hi), final)), 3
+
+
+def assemble_row_fn(name, src, first, n_words, half_at):
+    """Straight-line code for one alignment of a 54-byte row in shared memory: w[j] = stickers
+    first+4j .. first+4j+3 and *h = the two stickers half_at, half_at+1 (low 16 bits)."""
+    def op(s_):
+        if src[s_][0] == "const":
+            return ("0x%02xu" % src[s_][1], 0)
+        return ("L[%d]" % src[s_][0], src[s_][1])
+    lines = ["CUBE_HD void %s(const uint32_t* L, uint32_t* w, uint32_t* h)\n{\n" % name]
+    total = 0
+    for j in range(n_words):
+        e, k = _prmt_expr([op(first + 4 * j + b) for b in range(4)])
+        total += k
+        lines.append("    w[%d] = %s;\n" % (j, e))
+    e, k = _prmt_expr([op(half_at), op(half_at + 1), None, None])
+    total += k
+    lines.append("    *h = %s;\n}   // %d byte permutes\n\n" % (e, total))
+    return "".join(lines)
+
+
 def gather_words_fn(name, moves, n_words):
     """Straight-line code: c = child `a` of the parent row held as words p[]; every child word is a
     byte gather from at most four parent words (compile-time PRMT selectors)."""
@@ -372,6 +493,12 @@ def render():
     o.append(_c_array("uint32_t", "kMoveWords3", [v for r in t3 for v in r]))
     o.append("// [word][move] : A = selC0 | selC1 << 16, B = dC0 (dC1 == 2*B mod 3)\n")
     o.append(_c_array("uint32_t", "kMoveWords2", [v for r in t2 for v in r]))
+    o.append("#define CUBE_PAIR_BASE %d    // pair row = m0 + CUBE_PAIR_BASE * m1 (m0 first; index 12 = no move)\n" % PAIR_BASE)
+    o.append("#define CUBE_PAIR_ROWS %d\n" % PAIR_ROWS)
+    o.append("// [row][8]: P = selC0|selC1<<16, T0, T1, F(e0 bit 4 | e2 bit 5); Q = st0|so0<<16, st1|so1<<16, st2|so2<<16, F1\n")
+    o.append(_c_array("uint32_t", "kPairWords3", [v for p in range(PAIR_ROWS) for v in pair_words_3(p)]))
+    o.append("// [row][4]: selC0|selC1<<16, T0, T1, 0\n")
+    o.append(_c_array("uint32_t", "kPairWords2", [v for p in range(PAIR_ROWS) for v in pair_words_2(p)]))
     o.append("// colour LUTs: index = cubie byte (piece | twist << 3 corners; piece | a << 4 | b << 5 edges, flip = a ^ b)\n")
     o.append(_c_array("uint32_t", "kCornerColour3", C_LUT_3))
     o.append(_c_array("uint32_t", "kEdgeColour3", E_LUT_3))
@@ -382,6 +509,10 @@ def render():
     o.append("#ifdef CUBE_HD\n")
     o.append(assemble_fn("cube_assemble3", src3, 14))
     o.append(assemble_fn("cube_assemble2", src2, 6))
+    o.append("// the same row for the two alignments of a 54-byte row on the word grid (K1p): even rows start on\n"
+             "// a word (13 words + trailing half), odd rows two bytes later (leading half + 13 words)\n")
+    o.append(assemble_row_fn("cube_assemble3_even", src3, 0, 13, 52))
+    o.append(assemble_row_fn("cube_assemble3_odd", src3, 2, 13, 0))
     o.append("// sticker positions of 2x2x2 slot `pos` (py222 pieceDefs), usable as compile-time constants\n")
     o.append("CUBE_HD constexpr int cube_piece_def2(int pos, int k)\n{\n    constexpr int t[21] = {%s};\n"
              "    return t[pos * 3 + k];\n}\n\n" % ", ".join(str(v) for r in PIECE_DEFS_2 for v in r))
@@ -458,6 +589,51 @@ def emulate_2(seq):
     return [(C_LUT_2[regs[src[s][0]]] >> (8 * src[s][1])) & 255 for s in range(24)]
 
 
+
+def emulate_pairs_3(seq):
+    """The K1p register algorithm: pairs of moves through pair_words_3, odd tail padded with 12."""
+    c0, c1, e0, e1, e2 = 0x03020100, 0x07060504, 0x03020100, 0x07060504, 0x0b0a0908
+    seq = list(seq) + [12] * (len(seq) % 2)
+    for i in range(0, len(seq), 2):
+        P0, T0, T1, F, Q0, Q1, Q2, F1 = pair_words_3(seq[i] + PAIR_BASE * seq[i + 1])
+        n0, n1 = prmt(c0, c1, P0) + T0, prmt(c0, c1, P0 >> 16) + T1
+        if (i // 2) % 10 == 9:
+            n0, n1 = fold_twist(n0), fold_twist(n1)
+        assert all(((n >> 8 * k) & 255) >> 3 <= 31 for n in (n0, n1) for k in range(4)) and n0 < 2 ** 32 and n1 < 2 ** 32
+        t0, t1, t2 = prmt(e1, e2, Q0), prmt(e0, e2, Q1), prmt(e0, e1, Q2)
+        m0 = prmt(e0, t0, Q0 >> 16) ^ (F & 0x10101010)
+        m1 = prmt(e1, t1, Q1 >> 16) ^ F1
+        m2 = prmt(e2, t2, Q2 >> 16) ^ (F & 0x20202020)
+        c0, c1, e0, e1, e2 = n0, n1, m0, m1, m2
+    regs = [(c0 >> 8 * i) & 255 for i in range(4)] + [(c1 >> 8 * i) & 255 for i in range(4)]
+    regs = [(b & 7) | (((b >> 3) % 3) << 3) for b in regs]
+    regs += [(r >> 8 * i) & 255 for r in (e0, e1, e2) for i in range(4)]
+    src = sticker_sources([CORNER_SLOTS_3, EDGE_SLOTS_3], 54, {4 + 9 * f: f for f in range(6)})
+    out = []
+    for s in range(54):
+        if src[s][0] == "const":
+            out.append(src[s][1])
+        else:
+            slot, k = src[s]
+            lut = C_LUT_3 if slot < 8 else E_LUT_3
+            out.append((lut[regs[slot]] >> (8 * k)) & 255)
+    return out
+
+
+def emulate_pairs_2(seq):
+    c0, c1 = 0x03020100, 0x07060504
+    seq = list(seq) + [12] * (len(seq) % 2)
+    for i in range(0, len(seq), 2):
+        P0, T0, T1, _ = pair_words_2(seq[i] + PAIR_BASE * seq[i + 1])
+        c0, c1 = prmt(c0, c1, P0) + T0, prmt(c0, c1, P0 >> 16) + T1
+        if (i // 2) % 10 == 9:
+            c0, c1 = fold_twist(c0), fold_twist(c1)
+    regs = [(c0 >> 8 * i) & 255 for i in range(4)] + [(c1 >> 8 * i) & 255 for i in range(4)]
+    regs = [(b & 7) | (((b >> 3) % 3) << 3) for b in regs]
+    src = sticker_sources([CORNER_SLOTS_2], 24, {})
+    return [(C_LUT_2[regs[src[s][0]]] >> (8 * src[s][1])) & 255 for s in range(24)]
+
+
 def selftest(n=300, depth=37):
     rng = np.random.RandomState(0)
     for _ in range(n):
@@ -466,11 +642,22 @@ def selftest(n=300, depth=37):
         for m in seq:
             s = s[MOVES_3[m]]
         assert list(s) == emulate_3(seq), "3x3x3 cubie model disagrees with sticker gathers"
+        assert list(s) == emulate_pairs_3(seq), "3x3x3 pair tables disagree with sticker gathers"
         seq = rng.randint(6, size=depth)
         s = np.repeat(np.arange(6), 4)
         for m in seq:
             s = s[MOVES_2[m]]
         assert list(s) == emulate_2(seq), "2x2x2 cubie model disagrees with sticker gathers"
+        assert list(s) == emulate_pairs_2(seq), "2x2x2 pair tables disagree with sticker gathers"
+    for _ in range(60):                                   # the no-move index inside a sequence
+        for moves, n_act, per_face, emu in ((MOVES_3, 12, 9, emulate_pairs_3), (MOVES_2, 6, 4, emulate_pairs_2)):
+            seq = rng.randint(n_act + 1, size=depth)
+            seq[seq == n_act] = 12
+            s = np.repeat(np.arange(6), per_face)
+            for m in seq:
+                if m < n_act:
+                    s = s[moves[m]]
+            assert list(s) == emu(seq), "pair tables mishandle the no-move index"
     # cycles reproduce the gather rows
     for moves, cycles, n_s in ((MOVES_3, CYCLES_3, 54), (MOVES_2, CYCLES_2, 24)):
         for m in range(len(moves)):

@@ -17,6 +17,7 @@
 // different sector per lane).  Several CTAs per SM overlap load, compute and store.
 // The kernel is bound by the ALU pipe (PRMT/LOP3) and the shared-memory pipe (six
 // table words per move), not by HBM -- see DESIGN.md.
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include "cube_bulk.cuh"
 #include "cube_kernels.h"
@@ -138,6 +139,113 @@ scramble_tile_kernel(const uint8_t* __restrict__ moves, long long n, long long t
     if (full && tid == 0) bulk::wait_read_all();          // shared memory must outlive the copy's reads
 }
 
+
+// ---- K1p: persistent pair-table kernel (the default for depth 1..kMaxPairDepth) ----------------
+// One CTA per SM, up to 16 warp pairs.  Every warp pair owns a private pipeline over tiles of 64
+// instances: the tile's move bytes arrive by one bulk copy (double-buffered: tile i+1 is in flight
+// while tile i is computed), each lane walks its own instance through the PAIR table (one
+// conflict-free 2 x 128-bit row per two moves, see cube_threads.cuh), the 64 sticker rows are
+// assembled in a double-buffered output tile and leave by one bulk store.  The only
+// synchronisation is a 64-thread named barrier per tile; the 40 KB table is loaded once per CTA.
+constexpr int kPairTile = 64;
+constexpr int kMaxPairs = 16;
+constexpr int kMaxPairDepth = 96;
+constexpr int kPairTableBytes = CUBE_PAIR_ROWS * 256;
+
+template <int SIZE>
+struct PairSmem {
+    using G = CubeGeom<SIZE>;
+    static constexpr int kTable = 0;
+    static constexpr int kCornerLut = kPairTableBytes;
+    static constexpr int kEdgeLut = kCornerLut + 32 * 4;
+    static constexpr int kPerPair = kEdgeLut + 64 * 4;
+    static constexpr int kOutBytes = kPairTile * G::S;                // 3456 / 1536: multiples of 16
+    __host__ __device__ static constexpr int move_stride(int depth) { return kPairTile * depth + 16; }
+    __host__ __device__ static constexpr int per_pair(int depth) { return 32 + 2 * kOutBytes + 2 * move_stride(depth); }
+    // never below 65 792 bytes: a garbage move byte (> 12) makes a garbage pair row (<= 255) whose two
+    // vectors must still be inside the CTA's allocation (255 * 256 + 240 + 128 + 16)
+    __host__ __device__ static constexpr int bytes(int depth, int pairs)
+    {
+        return kPerPair + pairs * per_pair(depth) < 65792 ? 65792 : kPerPair + pairs * per_pair(depth);
+    }
+};
+
+__device__ __forceinline__ void pair_barrier(int id)
+{
+    asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory");
+}
+
+template <int SIZE>
+__global__ void __launch_bounds__(kMaxPairs * 64, 1)
+scramble_pairs_kernel(const uint8_t* __restrict__ moves, long long n_tiles, int depth, uint8_t* __restrict__ out,
+                      uint8_t* __restrict__ solved, float* __restrict__ reward, unsigned long long* __restrict__ counters)
+{
+    using G = CubeGeom<SIZE>;
+    using L = PairSmem<SIZE>;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, pair = warp >> 1, par = warp & 1;
+    const int pairs = blockDim.x >> 6;
+    uint8_t* s_ptbl = smem + L::kTable;
+    uint32_t* s_clut = reinterpret_cast<uint32_t*>(smem + L::kCornerLut);
+    uint32_t* s_elut = reinterpret_cast<uint32_t*>(smem + L::kEdgeLut);
+    uint8_t* mine = smem + L::kPerPair + pair * L::per_pair(depth);
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(mine);             // [2]
+    uint8_t* s_out = mine + 32;                                       // [2][kOutBytes]
+    uint8_t* s_moves = s_out + 2 * L::kOutBytes;                      // [2][move_stride]
+    const int mstride = L::move_stride(depth);
+    const uint32_t move_bytes = (uint32_t)(kPairTile * depth);
+    const bool leader = (par == 0) && (lane == 0);
+
+    pair_table_fill<SIZE>(s_ptbl, tid, blockDim.x);
+    if (tid < 32) s_clut[tid] = (SIZE == 3) ? kCornerColour3[tid] : kCornerColour2[tid];
+    if (tid >= 64 && tid < 128) s_elut[tid - 64] = (SIZE == 3) ? kEdgeColour3[tid - 64] : 0u;
+    if (leader) { bulk::mbar_init(&s_bar[0], 1); bulk::mbar_init(&s_bar[1], 1); }
+    __syncthreads();
+
+    const long long stride = (long long)gridDim.x * pairs;
+    long long tile = (long long)blockIdx.x * pairs + pair;
+    if (leader && tile < n_tiles) {
+        bulk::mbar_expect_tx(&s_bar[0], move_bytes);
+        bulk::load(s_moves, moves + tile * move_bytes, move_bytes, &s_bar[0]);
+    }
+    // 3x3x3: the pair's first warp takes the even rows, the second the odd rows (warp-uniform row
+    // alignment, lanes 27 words apart: conflict-free stores); 2x2x2: rows 0-31 / 32-63
+    const int row = (SIZE == 3) ? 2 * lane + par : lane + 32 * par;
+    const uint32_t lanereg = pair_lanereg<SIZE>(lane);
+    unsigned long long n_solved = 0;
+
+    for (int it = 0; tile < n_tiles; ++it, tile += stride) {
+        const int buf = it & 1;
+        if (leader && tile + stride < n_tiles) {                      // prefetch the next tile's moves
+            bulk::mbar_expect_tx(&s_bar[buf ^ 1], move_bytes);
+            bulk::load(s_moves + (buf ^ 1) * mstride, moves + (tile + stride) * move_bytes, move_bytes, &s_bar[buf ^ 1]);
+        }
+        bulk::mbar_wait(&s_bar[buf], (uint32_t)(it >> 1) & 1u);
+
+        CubieState st;
+        cubie_init(st);
+        scramble_pairs_run<SIZE>(st, row, depth, s_moves + buf * mstride, s_ptbl, lanereg);
+        const bool ok = scramble_pairs_finish<SIZE>(st, row, s_clut, s_elut, s_out + buf * L::kOutBytes);
+
+        const long long inst = tile * kPairTile + row;
+        if (solved) solved[inst] = ok ? 1 : 0;
+        if (reward) reward[inst] = ok ? 1.0f : -1.0f;
+        const unsigned bal = __ballot_sync(0xffffffffu, ok);
+        if (lane == 0) n_solved += (unsigned)__popc(bal);
+
+        bulk::fence_smem_writes();                                    // rows -> visible to the copy engine
+        if (leader) bulk::wait_read_all();                            // the previous store has released its buffer
+        pair_barrier(pair);
+        if (leader) {
+            bulk::store(out + tile * (long long)L::kOutBytes, s_out + buf * L::kOutBytes, (uint32_t)L::kOutBytes);
+            bulk::commit();
+        }
+    }
+    if (lane == 0 && n_solved && counters) atomicAdd(&counters[0], n_solved);
+    if (blockIdx.x == 0 && tid == 0 && counters) atomicAdd(&counters[1], (unsigned long long)(n_tiles * kPairTile));
+    if (leader) bulk::wait_read_all();                                // shared memory must outlive the copies' reads
+}
+
 // deep sequences (depth > kMaxStagedDepth): persistent CTAs, moves read straight from global
 template <int SIZE>
 __global__ void __launch_bounds__(kTile, 4)
@@ -187,8 +295,8 @@ scramble_deep_kernel(const uint8_t* __restrict__ moves, long long n, int depth, 
 }
 
 template <int SIZE>
-int launch_one(const uint8_t* moves, long long n, int depth, uint8_t* out, uint8_t* solved, float* reward,
-               unsigned long long* counters, cudaStream_t stream)
+int launch_classic(const uint8_t* moves, long long n, int depth, uint8_t* out, uint8_t* solved, float* reward,
+                   unsigned long long* counters, cudaStream_t stream)
 {
     const bool staged = depth <= kMaxStagedDepth;
     const int smem = ScrambleSmem<SIZE>::bytes(depth, staged);
@@ -220,6 +328,42 @@ int launch_one(const uint8_t* moves, long long n, int depth, uint8_t* out, uint8
         kern<<<(unsigned)grid, kTile, smem, stream>>>(moves, n, depth, out, solved, reward, counters);
     }
     return (int)cudaGetLastError();
+}
+
+constexpr int kSmemLimit = 227 * 1024;
+
+template <int SIZE>
+int launch_one(const uint8_t* moves, long long n, int depth, uint8_t* out, uint8_t* solved, float* reward,
+               unsigned long long* counters, cudaStream_t stream)
+{
+    using L = PairSmem<SIZE>;
+    using G = CubeGeom<SIZE>;
+    long long done = 0;
+    const char* force = getenv("CUBE_SCRAMBLE_CLASSIC");               // A/B switch for profiling
+    if (depth >= 1 && depth <= kMaxPairDepth && n >= kPairTile && !(force && force[0] == '1')) {
+        int pairs = (kSmemLimit - L::kPerPair) / L::per_pair(depth);
+        if (pairs > kMaxPairs) pairs = kMaxPairs;
+        if (pairs >= 2) {
+            const long long n_tiles = n / kPairTile;
+            const int smem = L::bytes(depth, pairs);
+            auto kern = scramble_pairs_kernel<SIZE>;
+            static int configured_smem = -1;
+            if (smem > configured_smem) {
+                cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+                if (e != cudaSuccess) return (int)e;
+                configured_smem = smem;
+            }
+            long long grid = (n_tiles + pairs - 1) / pairs;
+            if (grid > cube::sm_count()) grid = cube::sm_count();
+            kern<<<(unsigned)grid, pairs * 64, smem, stream>>>(moves, n_tiles, depth, out, solved, reward, counters);
+            const cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess) return (int)e;
+            done = n_tiles * kPairTile;
+        }
+    }
+    if (done == n) return 0;
+    return launch_classic<SIZE>(moves + done * depth, n - done, depth, out + done * G::S, solved ? solved + done : nullptr,
+                                reward ? reward + done : nullptr, counters, stream);
 }
 
 }  // namespace

@@ -33,6 +33,31 @@ void scramble_t(const uint8_t* moves, long long n, int depth, uint8_t* out, uint
     }
 }
 
+// K1p: persistent pair-table kernel, one 64-row tile at a time with the kernel's lane -> row map
+template <int SIZE>
+void scramble_pairs_t(const uint8_t* moves, long long n, int depth, uint8_t* out, uint8_t* solved)
+{
+    using G = CubeGeom<SIZE>;
+    const uint32_t* clut = SIZE == 3 ? kCornerColour3 : kCornerColour2;
+    std::vector<uint8_t> tbl(65792 + 256, 0xa5);
+    uint8_t* s_ptbl = tbl.data() + ((16 - (reinterpret_cast<uintptr_t>(tbl.data()) & 15)) & 15);
+    for (int t = 0; t < 96; ++t) pair_table_fill<SIZE>(s_ptbl, t, 96);
+    std::vector<uint8_t> s_moves(64 * depth + 16), s_out(64 * G::S);
+    for (long long base = 0; base + 64 <= n; base += 64) {
+        std::memset(s_moves.data(), 0xee, s_moves.size());
+        std::memcpy(s_moves.data(), moves + base * depth, (size_t)64 * depth);
+        for (int par = 0; par < 2; ++par)
+            for (int lane = 0; lane < 32; ++lane) {
+                const int row = (SIZE == 3) ? 2 * lane + par : lane + 32 * par;
+                CubieState st;
+                cubie_init(st);
+                scramble_pairs_run<SIZE>(st, row, depth, s_moves.data(), s_ptbl, pair_lanereg<SIZE>(lane));
+                solved[base + row] = scramble_pairs_finish<SIZE>(st, row, clut, kEdgeColour3, s_out.data());
+            }
+        std::memcpy(out + base * G::S, s_out.data(), (size_t)64 * G::S);
+    }
+}
+
 template <int SIZE>
 void walk_t(const uint8_t* in, const uint8_t* moves, long long n, int depth, uint8_t* out, uint8_t* solved)
 {
@@ -108,6 +133,10 @@ extern "C" {
 void emul_scramble(int size, const uint8_t* moves, long long n, int depth, uint8_t* out, uint8_t* solved)
 {
     if (size == 3) scramble_t<3>(moves, n, depth, out, solved); else scramble_t<2>(moves, n, depth, out, solved);
+}
+void emul_scramble_pairs(int size, const uint8_t* moves, long long n, int depth, uint8_t* out, uint8_t* solved)
+{
+    if (size == 3) scramble_pairs_t<3>(moves, n, depth, out, solved); else scramble_pairs_t<2>(moves, n, depth, out, solved);
 }
 void emul_walk(int size, const uint8_t* in, const uint8_t* moves, long long n, int depth, uint8_t* out,
                uint8_t* solved)

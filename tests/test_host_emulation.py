@@ -25,6 +25,7 @@ def emul():
     lib = ctypes.CDLL(LIB)
     vp, ll = ctypes.c_void_p, ctypes.c_longlong
     lib.emul_scramble.argtypes = [ctypes.c_int, vp, ll, ctypes.c_int, vp, vp]
+    lib.emul_scramble_pairs.argtypes = [ctypes.c_int, vp, ll, ctypes.c_int, vp, vp]
     lib.emul_walk.argtypes = [ctypes.c_int, vp, vp, ll, ctypes.c_int, vp, vp]
     lib.emul_expand.argtypes = [ctypes.c_int, ctypes.c_int, vp, ll, vp, vp, vp, vp]
     return lib
@@ -54,6 +55,52 @@ def test_scramble_emulation(emul, size, depth):
     assert (solved.astype(bool) == O.is_solved(size, want)).all()
     if depth >= 2 and depth % 2 == 0:
         assert solved[:50].all()
+
+
+@pytest.mark.parametrize("size", (2, 3))
+@pytest.mark.parametrize("depth", (1, 2, 3, 4, 5, 7, 8, 9, 20, 30, 31, 32, 43, 61, 96))
+def test_scramble_pairs_emulation(emul, size, depth):
+    """K1p (two moves per table row, persistent 64-row tiles): rows that return to solved, the
+    no-move index 12 in the stream, odd depths (padded tail pair) and the fold schedule."""
+    rng = np.random.RandomState(depth * 11 + size)
+    n = 192
+    A = T.N_ACTIONS[size]
+    moves = rng.randint(A, size=(n, depth)).astype(np.uint8)
+    if depth >= 2:
+        h = depth // 2
+        moves[:50, h:2 * h] = moves[:50, :h][:, ::-1] ^ 1          # rows that come back to solved
+        if depth % 2:
+            moves[:50, -1] = 12
+    moves[60:90][rng.rand(30, depth) < 0.3] = 12                     # no-move index anywhere
+    out = np.empty((n, T.N_STICKERS[size]), dtype=np.uint8)
+    solved = np.empty(n, dtype=np.uint8)
+    emul.emul_scramble_pairs(size, _p(moves), n, depth, _p(out), _p(solved))
+    want = np.empty_like(out)
+    for i in range(n):                                               # the oracle skips the no-move index
+        row = moves[i][moves[i] != 12]
+        want[i] = O.scramble(size, row[None, :])[0]
+    assert (out == want).all()
+    assert (solved.astype(bool) == O.is_solved(size, want)).all()
+    if depth >= 2:
+        assert solved[:50].all()
+
+
+@pytest.mark.parametrize("size", (2, 3))
+def test_pair_twist_field_never_overflows(size):
+    """K1p adds the composed twist of two moves (0..2 per corner) to a 5-bit field: no fold for
+    depth <= 30 (15 pairs), a fold every 10 pairs beyond.  Worst case of that schedule, exactly."""
+    worst, f = 0, 0
+    for pair in range(1, 16):
+        f += 2
+        worst = max(worst, f)
+    assert worst <= 31                                              # depth <= 30, never folded
+    f, worst, after = 0, 0, 0
+    for word in range(1, 400):                                      # deep: fold after every group of <= 5 words
+        f += 4
+        worst = max(worst, f)
+        if word % 5 == 0:
+            f = after = max(after, max((v & 3) + (v >> 2) for v in range(f + 1)))
+    assert worst <= 31 and after + 4 <= 31                          # the tail word follows a fold
 
 
 @pytest.mark.parametrize("size", (2, 3))
