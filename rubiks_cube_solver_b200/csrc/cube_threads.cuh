@@ -89,6 +89,54 @@ CUBE_HD CubeVec4 cube_ld128(const uint8_t* p)
 #endif
 }
 
+// Where the pair table is read from.  Host (test emulation): a plain pointer.  Device: absolute
+// 32-bit shared-window addresses -- the table sits on a 256-byte boundary of the window, so its
+// base is folded into the pair-row byte (`bias` = base >> 8 in bytes 1 and 3, added by the same
+// multiply-add that forms the row numbers) and the permute's result IS the load address.
+struct PairTableHost {
+    const uint8_t* base;
+    CUBE_HD uint32_t bias() const { return 0u; }
+    CUBE_HD CubeVec4 ld(uint32_t addr, int off) const { return cube_ld128(base + addr + off); }
+};
+#if defined(__CUDACC__)
+struct PairTableShared {
+    uint32_t bias_;                                     // (base >> 8) * 0x01000100
+    __device__ __forceinline__ uint32_t bias() const { return bias_; }
+    __device__ __forceinline__ CubeVec4 ld(uint32_t addr, int off) const
+    {
+        CubeVec4 v;
+        if (off == 0)
+            asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+        else
+            asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+128];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+        return v;
+    }
+};
+#endif
+
+// Colour LUT access of the finishing pass.  Host: pointers.  Device: each LUT sits on a 256-byte
+// boundary of the shared window, so "base | 4 * cubie byte" is ONE byte permute (byte 0 from the
+// scaled cubie register, bytes 1..3 from the base) and the load needs no address arithmetic.
+struct ColourLutHost {
+    const uint32_t* c;
+    const uint32_t* e;
+    CUBE_HD uint32_t corner(uint32_t x4, int q) const { return cube_lut_at(c, cube_prmt(x4, 0u, 0x4440u + q)); }
+    CUBE_HD uint32_t edge(uint32_t x4, int q) const { return cube_lut_at(e, cube_prmt(x4, 0u, 0x4440u + q)); }
+};
+#if defined(__CUDACC__)
+struct ColourLutShared {
+    uint32_t cbase, ebase;                              // shared-window addresses, multiples of 256
+    static __device__ __forceinline__ uint32_t lds32(uint32_t addr)
+    {
+        uint32_t v;
+        asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+        return v;
+    }
+    __device__ __forceinline__ uint32_t corner(uint32_t x4, int q) const { return lds32(cube_prmt(x4, cbase, 0x7650u + q)); }
+    __device__ __forceinline__ uint32_t edge(uint32_t x4, int q) const { return lds32(cube_prmt(x4, ebase, 0x7650u + q)); }
+};
+#endif
+
 template <int SIZE>
 CUBE_HD uint32_t pair_lanereg(int lane)
 {
@@ -109,15 +157,15 @@ CUBE_HD void pair_table_fill(uint8_t* s_ptbl, int t, int nthreads)
 }
 
 // two face turns: one row of the pair table (gen_tables.py pair_words_3 / pair_words_2)
-template <int SIZE>
-CUBE_HD void pair_apply(CubieState& s, const uint8_t* s_ptbl, uint32_t addr)
+template <int SIZE, class TBL>
+CUBE_HD void pair_apply(CubieState& s, const TBL& tbl, uint32_t addr)
 {
-    const CubeVec4 P = cube_ld128(s_ptbl + addr);
+    const CubeVec4 P = tbl.ld(addr, 0);
     const uint32_t n0 = cube_prmt(s.c0, s.c1, P.x) + P.y;
     const uint32_t n1 = cube_prmt(s.c0, s.c1, cube_hi16(P.x)) + P.z;
     s.c0 = n0; s.c1 = n1;
     if (SIZE == 3) {
-        const CubeVec4 Q = cube_ld128(s_ptbl + addr + 128);
+        const CubeVec4 Q = tbl.ld(addr, 128);
         const uint32_t t0 = cube_prmt(s.e1, s.e2, Q.x);
         const uint32_t t1 = cube_prmt(s.e0, s.e2, Q.y);
         const uint32_t t2 = cube_prmt(s.e0, s.e1, Q.z);
@@ -130,66 +178,121 @@ CUBE_HD void pair_apply(CubieState& s, const uint8_t* s_ptbl, uint32_t addr)
 
 // Moves of the tile are a flat byte image (row `row` at byte row*depth, any alignment; readable
 // up to 8 bytes past the last row).  A pair adds at most 2 to a twist field, so 15 pairs
-// (depth <= 30) never need a fold; deeper sequences fold every 10 pairs (<= 10 + 20 stays < 32).
-template <int SIZE>
-CUBE_HD void scramble_pairs_run(CubieState& st, int row, int depth, const uint8_t* s_moves, const uint8_t* s_ptbl,
-                                uint32_t lanereg)
+// (depth <= 30) never need a fold; deeper sequences fold after every 5 words (10 pairs:
+// <= 10 + 20 stays below 32).  DEPTH > 0 fixes the depth at compile time (straight-line code for
+// the reference's default scramble depth, config.yaml:7 sample_scramble_count = 30, and
+// BASELINE config 2's depth 20); DEPTH == 0 takes it from `depth_rt`.
+template <int SIZE, int DEPTH, int NS, class TBL>
+CUBE_HD void scramble_pairs_run(CubieState (&st)[NS], const int (&rows)[NS], int depth_rt, const uint8_t* s_moves,
+                                const TBL& tbl, uint32_t lanereg)
 {
+    // NS instances per lane advance in lockstep (independent dependency chains for the scheduler)
+    const int depth = DEPTH > 0 ? DEPTH : depth_rt;
     const uint32_t* mw = reinterpret_cast<const uint32_t*>(s_moves);
-    const uint32_t r = (uint32_t)row * (uint32_t)depth;
-    const uint32_t wi = r >> 2, sh = (r & 3u) << 3;
     const int nfull = depth >> 2, tail = depth & 3;
-    uint32_t lo = mw[wi];
+    const uint32_t bias = tbl.bias();
+    uint32_t wi[NS], sh[NS], lo[NS];
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+        const uint32_t r = (uint32_t)rows[k] * (uint32_t)depth;
+        wi[k] = r >> 2; sh[k] = (r & 3u) << 3;
+        lo[k] = mw[wi[k]];
+    }
     auto word = [&](int j) {
-        const uint32_t hi = mw[wi + j + 1];
-        const uint32_t y = cube_funnel_r(lo, hi, sh) * (uint32_t)(CUBE_PAIR_BASE + 256);   // bytes 1, 3 = pair rows
-        lo = hi;
-        pair_apply<SIZE>(st, s_ptbl, cube_prmt(y, lanereg, 0x5514u));
-        pair_apply<SIZE>(st, s_ptbl, cube_prmt(y, lanereg, 0x5534u));
+        uint32_t y[NS];
+#pragma unroll
+        for (int k = 0; k < NS; ++k) {
+            const uint32_t hi = mw[wi[k] + j + 1];
+            y[k] = cube_funnel_r(lo[k], hi, sh[k]) * (uint32_t)(CUBE_PAIR_BASE + 256) + bias;   // bytes 1, 3 = pair rows
+            lo[k] = hi;
+        }
+#pragma unroll
+        for (int k = 0; k < NS; ++k) pair_apply<SIZE>(st[k], tbl, cube_prmt(y[k], lanereg, 0x5514u));
+#pragma unroll
+        for (int k = 0; k < NS; ++k) pair_apply<SIZE>(st[k], tbl, cube_prmt(y[k], lanereg, 0x5534u));
     };
-    if (depth <= 30) {                                   // uniform over the grid
-#pragma unroll 2
+    auto fold = [&]() {
+#pragma unroll
+        for (int k = 0; k < NS; ++k) {
+            st[k].c0 = cubie_fold_twist(st[k].c0);
+            st[k].c1 = cubie_fold_twist(st[k].c1);
+        }
+    };
+    if (DEPTH > 0) {
+#pragma unroll
+        for (int j = 0; j < DEPTH / 4; ++j) {
+            word(j);
+            if (DEPTH > 30 && (j % 5 == 4 || j == DEPTH / 4 - 1)) fold();
+        }
+    } else if (depth <= 30) {                            // uniform over the grid
         for (int j = 0; j < nfull; ++j) word(j);
     } else {
         for (int j0 = 0; j0 < nfull; j0 += 5) {
             const int j1 = (j0 + 5 < nfull) ? j0 + 5 : nfull;
             for (int j = j0; j < j1; ++j) word(j);
-            st.c0 = cubie_fold_twist(st.c0);
-            st.c1 = cubie_fold_twist(st.c1);
+            fold();
         }
     }
     if (tail) {                                          // last 1..3 moves, padded with the no-move index
         const uint32_t keep = (1u << (8 * tail)) - 1u;
-        const uint32_t w = (cube_funnel_r(lo, mw[wi + nfull + 1], sh) & keep) | (0x0c0c0c0cu & ~keep);
-        const uint32_t y = w * (uint32_t)(CUBE_PAIR_BASE + 256);
-        pair_apply<SIZE>(st, s_ptbl, cube_prmt(y, lanereg, 0x5514u));
-        if (tail == 3) pair_apply<SIZE>(st, s_ptbl, cube_prmt(y, lanereg, 0x5534u));
+        uint32_t y[NS];
+#pragma unroll
+        for (int k = 0; k < NS; ++k) {
+            const uint32_t w = (cube_funnel_r(lo[k], mw[wi[k] + nfull + 1], sh[k]) & keep) | (0x0c0c0c0cu & ~keep);
+            y[k] = w * (uint32_t)(CUBE_PAIR_BASE + 256) + bias;
+        }
+#pragma unroll
+        for (int k = 0; k < NS; ++k) pair_apply<SIZE>(st[k], tbl, cube_prmt(y[k], lanereg, 0x5514u));
+        if (tail == 3) {
+#pragma unroll
+            for (int k = 0; k < NS; ++k) pair_apply<SIZE>(st[k], tbl, cube_prmt(y[k], lanereg, 0x5534u));
+        }
     }
+}
+
+CUBE_HD uint32_t cube_shr1(uint32_t x)          // x >> 1 on the FMA pipe
+{
+#if defined(__CUDA_ARCH__)
+    uint32_t r;
+    asm("mul.hi.u32 %0, %1, 2147483648;" : "=r"(r) : "r"(x));
+    return r;
+#else
+    return x >> 1;
+#endif
+}
+
+// edge byte piece | a << 4 | b << 5  ->  piece | (a ^ b) << 4: every (piece, flip) then has ONE
+// entry in the 32-entry colour LUT, one entry per bank, so the lookups never conflict
+CUBE_HD uint32_t cubie_canonical_flip(uint32_t e)
+{
+    return ((cube_shr1(e) & 0x10101010u) ^ e) & 0x1f1f1f1fu;
 }
 
 // reduce, judge, expand to stickers and store the row into a 64-row shared output tile.
 // 3x3x3: `row`'s parity must be uniform over the warp (odd rows sit two bytes off the word grid
 // and use the pre-shifted assembly), so the two warps of a pair take the even and the odd rows.
-template <int SIZE>
-CUBE_HD bool scramble_pairs_finish(CubieState& st, int row, const uint32_t* s_clut, const uint32_t* s_elut, uint8_t* s_out)
+template <int SIZE, class LUT>
+CUBE_HD bool scramble_pairs_finish(CubieState& st, int row, const LUT& lut, uint8_t* s_out)
 {
     st.c0 = cubie_reduce_twist(st.c0);
     st.c1 = cubie_reduce_twist(st.c1);
-    const bool ok = cubie_is_identity<SIZE>(st);
+    bool ok = (st.c0 == 0x03020100u) & (st.c1 == 0x07060504u);
     uint32_t L[20];
     const uint32_t c0 = st.c0 * 4u, c1 = st.c1 * 4u;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        L[q] = cube_lut_at(s_clut, cube_prmt(c0, 0u, 0x4440u + q));
-        L[4 + q] = cube_lut_at(s_clut, cube_prmt(c1, 0u, 0x4440u + q));
+        L[q] = lut.corner(c0, q);
+        L[4 + q] = lut.corner(c1, q);
     }
     if (SIZE == 3) {
-        const uint32_t e0 = st.e0 * 4u, e1 = st.e1 * 4u, e2 = st.e2 * 4u;
+        const uint32_t f0 = cubie_canonical_flip(st.e0), f1 = cubie_canonical_flip(st.e1), f2 = cubie_canonical_flip(st.e2);
+        ok = ok && ((f0 == 0x03020100u) & (f1 == 0x07060504u) & (f2 == 0x0b0a0908u));
+        const uint32_t e0 = f0 * 4u, e1 = f1 * 4u, e2 = f2 * 4u;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            L[8 + q] = cube_lut_at(s_elut, cube_prmt(e0, 0u, 0x4440u + q));
-            L[12 + q] = cube_lut_at(s_elut, cube_prmt(e1, 0u, 0x4440u + q));
-            L[16 + q] = cube_lut_at(s_elut, cube_prmt(e2, 0u, 0x4440u + q));
+            L[8 + q] = lut.edge(e0, q);
+            L[12 + q] = lut.edge(e1, q);
+            L[16 + q] = lut.edge(e2, q);
         }
         uint32_t w[13], h;
         uint8_t* rowp = s_out + 54 * row;
@@ -214,6 +317,22 @@ CUBE_HD bool scramble_pairs_finish(CubieState& st, int row, const uint32_t* s_cl
         for (int j = 0; j < 3; ++j) rowp[j] = (uint64_t)w[2 * j] | ((uint64_t)w[2 * j + 1] << 32);
     }
     return ok;
+}
+
+// verdicts of a 64-row tile from the warp ballots of its two passes (m0 = first, m1 = second).
+// 3x3x3: row 2l+p is bit l of m_p; 2x2x2: row l+32p is bit l of m_p.
+template <int SIZE>
+CUBE_HD uint32_t pair_row_bit(uint32_t m0, uint32_t m1, int row)
+{
+    if (SIZE == 3) return (((row & 1) ? m1 : m0) >> (row >> 1)) & 1u;
+    return (((row & 32) ? m1 : m0) >> (row & 31)) & 1u;
+}
+
+template <int SIZE>
+CUBE_HD uint32_t pair_solved_word(uint32_t m0, uint32_t m1, int k)          // solved bytes of rows 4k .. 4k+3
+{
+    return pair_row_bit<SIZE>(m0, m1, 4 * k) | pair_row_bit<SIZE>(m0, m1, 4 * k + 1) << 8 |
+           pair_row_bit<SIZE>(m0, m1, 4 * k + 2) << 16 | pair_row_bit<SIZE>(m0, m1, 4 * k + 3) << 24;
 }
 
 // ---- K2: one face turn of a sticker row in shared memory ------------------------------------

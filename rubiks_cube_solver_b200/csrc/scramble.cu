@@ -141,109 +141,121 @@ scramble_tile_kernel(const uint8_t* __restrict__ moves, long long n, long long t
 
 
 // ---- K1p: persistent pair-table kernel (the default for depth 1..kMaxPairDepth) ----------------
-// One CTA per SM, up to 16 warp pairs.  Every warp pair owns a private pipeline over tiles of 64
-// instances: the tile's move bytes arrive by one bulk copy (double-buffered: tile i+1 is in flight
-// while tile i is computed), each lane walks its own instance through the PAIR table (one
-// conflict-free 2 x 128-bit row per two moves, see cube_threads.cuh), the 64 sticker rows are
-// assembled in a double-buffered output tile and leave by one bulk store.  The only
-// synchronisation is a 64-thread named barrier per tile; the 40 KB table is loaded once per CTA.
+// One CTA per SM; every WARP owns a private pipeline over tiles of 64 instances and never
+// synchronises with another warp after the prologue.  The tile's move bytes arrive by one bulk copy
+// (double-buffered: tile i+1 is in flight while tile i is computed); each lane walks TWO instances
+// in lockstep through the PAIR table (one conflict-free 2 x 128-bit row per two moves, see
+// cube_threads.cuh) -- rows 2l and 2l+1 for 3x3x3, so that each finishing pass writes rows of one
+// parity (54-byte rows alternate between word-aligned and two bytes off); the 64 sticker rows are
+// assembled in the warp's output tile and leave by one bulk store.  The 43 KB table is loaded once
+// per CTA.  A tile of 64 rows keeps every bulk copy a multiple of 16 bytes for any depth.
 constexpr int kPairTile = 64;
-constexpr int kMaxPairs = 16;
 constexpr int kMaxPairDepth = 96;
 constexpr int kPairTableBytes = CUBE_PAIR_ROWS * 256;
+template <int SIZE> struct PairCfg;
+template <> struct PairCfg<3> { static constexpr int kMaxWarps = 24; };    // 768 threads: 85 registers each
+template <> struct PairCfg<2> { static constexpr int kMaxWarps = 32; };
 
 template <int SIZE>
 struct PairSmem {
     using G = CubeGeom<SIZE>;
-    static constexpr int kTable = 0;
-    static constexpr int kCornerLut = kPairTableBytes;
-    static constexpr int kEdgeLut = kCornerLut + 32 * 4;
-    static constexpr int kPerPair = kEdgeLut + 64 * 4;
+    static constexpr int kTable = 0;                                  // + up to 255 bytes: 256-byte aligned in the window
+    static constexpr int kCornerLut = kPairTableBytes + 256;          // (relative to the aligned table start: + 0)
+    static constexpr int kEdgeLut = kCornerLut + 256;
+    static constexpr int kPerWarp = kEdgeLut + 256;
     static constexpr int kOutBytes = kPairTile * G::S;                // 3456 / 1536: multiples of 16
     __host__ __device__ static constexpr int move_stride(int depth) { return kPairTile * depth + 16; }
-    __host__ __device__ static constexpr int per_pair(int depth) { return 32 + 2 * kOutBytes + 2 * move_stride(depth); }
-    // never below 65 792 bytes: a garbage move byte (> 12) makes a garbage pair row (<= 255) whose two
-    // vectors must still be inside the CTA's allocation (255 * 256 + 240 + 128 + 16)
-    __host__ __device__ static constexpr int bytes(int depth, int pairs)
+    __host__ __device__ static constexpr int per_warp(int depth) { return 16 + kOutBytes + 2 * move_stride(depth); }
+    // never below 65 792 + 256 bytes: a garbage move byte (> 12) makes a garbage pair row (<= 255) whose
+    // two vectors must still be inside the CTA's allocation (255 * 256 + 240 + 128 + 16)
+    __host__ __device__ static constexpr int bytes(int depth, int warps)
     {
-        return kPerPair + pairs * per_pair(depth) < 65792 ? 65792 : kPerPair + pairs * per_pair(depth);
+        return kPerWarp + warps * per_warp(depth) < 66048 ? 66048 : kPerWarp + warps * per_warp(depth);
     }
 };
 
-__device__ __forceinline__ void pair_barrier(int id)
-{
-    asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory");
-}
-
-template <int SIZE>
-__global__ void __launch_bounds__(kMaxPairs * 64, 1)
-scramble_pairs_kernel(const uint8_t* __restrict__ moves, long long n_tiles, int depth, uint8_t* __restrict__ out,
+template <int SIZE, int DEPTH>
+__global__ void __launch_bounds__(PairCfg<SIZE>::kMaxWarps * 32, 1)
+scramble_pairs_kernel(const uint8_t* __restrict__ moves, int n_tiles, int depth_rt, uint8_t* __restrict__ out,
                       uint8_t* __restrict__ solved, float* __restrict__ reward, unsigned long long* __restrict__ counters)
 {
-    using G = CubeGeom<SIZE>;
     using L = PairSmem<SIZE>;
-    extern __shared__ __align__(128) uint8_t smem[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, pair = warp >> 1, par = warp & 1;
-    const int pairs = blockDim.x >> 6;
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    const int depth = DEPTH > 0 ? DEPTH : depth_rt;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int warps = blockDim.x >> 5;
+    // everything is laid out from a 256-byte boundary of the shared window (see PairTableShared)
+    const uint32_t window = bulk::smem_addr(smem_raw);
+    uint8_t* smem = smem_raw + ((256u - (window & 255u)) & 255u);
     uint8_t* s_ptbl = smem + L::kTable;
+    const PairTableShared tbl{(bulk::smem_addr(s_ptbl) >> 8) * 0x01000100u};
     uint32_t* s_clut = reinterpret_cast<uint32_t*>(smem + L::kCornerLut);
     uint32_t* s_elut = reinterpret_cast<uint32_t*>(smem + L::kEdgeLut);
-    uint8_t* mine = smem + L::kPerPair + pair * L::per_pair(depth);
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(mine);             // [2]
-    uint8_t* s_out = mine + 32;                                       // [2][kOutBytes]
-    uint8_t* s_moves = s_out + 2 * L::kOutBytes;                      // [2][move_stride]
+    uint8_t* mine = smem + L::kPerWarp + warp * L::per_warp(depth);
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(mine);             // [2] mbarriers
+    uint8_t* s_out = mine + 16;                                       // [kOutBytes]
+    uint8_t* s_moves = s_out + L::kOutBytes;                          // [2][move_stride]
     const int mstride = L::move_stride(depth);
     const uint32_t move_bytes = (uint32_t)(kPairTile * depth);
-    const bool leader = (par == 0) && (lane == 0);
 
     pair_table_fill<SIZE>(s_ptbl, tid, blockDim.x);
     if (tid < 32) s_clut[tid] = (SIZE == 3) ? kCornerColour3[tid] : kCornerColour2[tid];
-    if (tid >= 64 && tid < 128) s_elut[tid - 64] = (SIZE == 3) ? kEdgeColour3[tid - 64] : 0u;
-    if (leader) { bulk::mbar_init(&s_bar[0], 1); bulk::mbar_init(&s_bar[1], 1); }
+    if (tid >= 64 && tid < 96) s_elut[tid - 64] = (SIZE == 3) ? kEdgeColour3[tid - 64] : 0u;   // canonical flips: 32 entries
+    if (lane == 0) { bulk::mbar_init(&s_bar[0], 1); bulk::mbar_init(&s_bar[1], 1); }
     __syncthreads();
 
-    const long long stride = (long long)gridDim.x * pairs;
-    long long tile = (long long)blockIdx.x * pairs + pair;
-    if (leader && tile < n_tiles) {
+    const int stride = (int)gridDim.x * warps;
+    int tile = (int)blockIdx.x * warps + warp;
+    const uint8_t* g_moves = moves + (long long)tile * move_bytes;    // this warp's next tile to prefetch
+    const long long g_step = (long long)stride * move_bytes;
+    if (lane == 0 && tile < n_tiles) {
         bulk::mbar_expect_tx(&s_bar[0], move_bytes);
-        bulk::load(s_moves, moves + tile * move_bytes, move_bytes, &s_bar[0]);
+        bulk::load(s_moves, g_moves, move_bytes, &s_bar[0]);
     }
-    // 3x3x3: the pair's first warp takes the even rows, the second the odd rows (warp-uniform row
-    // alignment, lanes 27 words apart: conflict-free stores); 2x2x2: rows 0-31 / 32-63
-    const int row = (SIZE == 3) ? 2 * lane + par : lane + 32 * par;
+    const int rows[2] = {(SIZE == 3) ? 2 * lane : lane, (SIZE == 3) ? 2 * lane + 1 : lane + 32};
     const uint32_t lanereg = pair_lanereg<SIZE>(lane);
-    unsigned long long n_solved = 0;
+    const ColourLutShared lut{bulk::smem_addr(s_clut), bulk::smem_addr(s_elut)};
+    unsigned n_solved = 0;
 
     for (int it = 0; tile < n_tiles; ++it, tile += stride) {
         const int buf = it & 1;
-        if (leader && tile + stride < n_tiles) {                      // prefetch the next tile's moves
+        g_moves += g_step;
+        if (lane == 0 && tile + stride < n_tiles) {                   // prefetch the next tile's moves
             bulk::mbar_expect_tx(&s_bar[buf ^ 1], move_bytes);
-            bulk::load(s_moves + (buf ^ 1) * mstride, moves + (tile + stride) * move_bytes, move_bytes, &s_bar[buf ^ 1]);
+            bulk::load(s_moves + (buf ^ 1) * mstride, g_moves, move_bytes, &s_bar[buf ^ 1]);
         }
         bulk::mbar_wait(&s_bar[buf], (uint32_t)(it >> 1) & 1u);
 
-        CubieState st;
-        cubie_init(st);
-        scramble_pairs_run<SIZE>(st, row, depth, s_moves + buf * mstride, s_ptbl, lanereg);
-        const bool ok = scramble_pairs_finish<SIZE>(st, row, s_clut, s_elut, s_out + buf * L::kOutBytes);
-
-        const long long inst = tile * kPairTile + row;
-        if (solved) solved[inst] = ok ? 1 : 0;
-        if (reward) reward[inst] = ok ? 1.0f : -1.0f;
-        const unsigned bal = __ballot_sync(0xffffffffu, ok);
-        if (lane == 0) n_solved += (unsigned)__popc(bal);
+        CubieState st[2];
+        cubie_init(st[0]);
+        cubie_init(st[1]);
+        scramble_pairs_run<SIZE, DEPTH, 2>(st, rows, depth, s_moves + buf * mstride, tbl, lanereg);
+        if (lane == 0) bulk::wait_read_all();                         // the previous store has released the out tile
+        __syncwarp();
+        const bool ok0 = scramble_pairs_finish<SIZE>(st[0], rows[0], lut, s_out);
+        const bool ok1 = scramble_pairs_finish<SIZE>(st[1], rows[1], lut, s_out);
+        const unsigned m0 = __ballot_sync(0xffffffffu, ok0), m1 = __ballot_sync(0xffffffffu, ok1);
+        n_solved += (unsigned)(__popc(m0) + __popc(m1));
 
         bulk::fence_smem_writes();                                    // rows -> visible to the copy engine
-        if (leader) bulk::wait_read_all();                            // the previous store has released its buffer
-        pair_barrier(pair);
-        if (leader) {
-            bulk::store(out + tile * (long long)L::kOutBytes, s_out + buf * L::kOutBytes, (uint32_t)L::kOutBytes);
+        __syncwarp();
+        if (lane == 0) {
+            bulk::store(out + (long long)tile * L::kOutBytes, s_out, (uint32_t)L::kOutBytes);
             bulk::commit();
         }
+        // verdicts leave coalesced: 64 solved bytes (lanes 0-15) and 64 rewards
+        if (solved && lane < 16)
+            reinterpret_cast<uint32_t*>(solved + (long long)tile * kPairTile)[lane] = pair_solved_word<SIZE>(m0, m1, lane);
+        if (reward) {
+            float2 v;
+            v.x = pair_row_bit<SIZE>(m0, m1, 2 * lane) ? 1.0f : -1.0f;
+            v.y = pair_row_bit<SIZE>(m0, m1, 2 * lane + 1) ? 1.0f : -1.0f;
+            reinterpret_cast<float2*>(reward + (long long)tile * kPairTile)[lane] = v;
+        }
     }
-    if (lane == 0 && n_solved && counters) atomicAdd(&counters[0], n_solved);
-    if (blockIdx.x == 0 && tid == 0 && counters) atomicAdd(&counters[1], (unsigned long long)(n_tiles * kPairTile));
-    if (leader) bulk::wait_read_all();                                // shared memory must outlive the copies' reads
+    if (lane == 0 && n_solved && counters) atomicAdd(&counters[0], (unsigned long long)n_solved);
+    if (blockIdx.x == 0 && tid == 0 && counters) atomicAdd(&counters[1], (unsigned long long)n_tiles * kPairTile);
+    if (lane == 0) bulk::wait_read_all();                             // shared memory must outlive the copies' reads
 }
 
 // deep sequences (depth > kMaxStagedDepth): persistent CTAs, moves read straight from global
@@ -341,21 +353,26 @@ int launch_one(const uint8_t* moves, long long n, int depth, uint8_t* out, uint8
     long long done = 0;
     const char* force = getenv("CUBE_SCRAMBLE_CLASSIC");               // A/B switch for profiling
     if (depth >= 1 && depth <= kMaxPairDepth && n >= kPairTile && !(force && force[0] == '1')) {
-        int pairs = (kSmemLimit - L::kPerPair) / L::per_pair(depth);
-        if (pairs > kMaxPairs) pairs = kMaxPairs;
-        if (pairs >= 2) {
-            const long long n_tiles = n / kPairTile;
-            const int smem = L::bytes(depth, pairs);
-            auto kern = scramble_pairs_kernel<SIZE>;
-            static int configured_smem = -1;
-            if (smem > configured_smem) {
+        int warps = (kSmemLimit - 256 - L::kPerWarp) / L::per_warp(depth);
+        if (warps > PairCfg<SIZE>::kMaxWarps) warps = PairCfg<SIZE>::kMaxWarps;
+        warps &= ~3;                                                   // the same number on every scheduler
+        if (warps >= 4) {
+            long long n_tiles = n / kPairTile;
+            if (n_tiles > 0x3fffffff) n_tiles = 0x3fffffff;           // 32-bit tile counters; the rest goes below
+            const int smem = L::bytes(depth, warps) + 256;
+            // straight-line specialisations: the reference's default depth (config.yaml:7) and BASELINE config 2's
+            auto kern = depth == 30 ? scramble_pairs_kernel<SIZE, 30>
+                      : depth == 20 ? scramble_pairs_kernel<SIZE, 20> : scramble_pairs_kernel<SIZE, 0>;
+            static int configured_smem[3] = {-1, -1, -1};
+            int& cfg = configured_smem[depth == 30 ? 1 : depth == 20 ? 2 : 0];
+            if (smem > cfg) {
                 cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
                 if (e != cudaSuccess) return (int)e;
-                configured_smem = smem;
+                cfg = smem;
             }
-            long long grid = (n_tiles + pairs - 1) / pairs;
+            long long grid = (n_tiles + warps - 1) / warps;
             if (grid > cube::sm_count()) grid = cube::sm_count();
-            kern<<<(unsigned)grid, pairs * 64, smem, stream>>>(moves, n_tiles, depth, out, solved, reward, counters);
+            kern<<<(unsigned)grid, warps * 32, smem, stream>>>(moves, (int)n_tiles, depth, out, solved, reward, counters);
             const cudaError_t e = cudaGetLastError();
             if (e != cudaSuccess) return (int)e;
             done = n_tiles * kPairTile;

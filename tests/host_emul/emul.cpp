@@ -35,25 +35,36 @@ void scramble_t(const uint8_t* moves, long long n, int depth, uint8_t* out, uint
 
 // K1p: persistent pair-table kernel, one 64-row tile at a time with the kernel's lane -> row map
 template <int SIZE>
-void scramble_pairs_t(const uint8_t* moves, long long n, int depth, uint8_t* out, uint8_t* solved)
+void scramble_pairs_t(const uint8_t* moves, long long n, int depth, uint8_t* out, uint8_t* solved, bool fixed)
 {
     using G = CubeGeom<SIZE>;
     const uint32_t* clut = SIZE == 3 ? kCornerColour3 : kCornerColour2;
     std::vector<uint8_t> tbl(65792 + 256, 0xa5);
-    uint8_t* s_ptbl = tbl.data() + ((16 - (reinterpret_cast<uintptr_t>(tbl.data()) & 15)) & 15);
-    for (int t = 0; t < 96; ++t) pair_table_fill<SIZE>(s_ptbl, t, 96);
+    uint8_t* s_ptbl_mem = tbl.data() + ((16 - (reinterpret_cast<uintptr_t>(tbl.data()) & 15)) & 15);
+    for (int t = 0; t < 96; ++t) pair_table_fill<SIZE>(s_ptbl_mem, t, 96);
     std::vector<uint8_t> s_moves(64 * depth + 16), s_out(64 * G::S);
     for (long long base = 0; base + 64 <= n; base += 64) {
         std::memset(s_moves.data(), 0xee, s_moves.size());
         std::memcpy(s_moves.data(), moves + base * depth, (size_t)64 * depth);
-        for (int par = 0; par < 2; ++par)
-            for (int lane = 0; lane < 32; ++lane) {
-                const int row = (SIZE == 3) ? 2 * lane + par : lane + 32 * par;
-                CubieState st;
-                cubie_init(st);
-                scramble_pairs_run<SIZE>(st, row, depth, s_moves.data(), s_ptbl, pair_lanereg<SIZE>(lane));
-                solved[base + row] = scramble_pairs_finish<SIZE>(st, row, clut, kEdgeColour3, s_out.data());
-            }
+        uint32_t ok[2] = {0, 0};
+        for (int lane = 0; lane < 32; ++lane) {                      // one lane = two rows in lockstep
+            const int rows[2] = {(SIZE == 3) ? 2 * lane : lane, (SIZE == 3) ? 2 * lane + 1 : lane + 32};
+            CubieState st[2];
+            cubie_init(st[0]);
+            cubie_init(st[1]);
+            const uint32_t lr = pair_lanereg<SIZE>(lane);
+            const PairTableHost s_ptbl{s_ptbl_mem};
+            if (fixed && depth == 30) scramble_pairs_run<SIZE, 30, 2>(st, rows, depth, s_moves.data(), s_ptbl, lr);
+            else if (fixed && depth == 20) scramble_pairs_run<SIZE, 20, 2>(st, rows, depth, s_moves.data(), s_ptbl, lr);
+            else if (fixed && depth == 43) scramble_pairs_run<SIZE, 43, 2>(st, rows, depth, s_moves.data(), s_ptbl, lr);
+            else scramble_pairs_run<SIZE, 0, 2>(st, rows, depth, s_moves.data(), s_ptbl, lr);
+            for (int k = 0; k < 2; ++k)
+                ok[k] |= (uint32_t)scramble_pairs_finish<SIZE>(st[k], rows[k], ColourLutHost{clut, kEdgeColour3}, s_out.data()) << lane;
+        }
+        for (int k = 0; k < 16; ++k) {                               // the kernel's verdict exchange
+            const uint32_t w = pair_solved_word<SIZE>(ok[0], ok[1], k);
+            std::memcpy(solved + base + 4 * k, &w, 4);
+        }
         std::memcpy(out + base * G::S, s_out.data(), (size_t)64 * G::S);
     }
 }
@@ -134,9 +145,12 @@ void emul_scramble(int size, const uint8_t* moves, long long n, int depth, uint8
 {
     if (size == 3) scramble_t<3>(moves, n, depth, out, solved); else scramble_t<2>(moves, n, depth, out, solved);
 }
-void emul_scramble_pairs(int size, const uint8_t* moves, long long n, int depth, uint8_t* out, uint8_t* solved)
+// fixed != 0: use the compile-time-depth instantiation when one exists (30, 20; 43 only here, to
+// exercise the unrolled fold schedule)
+void emul_scramble_pairs(int size, const uint8_t* moves, long long n, int depth, uint8_t* out, uint8_t* solved, int fixed)
 {
-    if (size == 3) scramble_pairs_t<3>(moves, n, depth, out, solved); else scramble_pairs_t<2>(moves, n, depth, out, solved);
+    if (size == 3) scramble_pairs_t<3>(moves, n, depth, out, solved, fixed != 0);
+    else scramble_pairs_t<2>(moves, n, depth, out, solved, fixed != 0);
 }
 void emul_walk(int size, const uint8_t* in, const uint8_t* moves, long long n, int depth, uint8_t* out,
                uint8_t* solved)

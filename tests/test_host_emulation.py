@@ -25,7 +25,7 @@ def emul():
     lib = ctypes.CDLL(LIB)
     vp, ll = ctypes.c_void_p, ctypes.c_longlong
     lib.emul_scramble.argtypes = [ctypes.c_int, vp, ll, ctypes.c_int, vp, vp]
-    lib.emul_scramble_pairs.argtypes = [ctypes.c_int, vp, ll, ctypes.c_int, vp, vp]
+    lib.emul_scramble_pairs.argtypes = [ctypes.c_int, vp, ll, ctypes.c_int, vp, vp, ctypes.c_int]
     lib.emul_walk.argtypes = [ctypes.c_int, vp, vp, ll, ctypes.c_int, vp, vp]
     lib.emul_expand.argtypes = [ctypes.c_int, ctypes.c_int, vp, ll, vp, vp, vp, vp]
     return lib
@@ -58,8 +58,9 @@ def test_scramble_emulation(emul, size, depth):
 
 
 @pytest.mark.parametrize("size", (2, 3))
-@pytest.mark.parametrize("depth", (1, 2, 3, 4, 5, 7, 8, 9, 20, 30, 31, 32, 43, 61, 96))
-def test_scramble_pairs_emulation(emul, size, depth):
+@pytest.mark.parametrize("depth,fixed", [(d, 0) for d in (1, 2, 3, 4, 5, 7, 8, 9, 20, 30, 31, 32, 43, 61, 96)]
+                         + [(20, 1), (30, 1), (43, 1)])
+def test_scramble_pairs_emulation(emul, size, depth, fixed):
     """K1p (two moves per table row, persistent 64-row tiles): rows that return to solved, the
     no-move index 12 in the stream, odd depths (padded tail pair) and the fold schedule."""
     rng = np.random.RandomState(depth * 11 + size)
@@ -74,7 +75,7 @@ def test_scramble_pairs_emulation(emul, size, depth):
     moves[60:90][rng.rand(30, depth) < 0.3] = 12                     # no-move index anywhere
     out = np.empty((n, T.N_STICKERS[size]), dtype=np.uint8)
     solved = np.empty(n, dtype=np.uint8)
-    emul.emul_scramble_pairs(size, _p(moves), n, depth, _p(out), _p(solved))
+    emul.emul_scramble_pairs(size, _p(moves), n, depth, _p(out), _p(solved), fixed)
     want = np.empty_like(out)
     for i in range(n):                                               # the oracle skips the no-move index
         row = moves[i][moves[i] != 12]
