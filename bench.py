@@ -401,11 +401,11 @@ def run_b200_arm(args):
             traffic = json.load(open(prof)).get("dram_bytes_per_launch")
         except Exception:                                   # noqa: BLE001
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "scramble_tile_kernel<3,true>", "achieved": alg_bytes / kern_s / 1e9,
+    roofline = {"bound": "hbm", "kernel": "scramble_pairs_kernel<3,30>", "achieved": alg_bytes / kern_s / 1e9,
                 "peak": peak_gbs, "unit": "GB/s", "frac": alg_bytes / kern_s / 1e9 / peak_gbs, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                 "kernel_ms": kern_s * 1e3, "transitions_per_s_kernel_only": n * depth / kern_s,
-                "note": "K1 is bound by instruction issue / the ALU pipe (PRMT, LOP3), not by HBM (SURVEY.md 8d, "
+                "note": "K1p is bound by the shared-memory data pipe (pair-table rows, 88 % of peak) and the ALU pipe (PRMT), not by HBM (SURVEY.md 8d, "
                         "DESIGN.md): the HBM fraction is reported as the contract asks; see profiles/"}
 
     # end to end through the host-buffer C-ABI pipeline (pinned host memory, copies inside the timed region)

@@ -20,9 +20,11 @@
  *     re-entrant.  Return value: 0, a negative CUBE_ERR_*, or a positive
  *     cudaError_t.  cube_last_error() describes the last non-zero return of
  *     the calling thread.
- *   - action indices are NOT range-checked on the hot path (indices >= A are
- *     reduced mod 16 and rows A..15 are no-ops); call cube_validate_actions
- *     when the reference's IndexError (cube_env.py:86,96) must be reproduced.
+ *   - action indices are NOT range-checked on the hot path: indices A..12 are
+ *     no-ops (12 = CUBE_NOOP, the padding index for ragged batches); indices
+ *     13..255 are memory-safe but give unspecified states.  Call
+ *     cube_validate_actions when the reference's IndexError (cube_env.py:86,96)
+ *     must be reproduced.
  *   - counters, when non-NULL, is uint64[4] on the device and is only ever
  *     ADDED to: [0] += outputs that are solved, [1] += outputs produced,
  *     [2] += out-of-range actions (cube_validate_actions), [3] reserved.
@@ -44,6 +46,8 @@ extern "C" {
 #define CUBE_ERR_ARG (-2)
 #define CUBE_ERR_ALIGN (-3)
 #define CUBE_ERR_ACTION (-4)
+
+#define CUBE_NOOP 12 /* action index that leaves the cube unchanged (both sizes) */
 
 #define CUBE_DTYPE_BF16 0
 #define CUBE_DTYPE_F32 1
