@@ -1,0 +1,100 @@
+// Tile scheduling for the persistent kernels (K1p, K2p): static bulk, dynamic tail.
+//
+// SMs do not get equal shares of HBM bandwidth (die-local L2, channel contention): with a purely
+// static split the fastest SM of a bandwidth-bound launch is done after ~80 % of the kernel's time.
+// A purely dynamic split does not work either -- same-address atomics retire at ~0.4 per ns while
+// the kernels retire up to 2 tiles per ns.  So the first (1 - 1/kTailDiv) of the tiles is strided
+// over the warps statically (neighbours in time are neighbours in memory), and the tail is claimed
+// by whoever gets there, kClaimChunk tiles at a time, from kRanges counters on separate cache
+// lines (a warp starts in its home sub-range and then steals from the others).  Claims are issued
+// one chunk ahead, so the atomic's round trip is not waited for, and the kernel's last CTA puts the
+// counters back to zero: a launch needs no memset and leaves no state behind.  Launches take their
+// counters from a ring of slots, so kernels in flight on different streams never share one.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace sched {
+
+constexpr int kClaimChunk = 2;
+constexpr int kRanges = 8;
+constexpr int kTailDiv = 4;            // the last 1/4 of the tiles is claimed dynamically (measured: 8 -> +10 %, 4 -> +13 % on K2p)
+constexpr int kSlots = 128;
+constexpr int kExhausted = 0x7fffff00;
+
+struct Slot { unsigned next[kRanges][32]; unsigned ctas_done; unsigned tail_div; unsigned pad[30]; };
+
+// host: the device address of a fresh slot for the current device (nullptr on error)
+Slot* claim_slot();
+// host: tail divisor (kTailDiv; CUBE_TAIL_DIV overrides it for A/B runs, 0 = fully static)
+int tail_div();
+
+// per-warp state, identical in all lanes except `pending` (lane 0 only)
+struct WarpTiles {
+    Slot* slot;
+    int n_tiles, total_warps, tail0;   // tiles [tail0, n_tiles) are dynamic
+    int next_static;
+    int r, visited;                    // tail sub-range being worked on, sub-ranges given up so far
+    int cur, end;                      // the claimed chunk in hand
+    unsigned pending;                  // lane 0: raw result of the claim issued ahead in sub-range r
+
+    __device__ __forceinline__ int lo(int range) const
+    {
+        return tail0 + (int)((long long)range * (n_tiles - tail0) / kRanges);
+    }
+    __device__ __forceinline__ void claim_ahead(int lane)
+    {
+        if (lane == 0) pending = atomicAdd(&slot->next[r][0], (unsigned)kClaimChunk);
+    }
+
+    __device__ __forceinline__ void init(Slot* s, int n, int warps_per_cta, int warp, int lane, int tail_div)
+    {
+        slot = s; n_tiles = n; total_warps = (int)gridDim.x * warps_per_cta;
+        const int gid = (int)blockIdx.x * warps_per_cta + warp;
+        tail0 = tail_div > 0 ? n - n / tail_div : n;
+        next_static = gid;
+        r = gid % kRanges; visited = 0; cur = end = 0; pending = 0;
+        if (next_static >= tail0) claim_ahead(lane);                  // no static share at all
+    }
+
+    // next tile of this warp, kExhausted once everything is handed out
+    __device__ __forceinline__ int pop(int lane)
+    {
+        if (next_static < tail0) {
+            const int t = next_static;
+            next_static += total_warps;
+            if (next_static >= tail0) claim_ahead(lane);              // last static tile: first claim goes out now
+            return t;
+        }
+        while (cur >= end) {
+            if (visited >= kRanges) return kExhausted;
+            const unsigned got = __shfl_sync(0xffffffffu, pending, 0);
+            const int hi = lo(r + 1);
+            const long long base = (long long)lo(r) + got;
+            if (base < hi) {
+                cur = (int)base;
+                end = cur + kClaimChunk < hi ? cur + kClaimChunk : hi;
+            } else {                                                  // sub-range used up: move on (steal)
+                r = (r + 1) % kRanges;
+                ++visited;
+            }
+            if (visited < kRanges) claim_ahead(lane);
+        }
+        return cur++;
+    }
+};
+
+// end of kernel, after a __syncthreads(): the last CTA of the grid re-arms the slot
+__device__ __forceinline__ void release(Slot* slot)
+{
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&slot->ctas_done, 1u) == gridDim.x - 1) {
+            for (int i = 0; i < kRanges; ++i) slot->next[i][0] = 0;
+            slot->ctas_done = 0;
+            __threadfence();
+        }
+    }
+}
+
+}  // namespace sched

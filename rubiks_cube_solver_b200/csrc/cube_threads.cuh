@@ -367,6 +367,65 @@ CUBE_HD bool row_solved(const uint8_t* row)
     return diff == 0;
 }
 
+
+// ---- K2p: moves on resident rows in a lane-private working layout ------------------------------
+// A lane keeps its row as an IMAGE of whole words: 2x2x2 the 6 words of the row; 3x3x3 the 14
+// words that cover the 54-byte row on the word grid -- even rows start on a word (image byte k =
+// sticker k, the last two bytes belong to the next row), odd rows two bytes later (image byte k =
+// sticker k - 2, the first two bytes belong to the previous row).  The face turn itself is a byte
+// gather at data-dependent offsets, so the image is parked in a scratch area where image word j
+// of lane l sits at word 32 j + l: every byte a lane touches is in the lane's own bank, whatever
+// the move, and the 4-cycles cost exactly one wavefront per access.
+template <int SIZE> struct WalkImage { static constexpr int W = (SIZE == 3) ? 14 : 6; };
+
+CUBE_HD uint32_t walk_private_off(int k) { return (uint32_t)((k >> 2) * 128 + (k & 3)); }
+
+// 8-byte table entry of one sticker 4-cycle (bytes a, b, c, d of kCycles*) for an image that starts
+// `shift` bytes before sticker 0: the four scratch offsets, 16 bits each
+CUBE_HD void walk_cycle_entry(uint32_t cw, int shift, uint32_t* e)
+{
+    const int a = (int)(cw & 0xffu) + shift, b = (int)((cw >> 8) & 0xffu) + shift;
+    const int c = (int)((cw >> 16) & 0xffu) + shift, d = (int)(cw >> 24) + shift;
+    e[0] = walk_private_off(a) | walk_private_off(b) << 16;
+    e[1] = walk_private_off(c) | walk_private_off(d) << 16;
+}
+
+// one face turn of the lane's image; lane_base = scratch + 4 * lane, ent = [cycle][16 moves][2]
+template <int SIZE>
+CUBE_HD void walk_turn_private(uint8_t* lane_base, const uint32_t* ent, uint32_t m)
+{
+#pragma unroll
+    for (int c = 0; c < CubeGeom<SIZE>::NCYC; ++c) {
+        const uint32_t w0 = ent[(c * CUBE_MOVE_ROWS + m) * 2], w1 = ent[(c * CUBE_MOVE_ROWS + m) * 2 + 1];
+        const uint32_t a = w0 & 0xffffu, b = cube_hi16(w0), cc = w1 & 0xffffu, d = cube_hi16(w1);
+        const uint8_t vb = lane_base[b], vc = lane_base[cc], vd = lane_base[d], va = lane_base[a];
+        lane_base[a] = vb; lane_base[b] = vc; lane_base[cc] = vd; lane_base[d] = va;
+    }
+}
+
+// face uniformity (py333.py:229-233 / py222 isSolved) of an image held in registers: every sticker
+// that does not start a face equals its predecessor.  SHIFT = image byte of sticker 0 (0 or 2).
+template <int SIZE, int SHIFT>
+CUBE_HD bool image_solved(const uint32_t* w)
+{
+    constexpr int S = CubeGeom<SIZE>::S, K = S / 6, W = WalkImage<SIZE>::W;
+    uint32_t acc = 0;
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+        uint32_t mask = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int i = 4 * j + k - SHIFT;              // sticker index of image byte 4j+k
+            if (i >= 1 && i < S && (i % K) != 0) mask |= 0xffu << (8 * k);
+        }
+        if (mask) {
+            const uint32_t prev = (j == 0) ? (w[0] << 8) : ((w[j] << 8) | (w[j - 1] >> 24));
+            acc |= (w[j] ^ prev) & mask;
+        }
+    }
+    return acc == 0;
+}
+
 // ---- K3: one-hot columns and vectors ----------------------------------------------------------
 template <int DTYPE> struct OneHot;      // V = elements per 16-byte vector
 template <> struct OneHot<0> { static constexpr int V = 8, ESIZE = 2; };   // bf16

@@ -21,6 +21,7 @@
 #include <cuda_runtime.h>
 #include "cube_bulk.cuh"
 #include "cube_kernels.h"
+#include "cube_sched.cuh"
 #include "cube_threads.cuh"
 
 namespace {
@@ -177,13 +178,13 @@ struct PairSmem {
 template <int SIZE, int DEPTH>
 __global__ void __launch_bounds__(PairCfg<SIZE>::kMaxWarps * 32, 1)
 scramble_pairs_kernel(const uint8_t* __restrict__ moves, int n_tiles, int depth_rt, uint8_t* __restrict__ out,
-                      uint8_t* __restrict__ solved, float* __restrict__ reward, unsigned long long* __restrict__ counters)
+                      uint8_t* __restrict__ solved, float* __restrict__ reward, unsigned long long* __restrict__ counters,
+                      sched::Slot* slot, int tail_div)
 {
     using L = PairSmem<SIZE>;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int depth = DEPTH > 0 ? DEPTH : depth_rt;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int warps = blockDim.x >> 5;
     // everything is laid out from a 256-byte boundary of the shared window (see PairTableShared)
     const uint32_t window = bulk::smem_addr(smem_raw);
     uint8_t* smem = smem_raw + ((256u - (window & 255u)) & 255u);
@@ -204,25 +205,25 @@ scramble_pairs_kernel(const uint8_t* __restrict__ moves, int n_tiles, int depth_
     if (lane == 0) { bulk::mbar_init(&s_bar[0], 1); bulk::mbar_init(&s_bar[1], 1); }
     __syncthreads();
 
-    const int stride = (int)gridDim.x * warps;
-    int tile = (int)blockIdx.x * warps + warp;
-    const uint8_t* g_moves = moves + (long long)tile * move_bytes;    // this warp's next tile to prefetch
-    const long long g_step = (long long)stride * move_bytes;
+    // tiles are claimed dynamically (cube_sched.cuh): `tile` is being computed, `next` is in flight
+    sched::WarpTiles tiles;
+    tiles.init(slot, n_tiles, (int)(blockDim.x >> 5), warp, lane, tail_div);
+    int tile = tiles.pop(lane);
     if (lane == 0 && tile < n_tiles) {
         bulk::mbar_expect_tx(&s_bar[0], move_bytes);
-        bulk::load(s_moves, g_moves, move_bytes, &s_bar[0]);
+        bulk::load(s_moves, moves + (long long)tile * move_bytes, move_bytes, &s_bar[0]);
     }
     const int rows[2] = {(SIZE == 3) ? 2 * lane : lane, (SIZE == 3) ? 2 * lane + 1 : lane + 32};
     const uint32_t lanereg = pair_lanereg<SIZE>(lane);
     const ColourLutShared lut{bulk::smem_addr(s_clut), bulk::smem_addr(s_elut)};
     unsigned n_solved = 0;
 
-    for (int it = 0; tile < n_tiles; ++it, tile += stride) {
+    for (int it = 0; tile < n_tiles; ++it) {
         const int buf = it & 1;
-        g_moves += g_step;
-        if (lane == 0 && tile + stride < n_tiles) {                   // prefetch the next tile's moves
+        const int next = tiles.pop(lane);
+        if (lane == 0 && next < n_tiles) {                            // prefetch the next tile's moves
             bulk::mbar_expect_tx(&s_bar[buf ^ 1], move_bytes);
-            bulk::load(s_moves + (buf ^ 1) * mstride, g_moves, move_bytes, &s_bar[buf ^ 1]);
+            bulk::load(s_moves + (buf ^ 1) * mstride, moves + (long long)next * move_bytes, move_bytes, &s_bar[buf ^ 1]);
         }
         bulk::mbar_wait(&s_bar[buf], (uint32_t)(it >> 1) & 1u);
 
@@ -252,10 +253,13 @@ scramble_pairs_kernel(const uint8_t* __restrict__ moves, int n_tiles, int depth_
             v.y = pair_row_bit<SIZE>(m0, m1, 2 * lane + 1) ? 1.0f : -1.0f;
             reinterpret_cast<float2*>(reward + (long long)tile * kPairTile)[lane] = v;
         }
+        tile = next;
     }
     if (lane == 0 && n_solved && counters) atomicAdd(&counters[0], (unsigned long long)n_solved);
     if (blockIdx.x == 0 && tid == 0 && counters) atomicAdd(&counters[1], (unsigned long long)n_tiles * kPairTile);
     if (lane == 0) bulk::wait_read_all();                             // shared memory must outlive the copies' reads
+    __syncthreads();
+    sched::release(slot);
 }
 
 // deep sequences (depth > kMaxStagedDepth): persistent CTAs, moves read straight from global
@@ -372,7 +376,9 @@ int launch_one(const uint8_t* moves, long long n, int depth, uint8_t* out, uint8
             }
             long long grid = (n_tiles + warps - 1) / warps;
             if (grid > cube::sm_count()) grid = cube::sm_count();
-            kern<<<(unsigned)grid, warps * 32, smem, stream>>>(moves, (int)n_tiles, depth, out, solved, reward, counters);
+            sched::Slot* slot = sched::claim_slot();
+            if (!slot) return (int)cudaErrorUnknown;
+            kern<<<(unsigned)grid, warps * 32, smem, stream>>>(moves, (int)n_tiles, depth, out, solved, reward, counters, slot, sched::tail_div());
             const cudaError_t e = cudaGetLastError();
             if (e != cudaSuccess) return (int)e;
             done = n_tiles * kPairTile;

@@ -13,9 +13,11 @@
 // depth = 1 is `step`; depth > 1 walks several moves without leaving shared
 // memory; depth = 0 with no output is `cube_solved`.
 // HBM traffic per instance: 2*S + depth + 1 + 4 bytes.
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include "cube_bulk.cuh"
 #include "cube_kernels.h"
+#include "cube_sched.cuh"
 #include "cube_threads.cuh"
 
 namespace {
@@ -94,6 +96,150 @@ walk_tile_kernel(const uint8_t* in, const uint8_t* __restrict__ moves, long long
     if (FULL && out && tid == 0) bulk::wait_read_all();
 }
 
+
+// ---- K2p: persistent lane-private kernel (depth >= 1 with an output, the step / walk hot path) ----
+// One CTA per SM, every warp owns a private pipeline over tiles of 64 rows (the same shape as the
+// scramble kernel K1p): rows + move bytes of tile i+1 arrive by bulk copies while tile i is turned;
+// per pass (even rows, then odd rows: 54-byte rows alternate between word-aligned and two bytes
+// off, and a pass must have one alignment) each lane lifts its row out of the packed tile into
+// registers (stride 27 words: conflict-free), parks it in the lane-private scratch layout
+// (cube_threads.cuh), applies the 4-cycles there (one wavefront per byte access, whatever the
+// moves), judges face uniformity in registers and writes the row back in place; the tile then
+// leaves by one bulk store.  Replaces byte gathers on the packed tile, which bank-conflicted ~3x.
+constexpr int kRowsPerTile = 64;
+constexpr int kMaxWalkWarps = 24;
+constexpr int kMaxPrivateDepth = 64;
+
+template <int SIZE>
+struct WalkSmem {
+    using G = CubeGeom<SIZE>;
+    static constexpr int kEntries = 0;                                // [2 shifts][NCYC][16][2] words
+    static constexpr int kPerWarp = 2 * G::NCYC * CUBE_MOVE_ROWS * 8;
+    static constexpr int kTileBytes = kRowsPerTile * G::S;            // 3456 / 1536
+    static constexpr int kScratch = 32 * WalkImage<SIZE>::W * 4;
+    __host__ __device__ static constexpr int move_stride(int depth) { return kRowsPerTile * depth + 16; }
+    __host__ __device__ static constexpr int per_warp(int depth)
+    {
+        return 16 + 2 * (kTileBytes + 16) + kScratch + 2 * move_stride(depth);
+    }
+    __host__ __device__ static constexpr int bytes(int depth, int warps) { return kPerWarp + warps * per_warp(depth); }
+};
+
+template <int SIZE>
+__global__ void __launch_bounds__(kMaxWalkWarps * 32, 1)
+walk_private_kernel(const uint8_t* in, const uint8_t* __restrict__ moves, int n_tiles, int depth, uint8_t* out,
+                    uint8_t* __restrict__ solved, float* __restrict__ reward, unsigned long long* __restrict__ counters,
+                    sched::Slot* slot, int tail_div)
+{
+    using G = CubeGeom<SIZE>;
+    using L = WalkSmem<SIZE>;
+    constexpr int W = WalkImage<SIZE>::W;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t* s_ent = reinterpret_cast<uint32_t*>(smem + L::kEntries);
+    uint8_t* mine = smem + L::kPerWarp + warp * L::per_warp(depth);
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(mine);             // [2]
+    uint8_t* s_tile = mine + 16;                                      // [2][kTileBytes + 16]
+    uint8_t* s_scratch = s_tile + 2 * (L::kTileBytes + 16);           // lane-private layout
+    uint8_t* s_moves = s_scratch + L::kScratch;                       // [2][move_stride]
+    const int mstride = L::move_stride(depth);
+    const uint32_t move_bytes = (uint32_t)(kRowsPerTile * depth);
+
+    for (int i = tid; i < 2 * G::NCYC * CUBE_MOVE_ROWS; i += blockDim.x) {
+        const int shift = (i >= G::NCYC * CUBE_MOVE_ROWS) ? 2 : 0;
+        const int cm = i - (shift ? G::NCYC * CUBE_MOVE_ROWS : 0);
+        walk_cycle_entry((SIZE == 3) ? kCycles3[cm] : kCycles2[cm], shift, s_ent + 2 * i);
+    }
+    if (lane == 0) { bulk::mbar_init(&s_bar[0], 1); bulk::mbar_init(&s_bar[1], 1); }
+    __syncthreads();
+
+    // tiles are claimed dynamically (cube_sched.cuh): `tile` is being turned, `next` is in flight
+    sched::WarpTiles tiles;
+    tiles.init(slot, n_tiles, (int)(blockDim.x >> 5), warp, lane, tail_div);
+    int tile = tiles.pop(lane);
+    if (lane == 0 && tile < n_tiles) {
+        bulk::mbar_expect_tx(&s_bar[0], (uint32_t)L::kTileBytes + move_bytes);
+        bulk::load(s_tile, in + (long long)tile * L::kTileBytes, (uint32_t)L::kTileBytes, &s_bar[0]);
+        bulk::load(s_moves, moves + (long long)tile * move_bytes, move_bytes, &s_bar[0]);
+    }
+    uint8_t* lane_base = s_scratch + 4 * lane;
+    unsigned n_solved = 0;
+
+    for (int it = 0; tile < n_tiles; ++it) {
+        const int buf = it & 1;
+        const int next = tiles.pop(lane);
+        if (lane == 0) {
+            bulk::wait_read_all();                                    // the previous tile's store has left its buffer
+            if (next < n_tiles) {                                     // ... which the next tile now fills
+                bulk::mbar_expect_tx(&s_bar[buf ^ 1], (uint32_t)L::kTileBytes + move_bytes);
+                bulk::load(s_tile + (buf ^ 1) * (L::kTileBytes + 16), in + (long long)next * L::kTileBytes,
+                           (uint32_t)L::kTileBytes, &s_bar[buf ^ 1]);
+                bulk::load(s_moves + (buf ^ 1) * mstride, moves + (long long)next * move_bytes, move_bytes, &s_bar[buf ^ 1]);
+            }
+        }
+        bulk::mbar_wait(&s_bar[buf], (uint32_t)(it >> 1) & 1u);
+        uint8_t* tile_p = s_tile + buf * (L::kTileBytes + 16);
+        const uint8_t* moves_p = s_moves + buf * mstride;
+
+        unsigned mask[2];
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+            const int row = (SIZE == 3) ? 2 * lane + pass : lane + 32 * pass;
+            constexpr int kShiftOdd = (SIZE == 3) ? 2 : 0;
+            const int shift = pass ? kShiftOdd : 0;
+            uint32_t* img_p = reinterpret_cast<uint32_t*>(tile_p + G::S * row - shift);
+            uint32_t w[W];
+            if (SIZE == 3) {
+#pragma unroll
+                for (int j = 0; j < W; ++j) w[j] = img_p[j];
+            } else {                                                  // 24-byte rows: 8-byte accesses are conflict-free
+                const uint2* q = reinterpret_cast<const uint2*>(img_p);
+#pragma unroll
+                for (int j = 0; j < 3; ++j) { const uint2 v = q[j]; w[2 * j] = v.x; w[2 * j + 1] = v.y; }
+            }
+#pragma unroll
+            for (int j = 0; j < W; ++j) reinterpret_cast<uint32_t*>(lane_base)[32 * j] = w[j];
+            const uint32_t* ent = s_ent + (shift ? 2 * G::NCYC * CUBE_MOVE_ROWS : 0);
+            const uint8_t* mrow = moves_p + row * depth;
+            for (int k = 0; k < depth; ++k) walk_turn_private<SIZE>(lane_base, ent, (uint32_t)mrow[k] & 0xfu);
+#pragma unroll
+            for (int j = 0; j < W; ++j) w[j] = reinterpret_cast<const uint32_t*>(lane_base)[32 * j];
+            const bool ok = (pass && SIZE == 3) ? image_solved<SIZE, kShiftOdd>(w) : image_solved<SIZE, 0>(w);
+            mask[pass] = __ballot_sync(0xffffffffu, ok);
+            if (SIZE == 3) {
+#pragma unroll
+                for (int j = 0; j < W; ++j) img_p[j] = w[j];
+            } else {
+                uint2* q = reinterpret_cast<uint2*>(img_p);
+#pragma unroll
+                for (int j = 0; j < 3; ++j) q[j] = make_uint2(w[2 * j], w[2 * j + 1]);
+            }
+        }
+        n_solved += (unsigned)(__popc(mask[0]) + __popc(mask[1]));
+
+        bulk::fence_smem_writes();
+        __syncwarp();
+        if (lane == 0) {
+            bulk::store(out + (long long)tile * L::kTileBytes, tile_p, (uint32_t)L::kTileBytes);
+            bulk::commit();
+        }
+        if (solved && lane < 16)
+            reinterpret_cast<uint32_t*>(solved + (long long)tile * kRowsPerTile)[lane] = pair_solved_word<SIZE>(mask[0], mask[1], lane);
+        if (reward) {
+            float2 v;
+            v.x = pair_row_bit<SIZE>(mask[0], mask[1], 2 * lane) ? 1.0f : -1.0f;
+            v.y = pair_row_bit<SIZE>(mask[0], mask[1], 2 * lane + 1) ? 1.0f : -1.0f;
+            reinterpret_cast<float2*>(reward + (long long)tile * kRowsPerTile)[lane] = v;
+        }
+        tile = next;
+    }
+    if (lane == 0 && n_solved && counters) atomicAdd(&counters[0], (unsigned long long)n_solved);
+    if (blockIdx.x == 0 && tid == 0 && counters) atomicAdd(&counters[1], (unsigned long long)n_tiles * kRowsPerTile);
+    if (lane == 0) bulk::wait_read_all();
+    __syncthreads();
+    sched::release(slot);
+}
+
 // out-of-range action scan (the reference raises IndexError, cube_env.py:86,96)
 __global__ void __launch_bounds__(256)
 validate_kernel(const uint8_t* __restrict__ actions, long long count, unsigned n_actions,
@@ -118,8 +264,8 @@ validate_kernel(const uint8_t* __restrict__ actions, long long count, unsigned n
 }
 
 template <int SIZE>
-int launch_tiles(const uint8_t* in, const uint8_t* moves, long long n, int depth, uint8_t* out, uint8_t* solved,
-                 float* reward, unsigned long long* counters, cudaStream_t stream)
+int launch_classic(const uint8_t* in, const uint8_t* moves, long long n, int depth, uint8_t* out, uint8_t* solved,
+                   float* reward, unsigned long long* counters, cudaStream_t stream)
 {
     static bool configured = false;
     if (!configured) {
@@ -135,6 +281,45 @@ int launch_tiles(const uint8_t* in, const uint8_t* moves, long long n, int depth
         walk_tile_kernel<SIZE, false><<<1, kTile, 0, stream>>>(in, moves, n, full_tiles, depth, out, solved, reward,
                                                               counters);
     return (int)cudaGetLastError();
+}
+
+template <int SIZE>
+int launch_tiles(const uint8_t* in, const uint8_t* moves, long long n, int depth, uint8_t* out, uint8_t* solved,
+                 float* reward, unsigned long long* counters, cudaStream_t stream)
+{
+    using L = WalkSmem<SIZE>;
+    using G = CubeGeom<SIZE>;
+    long long done = 0;
+    const char* force = getenv("CUBE_WALK_CLASSIC");                   // A/B switch for profiling
+    if (depth >= 1 && depth <= kMaxPrivateDepth && out && n >= kRowsPerTile && !(force && force[0] == '1')) {
+        int warps = (227 * 1024 - L::kPerWarp) / L::per_warp(depth);
+        if (warps > kMaxWalkWarps) warps = kMaxWalkWarps;
+        warps &= ~3;
+        if (warps >= 8) {
+            long long n_tiles = n / kRowsPerTile;
+            if (n_tiles > 0x3fffffff) n_tiles = 0x3fffffff;
+            const int smem = L::bytes(depth, warps);
+            auto kern = walk_private_kernel<SIZE>;
+            static int configured_smem = -1;
+            if (smem > configured_smem) {
+                const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+                if (e != cudaSuccess) return (int)e;
+                configured_smem = smem;
+            }
+            long long grid = (n_tiles + warps - 1) / warps;
+            if (grid > cube::sm_count()) grid = cube::sm_count();
+            sched::Slot* slot = sched::claim_slot();
+            if (!slot) return (int)cudaErrorUnknown;
+            kern<<<(unsigned)grid, warps * 32, smem, stream>>>(in, moves, (int)n_tiles, depth, out, solved, reward, counters, slot, sched::tail_div());
+            const cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess) return (int)e;
+            done = n_tiles * kRowsPerTile;
+        }
+    }
+    if (done == n) return 0;
+    return launch_classic<SIZE>(in + done * G::S, moves ? moves + done * depth : nullptr, n - done, depth,
+                                out ? out + done * G::S : nullptr, solved ? solved + done : nullptr,
+                                reward ? reward + done : nullptr, counters, stream);
 }
 
 }  // namespace

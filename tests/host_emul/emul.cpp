@@ -83,6 +83,49 @@ void walk_t(const uint8_t* in, const uint8_t* moves, long long n, int depth, uin
     }
 }
 
+// K2p: lane-private layout, 64-row tiles, the kernel's two passes per lane
+template <int SIZE>
+void walk_private_t(const uint8_t* in, const uint8_t* moves, long long n, int depth, uint8_t* out, uint8_t* solved)
+{
+    using G = CubeGeom<SIZE>;
+    constexpr int W = WalkImage<SIZE>::W;
+    const uint32_t* cyc = SIZE == 3 ? kCycles3 : kCycles2;
+    std::vector<uint32_t> ent(2 * G::NCYC * CUBE_MOVE_ROWS * 2);
+    for (int i = 0; i < 2 * G::NCYC * CUBE_MOVE_ROWS; ++i) {
+        const int shift = (i >= G::NCYC * CUBE_MOVE_ROWS) ? 2 : 0;
+        walk_cycle_entry(cyc[i - (shift ? G::NCYC * CUBE_MOVE_ROWS : 0)], shift, ent.data() + 2 * i);
+    }
+    std::vector<uint32_t> tile32(64 * G::S / 4 + 4), scratch32(32 * W);
+    uint8_t* tile = reinterpret_cast<uint8_t*>(tile32.data());
+    uint8_t* scratch = reinterpret_cast<uint8_t*>(scratch32.data());
+    for (long long base = 0; base + 64 <= n; base += 64) {
+        std::memcpy(tile, in + base * G::S, (size_t)64 * G::S);
+        uint32_t mask[2] = {0, 0};
+        for (int pass = 0; pass < 2; ++pass)
+            for (int lane = 0; lane < 32; ++lane) {
+                const int row = (SIZE == 3) ? 2 * lane + pass : lane + 32 * pass;
+                const int shift = (pass && SIZE == 3) ? 2 : 0;
+                uint32_t* img_p = reinterpret_cast<uint32_t*>(tile + G::S * row - shift);
+                uint32_t w[W];
+                for (int j = 0; j < W; ++j) w[j] = img_p[j];
+                uint8_t* lane_base = scratch + 4 * lane;
+                for (int j = 0; j < W; ++j) reinterpret_cast<uint32_t*>(lane_base)[32 * j] = w[j];
+                const uint32_t* e = ent.data() + (shift ? 2 * G::NCYC * CUBE_MOVE_ROWS : 0);
+                for (int k = 0; k < depth; ++k)
+                    walk_turn_private<SIZE>(lane_base, e, moves[(base + row) * depth + k] & 0xfu);
+                for (int j = 0; j < W; ++j) w[j] = reinterpret_cast<const uint32_t*>(lane_base)[32 * j];
+                const bool ok = shift ? image_solved<SIZE, (SIZE == 3 ? 2 : 0)>(w) : image_solved<SIZE, 0>(w);
+                mask[pass] |= (uint32_t)ok << lane;
+                for (int j = 0; j < W; ++j) img_p[j] = w[j];
+            }
+        std::memcpy(out + base * G::S, tile, (size_t)64 * G::S);
+        for (int k = 0; k < 16; ++k) {
+            const uint32_t v = pair_solved_word<SIZE>(mask[0], mask[1], k);
+            std::memcpy(solved + base + 4 * k, &v, 4);
+        }
+    }
+}
+
 template <int SIZE, int DTYPE>
 void expand_t(const uint8_t* states, long long n, uint8_t* children, uint8_t* child_oh, uint8_t* parent_oh,
               uint8_t* solved)
@@ -156,6 +199,12 @@ void emul_walk(int size, const uint8_t* in, const uint8_t* moves, long long n, i
                uint8_t* solved)
 {
     if (size == 3) walk_t<3>(in, moves, n, depth, out, solved); else walk_t<2>(in, moves, n, depth, out, solved);
+}
+void emul_walk_private(int size, const uint8_t* in, const uint8_t* moves, long long n, int depth, uint8_t* out,
+                       uint8_t* solved)
+{
+    if (size == 3) walk_private_t<3>(in, moves, n, depth, out, solved);
+    else walk_private_t<2>(in, moves, n, depth, out, solved);
 }
 void emul_expand(int size, int dtype, const uint8_t* states, long long n, uint8_t* children, uint8_t* child_oh,
                  uint8_t* parent_oh, uint8_t* solved)

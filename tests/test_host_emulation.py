@@ -26,6 +26,7 @@ def emul():
     vp, ll = ctypes.c_void_p, ctypes.c_longlong
     lib.emul_scramble.argtypes = [ctypes.c_int, vp, ll, ctypes.c_int, vp, vp]
     lib.emul_scramble_pairs.argtypes = [ctypes.c_int, vp, ll, ctypes.c_int, vp, vp, ctypes.c_int]
+    lib.emul_walk_private.argtypes = [ctypes.c_int, vp, vp, ll, ctypes.c_int, vp, vp]
     lib.emul_walk.argtypes = [ctypes.c_int, vp, vp, ll, ctypes.c_int, vp, vp]
     lib.emul_expand.argtypes = [ctypes.c_int, ctypes.c_int, vp, ll, vp, vp, vp, vp]
     return lib
@@ -135,6 +136,31 @@ def test_walk_emulation(emul, size, depth):
     solved = np.empty(n, dtype=np.uint8)
     emul.emul_walk(size, _p(start), _p(moves), n, depth, _p(out), _p(solved))
     want = O.scramble(size, moves, init=start)
+    assert (out == want).all()
+    assert (solved.astype(bool) == O.is_solved(size, want)).all()
+    assert solved[20:40].all()
+
+
+@pytest.mark.parametrize("size", (2, 3))
+@pytest.mark.parametrize("depth", (1, 2, 5))
+def test_walk_private_emulation(emul, size, depth):
+    """K2p (lane-private scratch layout, 64-row tiles, even / odd row passes): arbitrary bytes stay a
+    pure gather, rows that end solved are flagged, neighbours' bytes survive the in-place write-back."""
+    rng = np.random.RandomState(21 + size + depth)
+    n = 192
+    A = T.N_ACTIONS[size]
+    start = O.scramble(size, rng.randint(A, size=(n, 9)))
+    start[:20] = rng.randint(0, 256, size=(20, T.N_STICKERS[size]))
+    moves = rng.randint(A, size=(n, depth)).astype(np.uint8)
+    moves[40:60, -1] = 12                                                # no-op row
+    start[20:40] = O.scramble(size, (moves[20:40, ::-1] ^ 1))           # rows that end solved
+    out = np.empty_like(start)
+    solved = np.empty(n, dtype=np.uint8)
+    emul.emul_walk_private(size, _p(start), _p(moves), n, depth, _p(out), _p(solved))
+    want = start.copy()
+    for i in range(n):
+        row = moves[i][moves[i] < A]
+        want[i] = O.scramble(size, row[None, :], init=start[i:i + 1])[0]
     assert (out == want).all()
     assert (solved.astype(bool) == O.is_solved(size, want)).all()
     assert solved[20:40].all()
