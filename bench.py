@@ -130,7 +130,7 @@ def run_reference_arm(args):
         "cpu_baseline": {"value": value, "unit": "transitions/s", "cores": procs, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "transitions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -463,14 +463,30 @@ def run_b200_arm(args):
             line["cpu_baseline_c"] = {"value": cv, "unit": "transitions/s", "cores": threads, "kind": "port",
                                       "sample": "plain-C oracle (OpenMP), 2 Mi instances x depth 30"}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line of the contract, on the process's original stdout."""
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    # Libraries talk on stdout too (NCCL prints its version banner there when NCCL_DEBUG is set):
+    # keep a private handle on the real stdout for the JSON line and point fd 1 at stderr.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=1000)

@@ -59,6 +59,14 @@ const char* cube_last_error(void);
 /* number of SMs of the current device (grid sizing is done inside the library) */
 int cube_sm_count(void);
 
+/* The persistent kernels (cube_scramble, cube_step, cube_walk) run one CTA per SM and fill it
+ * (registers, shared memory).  A kernel of another stream that must make progress WHILE they run --
+ * NCCL's all-reduce of the counters in a multi-GPU job -- would otherwise wait for a CTA to retire.
+ * n SMs are left free for such kernels (default 0, or the CUBE_RESERVED_SMS environment variable).
+ * Measured on 2 x B200 with the 32-byte counter all-reduce per step: no gain (99 % weak-scaling
+ * efficiency either way), so nothing sets it by default. */
+int cube_set_reserved_sms(int n);
+
 /* Fused scramble from the solved cube -- reset()'s loop `init_state(); for a in
  * action_sequence: step(a)` (cube_env.py:61-67) and the per-cube loop of
  * get_random_samples (cube_env.py:187-191), for n instances at once.

@@ -1,5 +1,6 @@
 // extern "C" boundary of libcube_b200.so: argument checks, then the launchers.
 // See include/cube_b200.h for the contract of every entry point.
+#include <cstdlib>
 #include <cstdio>
 #include <cuda_runtime.h>
 
@@ -33,6 +34,24 @@ inline bool misaligned(const void* p) { return (reinterpret_cast<uintptr_t>(p) &
 
 namespace cube {
 
+static int g_reserved_sms = -1;          // -1: take CUBE_RESERVED_SMS (default 0)
+
+int reserved_sms()
+{
+    if (g_reserved_sms < 0) {
+        const char* e = getenv("CUBE_RESERVED_SMS");
+        g_reserved_sms = e ? atoi(e) : 0;
+        if (g_reserved_sms < 0) g_reserved_sms = 0;
+    }
+    return g_reserved_sms;
+}
+
+int persistent_ctas()
+{
+    const int n = sm_count() - reserved_sms();
+    return n < 1 ? 1 : n;
+}
+
 int sm_count()
 {
     static int cached_dev = -1, cached = 0;
@@ -56,6 +75,13 @@ int cube_abi_version(void) { return CUBE_ABI_VERSION; }
 const char* cube_last_error(void) { return t_err; }
 
 int cube_sm_count(void) { return cube::sm_count(); }
+
+int cube_set_reserved_sms(int n)
+{
+    if (n < 0) return fail(CUBE_ERR_ARG, "cube_set_reserved_sms");
+    cube::g_reserved_sms = n;
+    return CUBE_OK;
+}
 
 int cube_scramble(int cube_size, const uint8_t* moves, int64_t n, int depth, uint8_t* states_out,
                   uint8_t* solved, float* reward, uint64_t* counters, void* stream)

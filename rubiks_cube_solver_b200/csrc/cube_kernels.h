@@ -37,5 +37,8 @@ long long launch_leaf2(const uint8_t* states, long long n, uint8_t* children, vo
 int launch_decode2(const void* onehot, int dtype, long long n, uint8_t* out, cudaStream_t stream);
 
 int sm_count();
+// CTAs of a persistent (one-per-SM) grid: sm_count() minus the SMs the caller reserved for other
+// kernels (cube_set_reserved_sms / CUBE_RESERVED_SMS), e.g. one for NCCL's reduction kernel
+int persistent_ctas();
 
 }  // namespace cube

@@ -375,7 +375,7 @@ int launch_one(const uint8_t* moves, long long n, int depth, uint8_t* out, uint8
                 cfg = smem;
             }
             long long grid = (n_tiles + warps - 1) / warps;
-            if (grid > cube::sm_count()) grid = cube::sm_count();
+            if (grid > cube::persistent_ctas()) grid = cube::persistent_ctas();
             sched::Slot* slot = sched::claim_slot();
             if (!slot) return (int)cudaErrorUnknown;
             kern<<<(unsigned)grid, warps * 32, smem, stream>>>(moves, (int)n_tiles, depth, out, solved, reward, counters, slot, sched::tail_div());

@@ -307,7 +307,7 @@ int launch_tiles(const uint8_t* in, const uint8_t* moves, long long n, int depth
                 configured_smem = smem;
             }
             long long grid = (n_tiles + warps - 1) / warps;
-            if (grid > cube::sm_count()) grid = cube::sm_count();
+            if (grid > cube::persistent_ctas()) grid = cube::persistent_ctas();
             sched::Slot* slot = sched::claim_slot();
             if (!slot) return (int)cudaErrorUnknown;
             kern<<<(unsigned)grid, warps * 32, smem, stream>>>(in, moves, (int)n_tiles, depth, out, solved, reward, counters, slot, sched::tail_div());
