@@ -110,6 +110,22 @@ int cube_expand(int cube_size, const uint8_t* states, int64_t n, uint8_t* childr
                 void* parent_onehot, int dtype, uint8_t* solved, float* reward, uint64_t* counters,
                 void* stream);
 
+/* ADI target assembly -- the tail of get_target_value (cube_env.py:239-252) for n parents whose
+ * children came from cube_expand and were valued by the caller's network:
+ *   child_values   [n, A] float32  in   V(child_a)
+ *   child_solved   [n, A] uint8    in   cube_expand's `solved`
+ *   parent_values  [n]    float32  in   V(state)
+ *   scramble_count [n]    int32    in   depth k of every parent (cube_env.py:190-192)
+ *   weight         [table_len] float64 in  weight[k] = k ** (-temperature), computed by the HOST so the
+ *                                       priorities match Python's float power bit for bit
+ *   target_value   [n]    float32  out  1.0 at the first solved child, else max_a(V(child_a) + (-1.0))
+ *   target_policy  [n]    int32    out  that child (the first maximum wins, like torch.max)
+ *   error          [n]    float64  out  |V(state) - target_value| * weight[scramble_count] */
+int cube_adi_targets(int cube_size, const float* child_values, const uint8_t* child_solved,
+                     const float* parent_values, const int32_t* scramble_count, const double* weight,
+                     int table_len, int64_t n, float* target_value, int32_t* target_policy, double* error,
+                     void* stream);
+
 /* state_to_sim_state (cube_env.py:154-175 + py222 getStickers): one-hot [n, 7, 21] of
  * `dtype` -> sticker rows [n, 24].  2x2x2 only: for cube_size 3 the reference raises
  * NotImplementedError (cube_env.py:171-172) and this returns CUBE_ERR_SIZE. */

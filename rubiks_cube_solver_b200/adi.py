@@ -5,8 +5,8 @@ The reference emits one sample after EVERY move of every scramble (cube_env.py:1
 so the parents of an ADI batch are all scramble prefixes.  Here the prefixes are produced
 step by step on the device (K2, one launch per depth level, step-major so each level is a
 contiguous slab), expanded into all children + their one-hot rows by K3, evaluated by the
-caller's network in one batch, and reduced to (target_value, target_policy, error) with
-the reference's rules: first solved child a -> (1.0, a) (cube_env.py:217-220), otherwise
+caller's network in one batch, and reduced to (target_value, target_policy, error) by kernel K4
+(C ABI cube_adi_targets) with the reference's rules: first solved child a -> (1.0, a) (cube_env.py:217-220), otherwise
 max_a(V(child_a) + (-1.0)) with the first maximum winning (cube_env.py:240-246), and
 error = |V(state) - target| * depth**(-temperature) in float64 (cube_env.py:247-251).
 """
@@ -36,29 +36,11 @@ def scramble_prefixes(cube_size, moves):
     return trail, n_pad
 
 
-def _first_index_where(mask):
-    """Index of the first True per row, A if none."""
-    a = mask.shape[1]
-    idx = torch.arange(a, device=mask.device).expand_as(mask)
-    return torch.where(mask, idx, torch.full_like(idx, a)).min(dim=1).values
-
-
-def assemble_targets(child_values, solved, parent_values, depth_of_row, temperature):
-    """cube_env.py:239-252 on tensors.  child_values [P, A] float32 = V(child); solved [P, A];
-    parent_values [P] float32; depth_of_row [P] (scramble counts).  Returns
-    (target_value float32 [P], target_policy int64 [P], error float64 [P])."""
-    a = child_values.shape[1]
-    value = child_values.float() + torch.tensor(-1.0, dtype=torch.float32, device=child_values.device)
-    best = value.max(dim=1, keepdim=True).values
-    tp = _first_index_where(value == best)
-    tv = best.squeeze(1)
-    first = _first_index_where(solved.bool())
-    has = first < a
-    tv = torch.where(has, torch.ones_like(tv), tv)
-    tp = torch.where(has, first, tp)
-    weight = depth_of_row.double() ** (-1.0 * float(temperature))
-    err = (parent_values.double() - tv.double()).abs() * weight
-    return tv, tp, err
+def assemble_targets(cube_size, child_values, solved, parent_values, depth_of_row, temperature):
+    """cube_env.py:239-252 for a batch, on the device (kernel K4, C ABI cube_adi_targets).
+    child_values [P, A] float32 = V(child); solved [P, A]; parent_values [P] float32; depth_of_row [P]
+    (scramble counts).  Returns (target_value float32 [P], target_policy int64 [P], error float64 [P])."""
+    return ops.adi_targets(cube_size, child_values, solved, parent_values, depth_of_row, temperature)
 
 
 @torch.no_grad()
@@ -90,7 +72,7 @@ def generate_samples(cube_size, moves, model, temperature, model_device=None, on
     child_v = values_of(res["child_onehot"].view(p * a, r, c)).view(p, a)
     parent_v = values_of(res["parent_onehot"])
     depth_of_row = torch.arange(1, depth + 1, device=dev).repeat_interleave(n_pad)
-    tv, tp, err = assemble_targets(child_v, res["solved"], parent_v, depth_of_row, temperature)
+    tv, tp, err = assemble_targets(cube_size, child_v, res["solved"], parent_v, depth_of_row, temperature)
 
     # step-major (k, cube) -> cube-major (cube, k), dropping the padding cubes
     def cube_major(t):

@@ -124,6 +124,20 @@ int cube_solved(int cube_size, const uint8_t* states, int64_t n, uint8_t* solved
                                                  (unsigned long long*)counters, (cudaStream_t)stream));
 }
 
+int cube_adi_targets(int cube_size, const float* child_values, const uint8_t* child_solved, const float* parent_values,
+                     const int32_t* scramble_count, const double* weight, int table_len, int64_t n,
+                     float* target_value, int32_t* target_policy, double* error, void* stream)
+{
+    CUBE_CHECK_SIZE("cube_adi_targets");
+    if (n < 0 || table_len < 0 || (n > 0 && (!child_values || !child_solved || !parent_values || !scramble_count ||
+                                             !weight || !target_value || !target_policy || !error)))
+        return fail(CUBE_ERR_ARG, "cube_adi_targets");
+    if (misaligned(child_values)) return fail(CUBE_ERR_ALIGN, "cube_adi_targets");
+    CUBE_DONE("cube_adi_targets", cube::launch_adi_targets(cube_size, child_values, child_solved, parent_values,
+                                                           scramble_count, weight, table_len, n, target_value,
+                                                           target_policy, error, (cudaStream_t)stream));
+}
+
 int cube_encode(int cube_size, const uint8_t* states, int64_t n, void* onehot, int dtype, void* stream)
 {
     CUBE_CHECK_SIZE("cube_encode");

@@ -186,6 +186,35 @@ def expand(cube_size, states, dtype=torch.bfloat16, want_children=False, want_ch
                 reward=reward)
 
 
+def adi_targets(cube_size, child_values, child_solved, parent_values, scramble_count, temperature):
+    """ADI targets of cube_env.py:239-252 for a batch (C ABI cube_adi_targets).
+
+    child_values float32 [P, A] = V(child); child_solved uint8 [P, A]; parent_values float32 [P];
+    scramble_count int32 [P].  Returns (target_value float32 [P], target_policy int64 [P],
+    error float64 [P]).  The weights k ** (-temperature) are computed here with Python's float power,
+    exactly as the reference does, and looked up on the device."""
+    _, a, _ = _geom(cube_size)
+    child_values = _require_cuda(child_values.float().contiguous(), "child_values", torch.float32)
+    p = child_values.shape[0]
+    dev = child_values.device
+    child_solved = _require_cuda(child_solved.contiguous(), "child_solved", torch.uint8)
+    parent_values = _require_cuda(parent_values.float().contiguous(), "parent_values", torch.float32)
+    scramble_count = scramble_count.to(device=dev, dtype=torch.int32).contiguous()
+    if child_values.shape != (p, a) or child_solved.shape != (p, a) or parent_values.numel() != p or scramble_count.numel() != p:
+        raise ValueError("adi_targets: shapes must be [P, %d], [P, %d], [P], [P]" % (a, a))
+    kmax = int(scramble_count.max().item()) if p else 0
+    table = [0.0] + [k ** (-1 * temperature) for k in range(1, kmax + 1)]          # cube_env.py:247
+    weight = torch.tensor(table, dtype=torch.float64, device=dev)
+    tv = torch.empty(p, dtype=torch.float32, device=dev)
+    tp = torch.empty(p, dtype=torch.int32, device=dev)
+    err = torch.empty(p, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().cube_adi_targets(cube_size, _ptr(child_values), _ptr(child_solved), _ptr(parent_values),
+                                                _ptr(scramble_count), _ptr(weight), len(table), p, _ptr(tv), _ptr(tp),
+                                                _ptr(err), _stream(dev)), "cube_adi_targets")
+    return tv, tp.long(), err
+
+
 def decode(cube_size, onehot):
     """One-hot [N, 7, 21] -> sticker rows [N, 24]; 2x2x2 only (C ABI cube_decode)."""
     _geom(cube_size)

@@ -402,6 +402,35 @@ def test_adi_against_reference_golden(size):
         k += 1
 
 
+@pytest.mark.parametrize("size", SIZES)
+@pytest.mark.parametrize("temperature", (1.0, 0.5, 0.3))
+def test_adi_targets_kernel_vs_reference_rules(size, temperature):
+    """K4 (cube_adi_targets) against the reference's rules restated per parent in Python:
+    first solved child -> (1.0, a); else torch.max of float32 V(child) + (-1.0), first maximum wins
+    (cube_env.py:217-220, 243-245); error = |V(s) - target| * k ** (-T) in Python floats (:247-251)."""
+    rng = np.random.RandomState(5 + size)
+    a, p = T.N_ACTIONS[size], 5000
+    cv = rng.randn(p, a).astype(np.float32)
+    cv[:500] = np.round(cv[:500])                                    # ties: the first maximum must win
+    solved = (rng.rand(p, a) < 0.03).astype(np.uint8)
+    solved[1000:1010] = 1
+    pv = rng.randn(p).astype(np.float32)
+    k = rng.randint(1, 31, size=p).astype(np.int32)
+    tv, tp, err = ops.adi_targets(size, torch.from_numpy(cv).to(dev()), torch.from_numpy(solved).to(dev()),
+                                  torch.from_numpy(pv).to(dev()), torch.from_numpy(k).to(dev()), temperature)
+    tv, tp, err = tv.cpu().numpy(), tp.cpu().numpy(), err.cpu().numpy()
+    assert tv.dtype == np.float32 and tp.dtype == np.int64 and err.dtype == np.float64
+    for i in range(p):
+        if solved[i].any():
+            want_v, want_p = 1.0, int(solved[i].argmax())
+        else:
+            value = torch.from_numpy(cv[i]) + torch.full((a,), -1.0)
+            m, j = torch.max(value, -1, keepdim=True)
+            want_v, want_p = m.item(), j.item()
+        want_e = abs(float(pv[i]) - want_v) * int(k[i]) ** (-1 * temperature)
+        assert float(tv[i]) == want_v and int(tp[i]) == want_p and float(err[i]) == want_e, i
+
+
 def test_batched_env_matches_reference_seeds():
     for size in SIZES:
         g = golden("config1_%d.npz" % size)
