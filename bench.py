@@ -92,6 +92,7 @@ def cpu_c_oracle(cube_size, depth, n):
     import numpy as np
     from oracle import cube_c
     moves = np.random.RandomState(0).randint(12 if cube_size == 3 else 6, size=(n, depth)).astype(np.uint8)
+    cube_c.set_threads(host_procs())                         # torch / torchrun may have pinned OpenMP to one thread
     cube_c.scramble(cube_size, moves[: n // 8])
     t0 = time.perf_counter()
     cube_c.scramble(cube_size, moves)
