@@ -272,7 +272,70 @@ def measure_other_configs(torch, ops, adi, dev, peak_gbs):
                                                 want_child_onehot=False, want_parent_onehot=True), 10)
     entry("config5_2x2_mcts_leaf_expand_1Mi", t, n, "leaves/s", n * (24 + 294 + 144 + 6 + 24))   # + reward f32 x6
     out["drop_in_get_random_samples"] = measure_drop_in_adi(torch, dev)
+    out["mcts_2x2_batched_search"] = measure_mcts(torch, dev)
     return out
+
+
+def measure_mcts(torch, dev):
+    """test.py's MCTS branch (test.py:139-147: up to numMCTSSim = 50 simulations per cube, config.yaml:29)
+    for 4096 2x2x2 cubes in lock-step through BatchedMCTS (device tree store + one leaf batch per
+    simulation), beside the reference-semantics per-cube search (oracle/mcts_ref.py) on one host core.
+    Net: DeepCube's 2x2x2 layer shapes (147-512-128-{64-6, 64-1}, pretrained/222model.pt), random init."""
+    import random
+    import numpy as np
+    from rubiks_cube_solver_b200 import mcts_batch, ops
+    from oracle import mcts_ref
+    from oracle.scalar_env import ScalarCubeEnv
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            nn = torch.nn
+            self.enc = nn.Sequential(nn.Flatten(), nn.Linear(147, 512), nn.ELU(), nn.Linear(512, 128), nn.ELU())
+            self.pol = nn.Sequential(nn.Linear(128, 64), nn.ELU(), nn.Linear(64, 6))
+            self.val = nn.Sequential(nn.Linear(128, 64), nn.ELU(), nn.Linear(64, 1))
+
+        def forward(self, x):
+            if x.dim() == 2:
+                x = x.unsqueeze(0)
+            h = self.enc(x)
+            return self.val(h), self.pol(h)
+
+        def predict(self, x):                                  # model.py:78-91
+            v, p = self.forward(torch.tensor(x).float())
+            return v.numpy()[0], torch.nn.functional.softmax(p, dim=-1).numpy()[0]
+
+    torch.manual_seed(1)
+    net = Net()
+    gpu_net = Net().to(dev)
+    gpu_net.load_state_dict(net.state_dict())
+    n_trees, num_sim, depth = 4096, 50, 8
+    gen = torch.Generator(device=dev).manual_seed(77)
+    roots, _, _ = ops.scramble(2, torch.randint(0, 6, (n_trees, depth), dtype=torch.uint8, device=dev, generator=gen),
+                               want_flags=False)
+    table = torch.randint(0, 6, (n_trees, num_sim + 1), generator=torch.Generator().manual_seed(3))
+    search = mcts_batch.BatchedMCTS(gpu_net, 2, num_sim=num_sim)
+    search.run(roots[:256], rand_table=table[:256])            # warm-up
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    res = search.run(roots, rand_table=table)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    sims = int(res["n_sims"].sum())
+    env = ScalarCubeEnv(2)
+    torch.set_num_threads(1)
+    cpu_sims, t0 = 0, time.perf_counter()
+    with torch.no_grad():
+        for i in range(3):
+            env.sim_cube = roots[i].cpu().numpy().astype(np.int64)
+            env.cube = env._observe(env.sim_cube)
+            _, used, _ = mcts_ref.solve(net.predict, env, env.cube, num_sim, random.Random(i))
+            cpu_sims += used
+    cpu_dt = time.perf_counter() - t0
+    return {"simulations_per_s_batched_gpu": sims / dt, "simulations_per_s_reference_semantics_1_core": cpu_sims / cpu_dt,
+            "trees": n_trees, "solved": int(res["solved"].sum()), "ms": dt * 1e3,
+            "note": "one simulation = traverse + leaf expansion (6 children, net value/policy) + back-propagation "
+                    "(mcts.py:36-130); 4096 cubes scrambled 8 deep, 50 simulations each"}
 
 
 def measure_drop_in_adi(torch, dev):

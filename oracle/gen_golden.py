@@ -42,6 +42,83 @@ class ExactValueNet(torch.nn.Module):
         return v, torch.zeros(x.shape[0], self.action_dim)
 
 
+class ExactSearchNet(torch.nn.Module):
+    """DeepCube-shaped net for the MCTS vectors whose value AND softmax policy are bit-identical on
+    any device: the value is a sum of multiples of 1/8; the logits are 0 or -inf (chosen by small
+    integer hashes of the observation), so softmax is 1/m on m actions and exactly 0 on the rest.
+    `predict` restates model.py:78-91."""
+
+    def __init__(self, state_dim, action_dim, seed=5):
+        super().__init__()
+        r = np.random.RandomState(seed)
+        d = state_dim[0] * state_dim[1]
+        self.register_buffer("wv", torch.tensor(r.randint(-8, 9, size=(d,)).astype(np.float32) / 8.0))
+        self.register_buffer("wm", torch.tensor(r.randint(0, 4, size=(d, action_dim)).astype(np.float32)))
+        self.action_dim = action_dim
+
+    def forward(self, x):
+        if x.dim() == 2:
+            x = x.unsqueeze(0)
+        flat = x.reshape(x.shape[0], -1).float()
+        v = (flat * self.wv).sum(dim=1, keepdim=True)
+        h = flat @ self.wm                                          # small integers: exact
+        banned = torch.remainder(h, 3.0) == 0
+        banned[:, 0] = False
+        logits = torch.where(banned, torch.full_like(h, float("-inf")), torch.zeros_like(h))
+        return v, logits
+
+    def predict(self, x):
+        x = torch.tensor(x).float().detach()
+        value, policy = self.forward(x)
+        policy = torch.nn.functional.softmax(policy, dim=-1)
+        return value.numpy()[0], policy.numpy()[0]
+
+
+MCTS_CFG = {"mcts": {"numMCTSSim": 50, "cpuct": 1.0, "virtual_loss_const": 150, "value_min": -10.0}}
+
+
+def mcts_cases(size):
+    """(seed, scramble depth) of the golden MCTS searches."""
+    return [(s, 1 + s % (5 if size == 3 else 7)) for s in range(16)]
+
+
+def _mcts(R, size):
+    """The reference's own MCTS (mcts.py) on its own env: test.py's MCTS branch for one time step
+    (test.py:139-147), `random` seeded per cube with 1000 + seed."""
+    import importlib
+    import random
+    mcts_mod = importlib.import_module("mcts")
+    env = R.make_env(size)
+    net = ExactSearchNet(env.state_dim, env.action_dim)
+    cfg = dict(MCTS_CFG, test={"cube_size": size})
+    n_sim = cfg["mcts"]["numMCTSSim"]
+    A = env.action_dim
+    rows = dict(actions=[], n_actions=[], n_sims=[], n_nodes=[], root_N=[], root_W=[], root_L=[])
+    for seed, depth in mcts_cases(size):
+        state = env.reset(seed=seed, scramble_count=depth)
+        random.seed(1000 + seed)
+        tree = mcts_mod.MCTS(net, cfg)
+        result, used = None, n_sim
+        with torch.no_grad():
+            for k in range(n_sim):
+                result = tree.train(state, env)
+                if result is not None:
+                    used = k + 1
+                    break
+        root = tree.children_and_data[np.array2string(state)]
+        acts = list(result) if result is not None else []
+        rows["actions"].append(acts + [-1] * (n_sim + 1 - len(acts)))
+        rows["n_actions"].append(len(acts))
+        rows["n_sims"].append(used)
+        rows["n_nodes"].append(len(tree.children_and_data))
+        rows["root_N"].append([int(v) for v in root[tree.n_of_v_i]])
+        rows["root_W"].append([float(np.asarray(v).reshape(-1)[0]) for v in root[tree.s_i]])
+        rows["root_L"].append([int(v) for v in root[tree.v_l_i]])
+    out = {k: np.array(v) for k, v in rows.items()}
+    out["cases"] = np.array(mcts_cases(size))
+    return out
+
+
 def _config1(R, size, n_seeds=1024, depth=10):
     env = R.make_env(size)
     moves, stickers, onehot, reward, done = [], [], [], [], []
@@ -160,6 +237,7 @@ def main():
         np.savez_compressed(os.path.join(OUT, "walks_%d.npz" % size), **_walks(R, size))
         np.savez_compressed(os.path.join(OUT, "adi_%d.npz" % size), **_adi(R, size))
         np.savez_compressed(os.path.join(OUT, "expand_%d.npz" % size), **_expand(R, size))
+        np.savez_compressed(os.path.join(OUT, "mcts_%d.npz" % size), **_mcts(R, size))
     # 2x2x2 decode (state_to_sim_state, cube_env.py:154-175)
     env = R.make_env(2)
     rng = np.random.RandomState(3)

@@ -525,3 +525,59 @@ def test_mcts_leaf_batch_matches_per_leaf_expand(size):
             _, _, done, _ = child.step(a)
             assert (out["children"][i, a].cpu().numpy() == child.sim_cube).all() and bool(out["done"][i, a]) == done
     assert bool(out["done"][0, 3])
+
+
+@pytest.mark.parametrize("size", SIZES)
+def test_batched_mcts_matches_reference_golden(size):
+    """BatchedMCTS (device tree store, all cubes in lock-step) against the reference's own mcts.py run
+    on its own env (tests/golden/mcts_*.npz, oracle/gen_golden.py): returned action lists, simulations
+    used, node counts and the root's N / W / L after the search."""
+    from rubiks_cube_solver_b200 import mcts_batch
+    from oracle.gen_golden import ExactSearchNet, MCTS_CFG
+    g = golden("mcts_%d.npz" % size)
+    cases = g["cases"]
+    roots = np.stack([O.scramble(size, O.reference_moves(size, int(sd), int(d))[None])[0] for sd, d in cases])
+    net = ExactSearchNet(T.STATE_DIM[size], T.N_ACTIONS[size]).to(dev())
+    cfg = MCTS_CFG["mcts"]
+    search = mcts_batch.BatchedMCTS(net, size, num_sim=cfg["numMCTSSim"], cpuct=cfg["cpuct"],
+                                    virtual_loss_const=cfg["virtual_loss_const"], value_min=cfg["value_min"])
+    out = search.run(cu(roots), seeds=[1000 + int(sd) for sd, _ in cases])
+    assert (out["n_sims"].cpu().numpy() == g["n_sims"]).all()
+    assert (out["n_actions"].cpu().numpy() == g["n_actions"]).all()
+    assert (out["actions"].cpu().numpy() == g["actions"]).all()
+    assert (out["n_nodes"].cpu().numpy() == g["n_nodes"]).all()
+    assert (out["root_N"].cpu().numpy() == g["root_N"]).all()
+    assert (out["root_L"].cpu().numpy() == g["root_L"]).all()
+    assert (out["root_W"].cpu().numpy().astype(np.float64) == g["root_W"]).all()
+    assert out["solved"].any() and not out["solved"].all()
+
+
+@pytest.mark.parametrize("size", SIZES)
+def test_batched_mcts_matches_oracle_more_cases(size):
+    """More cubes, fewer simulations, against oracle/mcts_ref.py (itself pinned to the reference by
+    tests/test_oracle.py): ragged batch sizes and cubes solved at different simulations."""
+    import random
+    from rubiks_cube_solver_b200 import mcts_batch
+    from oracle import mcts_ref
+    from oracle.gen_golden import ExactSearchNet
+    from oracle.scalar_env import ScalarCubeEnv
+    n, num_sim = 70, 12
+    rng = np.random.RandomState(17 + size)
+    A = T.N_ACTIONS[size]
+    depths = rng.randint(1, 4, size=n)
+    roots = np.stack([O.scramble(size, rng.randint(A, size=(1, int(d))))[0] for d in depths])
+    gpu_net = ExactSearchNet(T.STATE_DIM[size], A).to(dev())
+    cpu_net = ExactSearchNet(T.STATE_DIM[size], A)
+    out = mcts_batch.BatchedMCTS(gpu_net, size, num_sim=num_sim).run(cu(roots), seeds=list(range(n)))
+    env = ScalarCubeEnv(size)
+    for i in range(n):
+        env.sim_cube = roots[i].astype(np.int64)
+        env.cube = env._observe(env.sim_cube)
+        with torch.no_grad():
+            acts, used, tree = mcts_ref.solve(cpu_net.predict, env, env.cube, num_sim, random.Random(i))
+        k = int(out["n_actions"][i])
+        assert out["actions"][i, :k].tolist() == (acts or []), i
+        assert int(out["n_sims"][i]) == used and int(out["n_nodes"][i]) == len(tree.nodes), i
+        root = tree.nodes[tree.key(env.cube)]
+        assert out["root_N"][i].tolist() == [int(v) for v in root[3]], i
+        assert out["root_W"][i].tolist() == [float(v) for v in root[2]], i

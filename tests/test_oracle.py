@@ -230,3 +230,30 @@ def test_reset_sequence_equals_one_big_draw():
         a = np.stack([r1.randint(A, size=30) for _ in range(20)])
         b = r2.randint(A, size=(20, 30))
         assert (a == b).all()
+
+
+@pytest.mark.parametrize("size", (2, 3))
+def test_mcts_oracle_matches_reference_golden(size):
+    """oracle/mcts_ref.py against the reference's own mcts.py (golden vectors generated by running it,
+    oracle/gen_golden.py::_mcts): action lists, simulations used, node counts, root statistics."""
+    import random
+    import torch
+    from oracle import mcts_ref
+    from oracle.gen_golden import ExactSearchNet, MCTS_CFG
+    from oracle.scalar_env import ScalarCubeEnv
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mcts_%d.npz" % size))
+    env = ScalarCubeEnv(size)
+    net = ExactSearchNet(env.state_dim, env.action_dim)
+    cfg = MCTS_CFG["mcts"]
+    for i, (seed, depth) in enumerate(g["cases"]):
+        obs = env.reset(seed=int(seed), scramble_count=int(depth))
+        with torch.no_grad():
+            acts, used, tree = mcts_ref.solve(net.predict, env, obs, cfg["numMCTSSim"], random.Random(1000 + int(seed)),
+                                              loss_constant=cfg["virtual_loss_const"], cpuct=cfg["cpuct"],
+                                              value_min=cfg["value_min"])
+        root = tree.nodes[tree.key(obs)]
+        assert (acts or []) == g["actions"][i][:g["n_actions"][i]].tolist()
+        assert used == g["n_sims"][i] and len(tree.nodes) == g["n_nodes"][i]
+        assert [int(v) for v in root[3]] == g["root_N"][i].tolist()
+        assert [float(v) for v in root[2]] == g["root_W"][i].tolist()
+        assert [int(v) for v in root[4]] == g["root_L"][i].tolist()
