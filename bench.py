@@ -502,7 +502,7 @@ def run_b200_arm(args):
         "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": step_s * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": WORKLOAD, "cube_size": size, "depth": depth, "instances_per_gpu": n,
-                   "instances_total": world * n, "l2": "inputs (252 MB/GPU) and outputs (495 MB/GPU) exceed the 126 MB L2",
+                   "instances_total": world * n, "sm_count": R.load_library().cube_sm_count(), "l2": "inputs (252 MB/GPU) and outputs (495 MB/GPU) exceed the 126 MB L2",
                    "collective": "int64[4] all-reduce(SUM) of solved/produced counters per step, asynchronous"},
         "solved_total": solved_total, "reward_total": 2 * solved_total - produced_total,
         "e2e": e2e, "roofline": roofline, "gpu_launches": args.steps, "clocks": clocks.summary(),
