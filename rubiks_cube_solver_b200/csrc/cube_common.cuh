@@ -54,6 +54,20 @@ CUBE_HD uint32_t cube_hi16(uint32_t x)
 #endif
 }
 
+// sum of byte products + c (IDP.4A): measured to issue beside PRMT (tools/microbench_pipes.cu), i.e. it
+// runs on the FMA pipe -- used to pull ONE byte out of a register (weights = 0 except one) and scale
+// and offset it in the same instruction, where a PRMT + multiply + add would load the ALU pipe
+CUBE_HD uint32_t cube_dp4a(uint32_t x, uint32_t w, uint32_t c)
+{
+#if defined(__CUDA_ARCH__)
+    return __dp4a(x, w, c);
+#else
+    uint32_t r = c;
+    for (int i = 0; i < 4; ++i) r += ((x >> (8 * i)) & 0xffu) * ((w >> (8 * i)) & 0xffu);
+    return r;
+#endif
+}
+
 CUBE_HD uint32_t cube_shr2(uint32_t x)          // x >> 2, also on the FMA pipe
 {
 #if defined(__CUDA_ARCH__)
@@ -136,7 +150,13 @@ CUBE_HD uint32_t cubie_fold_twist(uint32_t c)
 CUBE_HD uint32_t cubie_reduce_twist(uint32_t c)
 {
     c = cubie_fold_twist(cubie_fold_twist(c));
-    uint32_t ge3 = ((c + 0x28282828u) >> 6) & 0x01010101u;      // (f + 5) >= 8  <=>  f >= 3
+#if defined(__CUDA_ARCH__)
+    uint32_t sh6;                                                // >> 6 on the FMA pipe
+    asm("mul.hi.u32 %0, %1, 67108864;" : "=r"(sh6) : "r"(c + 0x28282828u));
+#else
+    const uint32_t sh6 = (c + 0x28282828u) >> 6;
+#endif
+    uint32_t ge3 = sh6 & 0x01010101u;                            // (f + 5) >= 8  <=>  f >= 3
     return c - ge3 * 24u;                                        // 3 << 3
 }
 

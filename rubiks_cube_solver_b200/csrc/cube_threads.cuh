@@ -114,26 +114,27 @@ struct PairTableShared {
 };
 #endif
 
-// Colour LUT access of the finishing pass.  Host: pointers.  Device: each LUT sits on a 256-byte
-// boundary of the shared window, so "base | 4 * cubie byte" is ONE byte permute (byte 0 from the
-// scaled cubie register, bytes 1..3 from the base) and the load needs no address arithmetic.
+// Colour LUT access of the finishing pass.  Host: pointers.  Device: "base + 4 * cubie byte q" is ONE
+// dot-product instruction (weights 4 << 8q, accumulator = the LUT's shared-window address): byte
+// extraction, scaling and address arithmetic on the FMA pipe instead of PRMT + shift on the ALU pipe.
 struct ColourLutHost {
     const uint32_t* c;
     const uint32_t* e;
-    CUBE_HD uint32_t corner(uint32_t x4, int q) const { return cube_lut_at(c, cube_prmt(x4, 0u, 0x4440u + q)); }
-    CUBE_HD uint32_t edge(uint32_t x4, int q) const { return cube_lut_at(e, cube_prmt(x4, 0u, 0x4440u + q)); }
+    // x = four cubie bytes; entry of byte q
+    CUBE_HD uint32_t corner(uint32_t x, int q) const { return cube_lut_at(c, cube_dp4a(x, 4u << (8 * q), 0u)); }
+    CUBE_HD uint32_t edge(uint32_t x, int q) const { return cube_lut_at(e, cube_dp4a(x, 4u << (8 * q), 0u)); }
 };
 #if defined(__CUDACC__)
 struct ColourLutShared {
-    uint32_t cbase, ebase;                              // shared-window addresses, multiples of 256
+    uint32_t cbase, ebase;                              // shared-window addresses
     static __device__ __forceinline__ uint32_t lds32(uint32_t addr)
     {
         uint32_t v;
         asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
         return v;
     }
-    __device__ __forceinline__ uint32_t corner(uint32_t x4, int q) const { return lds32(cube_prmt(x4, cbase, 0x7650u + q)); }
-    __device__ __forceinline__ uint32_t edge(uint32_t x4, int q) const { return lds32(cube_prmt(x4, ebase, 0x7650u + q)); }
+    __device__ __forceinline__ uint32_t corner(uint32_t x, int q) const { return lds32(cube_dp4a(x, 4u << (8 * q), cbase)); }
+    __device__ __forceinline__ uint32_t edge(uint32_t x, int q) const { return lds32(cube_dp4a(x, 4u << (8 * q), ebase)); }
 };
 #endif
 
@@ -182,6 +183,29 @@ CUBE_HD void pair_apply(CubieState& s, const TBL& tbl, uint32_t addr)
 // <= 10 + 20 stays below 32).  DEPTH > 0 fixes the depth at compile time (straight-line code for
 // the reference's default scramble depth, config.yaml:7 sample_scramble_count = 30, and
 // BASELINE config 2's depth 20); DEPTH == 0 takes it from `depth_rt`.
+// Byte shift of instance k's move stream relative to the word grid when it is the same for every
+// lane (compile-time depth, the kernel's lane -> row maps: 3x3x3 rows 2l + k, 2x2x2 rows l + 32k);
+// -1 = depends on the lane.
+template <int SIZE, int DEPTH>
+CUBE_HD constexpr int pair_static_shift(int k)
+{
+    return DEPTH <= 0 ? -1
+         : SIZE == 3 ? ((2 * DEPTH) % 4 == 0 ? ((k * DEPTH) % 4) * 8 : -1)
+                     : (DEPTH % 4 == 0 ? 0 : -1);
+}
+
+// pair rows (bytes 1 and 3) of the next four moves: (move word) * 269 + bias.  With a static shift
+// the funnel shift (ALU pipe) is folded into multiply-adds (FMA pipe):
+//   shift 0: lo * 269;   shift 16: (lo >> 16) * 269 + hi * (269 << 16)   (mod 2^32, like the product)
+template <int SSH>
+CUBE_HD uint32_t pair_rows_word(uint32_t lo, uint32_t hi, uint32_t sh, uint32_t bias)
+{
+    constexpr uint32_t K = (uint32_t)(CUBE_PAIR_BASE + 256);
+    if (SSH == 0) return lo * K + bias;
+    if (SSH == 16) return hi * (K << 16) + (cube_hi16(lo) * K + bias);
+    return cube_funnel_r(lo, hi, sh) * K + bias;
+}
+
 template <int SIZE, int DEPTH, int NS, class TBL>
 CUBE_HD void scramble_pairs_run(CubieState (&st)[NS], const int (&rows)[NS], int depth_rt, const uint8_t* s_moves,
                                 const TBL& tbl, uint32_t lanereg)
@@ -200,11 +224,18 @@ CUBE_HD void scramble_pairs_run(CubieState (&st)[NS], const int (&rows)[NS], int
     }
     auto word = [&](int j) {
         uint32_t y[NS];
-#pragma unroll
-        for (int k = 0; k < NS; ++k) {
-            const uint32_t hi = mw[wi[k] + j + 1];
-            y[k] = cube_funnel_r(lo[k], hi, sh[k]) * (uint32_t)(CUBE_PAIR_BASE + 256) + bias;   // bytes 1, 3 = pair rows
-            lo[k] = hi;
+        static_assert(NS <= 2, "static shifts are written out for two instances per lane");
+        {
+            constexpr int s0 = (NS == 2) ? pair_static_shift<SIZE, DEPTH>(0) : -1;
+            const uint32_t hi = (s0 == 0) ? 0u : mw[wi[0] + j + 1];
+            y[0] = pair_rows_word<s0>(lo[0], hi, sh[0], bias);                  // bytes 1, 3 = pair rows
+            lo[0] = (s0 == 0) ? mw[wi[0] + j + 1] : hi;
+        }
+        if (NS == 2) {
+            constexpr int s1 = pair_static_shift<SIZE, DEPTH>(1);
+            const uint32_t hi = (s1 == 0) ? 0u : mw[wi[NS - 1] + j + 1];
+            y[NS - 1] = pair_rows_word<s1>(lo[NS - 1], hi, sh[NS - 1], bias);
+            lo[NS - 1] = (s1 == 0) ? mw[wi[NS - 1] + j + 1] : hi;
         }
 #pragma unroll
         for (int k = 0; k < NS; ++k) pair_apply<SIZE>(st[k], tbl, cube_prmt(y[k], lanereg, 0x5514u));
@@ -278,21 +309,19 @@ CUBE_HD bool scramble_pairs_finish(CubieState& st, int row, const LUT& lut, uint
     st.c1 = cubie_reduce_twist(st.c1);
     bool ok = (st.c0 == 0x03020100u) & (st.c1 == 0x07060504u);
     uint32_t L[20];
-    const uint32_t c0 = st.c0 * 4u, c1 = st.c1 * 4u;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        L[q] = lut.corner(c0, q);
-        L[4 + q] = lut.corner(c1, q);
+        L[q] = lut.corner(st.c0, q);
+        L[4 + q] = lut.corner(st.c1, q);
     }
     if (SIZE == 3) {
         const uint32_t f0 = cubie_canonical_flip(st.e0), f1 = cubie_canonical_flip(st.e1), f2 = cubie_canonical_flip(st.e2);
         ok = ok && ((f0 == 0x03020100u) & (f1 == 0x07060504u) & (f2 == 0x0b0a0908u));
-        const uint32_t e0 = f0 * 4u, e1 = f1 * 4u, e2 = f2 * 4u;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            L[8 + q] = lut.edge(e0, q);
-            L[12 + q] = lut.edge(e1, q);
-            L[16 + q] = lut.edge(e2, q);
+            L[8 + q] = lut.edge(f0, q);
+            L[12 + q] = lut.edge(f1, q);
+            L[16 + q] = lut.edge(f2, q);
         }
         uint32_t w[13], h;
         uint8_t* rowp = s_out + 54 * row;
