@@ -558,7 +558,7 @@ def main():
     ap.add_argument("--impl", choices=("b200", "reference"), default="b200")
     ap.add_argument("--instances-per-gpu", type=int, default=N_PER_GPU)
     ap.add_argument("--e2e-steps", type=int, default=5)
-    ap.add_argument("--e2e-chunk", type=int, default=1 << 20)
+    ap.add_argument("--e2e-chunk", type=int, default=1 << 19)
     ap.add_argument("--cpu-cubes-per-proc", type=int, default=15000)
     ap.add_argument("--ref-seconds", type=float, default=45.0)
     ap.add_argument("--skip-cpu", action="store_true")
