@@ -132,6 +132,80 @@ def test_scramble_ragged_sizes(size, n):
     assert (states.cpu().numpy() == want).all() and (solved.cpu().numpy().astype(bool) == ws).all()
 
 
+@pytest.mark.parametrize("size", SIZES)
+@pytest.mark.parametrize("n,depth", [(n, d) for n in (63, 64, 65, 129) for d in (2, 95, 96, 97)]
+                         + [(64 * 148 * 24 + 1, 30), (64 * 148 * 32 + 65, 20)])
+def test_scramble_tile_and_depth_boundaries(size, n, depth):
+    """K1p handles whole 64-row tiles at depth 1..96; the single-move kernels take the ragged tail,
+    deeper sequences and everything around: the seams must not show."""
+    rng = np.random.RandomState(n % 1000 + depth)
+    moves = rng.randint(T.N_ACTIONS[size], size=(n, depth)).astype(np.uint8)
+    if depth % 2 == 0:
+        moves[-3:, depth // 2:] = moves[-3:, :depth // 2][:, ::-1] ^ 1                   # the last rows end solved
+    counters = ops.new_counters(dev())
+    states, solved, reward = ops.scramble(size, cu(moves), counters=counters)
+    want, ws, wr, cnt = C.scramble(size, moves)
+    assert (states.cpu().numpy() == want).all()
+    assert (solved.cpu().numpy().astype(bool) == ws).all() and (depth % 2 or ws[-3:].all())
+    assert (reward.cpu().numpy() == wr).all()
+    assert counters.tolist()[:2] == [cnt, n]
+
+
+@pytest.mark.parametrize("size", SIZES)
+@pytest.mark.parametrize("n", (63, 64, 65, 4097))
+@pytest.mark.parametrize("depth", (1, 64, 65))
+def test_walk_tile_and_depth_boundaries(size, n, depth):
+    """K2p (lane-private layout) handles whole 64-row tiles at depth 1..64, walk_tile_kernel the rest."""
+    rng = np.random.RandomState(n + depth)
+    A = T.N_ACTIONS[size]
+    start = O.scramble(size, rng.randint(A, size=(n, 7)))
+    moves = rng.randint(A, size=(n, depth)).astype(np.uint8)
+    counters = ops.new_counters(dev())
+    out, solved, reward = ops.walk(size, cu(start), cu(moves), counters=counters)
+    want = O.scramble(size, moves, init=start)
+    ws = O.is_solved(size, want)
+    assert (out.cpu().numpy() == want).all() and (solved.cpu().numpy().astype(bool) == ws).all()
+    assert (reward.cpu().numpy() == O.rewards(ws)).all()
+    assert counters.tolist()[:2] == [int(ws.sum()), n]
+
+
+def test_persistent_kernels_on_concurrent_streams_and_in_a_graph():
+    """The tile scheduler's counters come from a ring of slots that every kernel re-arms: launches that
+    overlap on different streams must not see each other, and a captured launch must replay."""
+    rng = np.random.RandomState(9)
+    n, depth = 64 * 600 + 5, 30
+    streams = [torch.cuda.Stream() for _ in range(4)]
+    jobs = []
+    for i, st in enumerate(streams * 3):
+        moves = rng.randint(12, size=(n, depth)).astype(np.uint8)
+        m = cu(moves)
+        torch.cuda.synchronize()
+        with torch.cuda.stream(st):
+            states, solved, _ = ops.scramble(3, m)
+            stepped, s2, _ = ops.step(3, states.clone(), m[:, 0].contiguous())
+        jobs.append((moves, states, stepped))
+    torch.cuda.synchronize()
+    for moves, states, stepped in jobs:
+        want = O.scramble(3, moves)
+        assert (states.cpu().numpy() == want).all()
+        assert (stepped.cpu().numpy() == O.apply_moves(3, want, moves[:, 0])).all()
+    # CUDA graph: capture one scramble, replay it with new moves in the same buffer
+    moves = cu(rng.randint(12, size=(n, depth)).astype(np.uint8))
+    out = torch.empty((n, 54), dtype=torch.uint8, device=dev())
+    so = torch.empty(n, dtype=torch.uint8, device=dev())
+    rw = torch.empty(n, dtype=torch.float32, device=dev())
+    ops.scramble(3, moves, out=out, solved=so, reward=rw)              # warm-up outside the capture
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        ops.scramble(3, moves, out=out, solved=so, reward=rw)
+    for _ in range(3):
+        fresh = rng.randint(12, size=(n, depth)).astype(np.uint8)
+        moves.copy_(torch.from_numpy(fresh))
+        g.replay()
+        torch.cuda.synchronize()
+        assert (out.cpu().numpy() == O.scramble(3, fresh)).all()
+
+
 def test_scramble_empty_and_optional_outputs():
     for size in SIZES:
         s, so, rw = ops.scramble(size, torch.empty((0, 5), dtype=torch.uint8, device=dev()))
