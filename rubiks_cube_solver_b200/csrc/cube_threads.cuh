@@ -432,6 +432,33 @@ CUBE_HD void walk_turn_private(uint8_t* lane_base, const uint32_t* ent, uint32_t
     }
 }
 
+// 2x2x2: the row is six registers and every child is a compile-time byte gather (<= 6 PRMT,
+// gen_tables.py cube_child2), so the turn stays in registers: all six children are formed and the
+// lane's own is kept by predicated selects -- no shared-memory traffic at all, no divergence.
+template <int A>
+CUBE_HD void walk_select_child2(const uint32_t* p, uint32_t m, uint32_t* out)
+{
+    uint32_t c[6];
+    cube_child2<A>(p, c);
+#pragma unroll
+    for (int j = 0; j < 6; ++j) out[j] = (m == (uint32_t)A) ? c[j] : out[j];
+}
+
+CUBE_HD void walk_turn_registers2(uint32_t* w, uint32_t m)            // m >= 6: no move
+{
+    uint32_t out[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) out[j] = w[j];
+    walk_select_child2<0>(w, m, out);
+    walk_select_child2<1>(w, m, out);
+    walk_select_child2<2>(w, m, out);
+    walk_select_child2<3>(w, m, out);
+    walk_select_child2<4>(w, m, out);
+    walk_select_child2<5>(w, m, out);
+#pragma unroll
+    for (int j = 0; j < 6; ++j) w[j] = out[j];
+}
+
 // face uniformity (py333.py:229-233 / py222 isSolved) of an image held in registers: every sticker
 // that does not start a face equals its predecessor.  SHIFT = image byte of sticker 0 (0 or 2).
 template <int SIZE, int SHIFT>

@@ -197,13 +197,17 @@ walk_private_kernel(const uint8_t* in, const uint8_t* __restrict__ moves, int n_
 #pragma unroll
                 for (int j = 0; j < 3; ++j) { const uint2 v = q[j]; w[2 * j] = v.x; w[2 * j + 1] = v.y; }
             }
-#pragma unroll
-            for (int j = 0; j < W; ++j) reinterpret_cast<uint32_t*>(lane_base)[32 * j] = w[j];
-            const uint32_t* ent = s_ent + (shift ? 2 * G::NCYC * CUBE_MOVE_ROWS : 0);
             const uint8_t* mrow = moves_p + row * depth;
-            for (int k = 0; k < depth; ++k) walk_turn_private<SIZE>(lane_base, ent, (uint32_t)mrow[k] & 0xfu);
+            if (SIZE == 3) {
 #pragma unroll
-            for (int j = 0; j < W; ++j) w[j] = reinterpret_cast<const uint32_t*>(lane_base)[32 * j];
+                for (int j = 0; j < W; ++j) reinterpret_cast<uint32_t*>(lane_base)[32 * j] = w[j];
+                const uint32_t* ent = s_ent + (shift ? 2 * G::NCYC * CUBE_MOVE_ROWS : 0);
+                for (int k = 0; k < depth; ++k) walk_turn_private<SIZE>(lane_base, ent, (uint32_t)mrow[k] & 0xfu);
+#pragma unroll
+                for (int j = 0; j < W; ++j) w[j] = reinterpret_cast<const uint32_t*>(lane_base)[32 * j];
+            } else {
+                for (int k = 0; k < depth; ++k) walk_turn_registers2(w, (uint32_t)mrow[k] & 0xfu);
+            }
             const bool ok = (pass && SIZE == 3) ? image_solved<SIZE, kShiftOdd>(w) : image_solved<SIZE, 0>(w);
             mask[pass] = __ballot_sync(0xffffffffu, ok);
             if (SIZE == 3) {

@@ -109,11 +109,15 @@ void walk_private_t(const uint8_t* in, const uint8_t* moves, long long n, int de
                 uint32_t w[W];
                 for (int j = 0; j < W; ++j) w[j] = img_p[j];
                 uint8_t* lane_base = scratch + 4 * lane;
-                for (int j = 0; j < W; ++j) reinterpret_cast<uint32_t*>(lane_base)[32 * j] = w[j];
-                const uint32_t* e = ent.data() + (shift ? 2 * G::NCYC * CUBE_MOVE_ROWS : 0);
-                for (int k = 0; k < depth; ++k)
-                    walk_turn_private<SIZE>(lane_base, e, moves[(base + row) * depth + k] & 0xfu);
-                for (int j = 0; j < W; ++j) w[j] = reinterpret_cast<const uint32_t*>(lane_base)[32 * j];
+                if (SIZE == 3) {
+                    for (int j = 0; j < W; ++j) reinterpret_cast<uint32_t*>(lane_base)[32 * j] = w[j];
+                    const uint32_t* e = ent.data() + (shift ? 2 * G::NCYC * CUBE_MOVE_ROWS : 0);
+                    for (int k = 0; k < depth; ++k)
+                        walk_turn_private<SIZE>(lane_base, e, moves[(base + row) * depth + k] & 0xfu);
+                    for (int j = 0; j < W; ++j) w[j] = reinterpret_cast<const uint32_t*>(lane_base)[32 * j];
+                } else {
+                    for (int k = 0; k < depth; ++k) walk_turn_registers2(w, moves[(base + row) * depth + k] & 0xfu);
+                }
                 const bool ok = shift ? image_solved<SIZE, (SIZE == 3 ? 2 : 0)>(w) : image_solved<SIZE, 0>(w);
                 mask[pass] |= (uint32_t)ok << lane;
                 for (int j = 0; j < W; ++j) img_p[j] = w[j];
