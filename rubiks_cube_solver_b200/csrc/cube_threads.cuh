@@ -179,8 +179,8 @@ CUBE_HD void pair_apply(CubieState& s, const TBL& tbl, uint32_t addr)
 
 // Moves of the tile are a flat byte image (row `row` at byte row*depth, any alignment; readable
 // up to 8 bytes past the last row).  A pair adds at most 2 to a twist field, so 15 pairs
-// (depth <= 30) never need a fold; deeper sequences fold after every 5 words (10 pairs:
-// <= 10 + 20 stays below 32).  DEPTH > 0 fixes the depth at compile time (straight-line code for
+// (depth <= 30) never need a fold; the generic path folds after every complete group of 5 words
+// (10 pairs: <= 10 + 20 stays below 32).  DEPTH > 0 fixes the depth at compile time (straight-line code for
 // the reference's default scramble depth, config.yaml:7 sample_scramble_count = 30, and
 // BASELINE config 2's depth 20); DEPTH == 0 takes it from `depth_rt`.
 // Byte shift of instance k's move stream relative to the word grid when it is the same for every
@@ -255,14 +255,15 @@ CUBE_HD void scramble_pairs_run(CubieState (&st)[NS], const int (&rows)[NS], int
             word(j);
             if (DEPTH > 30 && (j % 5 == 4 || j == DEPTH / 4 - 1)) fold();
         }
-    } else if (depth <= 30) {                            // uniform over the grid
-        for (int j = 0; j < nfull; ++j) word(j);
     } else {
-        for (int j0 = 0; j0 < nfull; j0 += 5) {
-            const int j1 = (j0 + 5 < nfull) ? j0 + 5 : nfull;
-            for (int j = j0; j < j1; ++j) word(j);
+        // groups of five words (ten pairs: a field grows by <= 20), each followed by a fold (<= 31 -> <= 10);
+        // the <= 4 words left over and the tail add <= 16 + 4 on top of <= 10: no further fold needed
+        int j = 0;
+        for (; j + 5 <= nfull; j += 5) {
+            word(j); word(j + 1); word(j + 2); word(j + 3); word(j + 4);
             fold();
         }
+        for (; j < nfull; ++j) word(j);
     }
     if (tail) {                                          // last 1..3 moves, padded with the no-move index
         const uint32_t keep = (1u << (8 * tail)) - 1u;

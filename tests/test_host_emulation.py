@@ -100,12 +100,12 @@ def test_pair_twist_field_never_overflows(size):
         worst = max(worst, f)
     assert worst <= 31                                              # depth <= 30, never folded
     f, worst, after = 0, 0, 0
-    for word in range(1, 400):                                      # deep: fold after every group of <= 5 words
+    for word in range(1, 400):                                      # generic path: fold after every 5th word
         f += 4
         worst = max(worst, f)
         if word % 5 == 0:
             f = after = max(after, max((v & 3) + (v >> 2) for v in range(f + 1)))
-    assert worst <= 31 and after + 4 <= 31                          # the tail word follows a fold
+    assert worst <= 31 and after + 4 * 4 + 4 <= 31                  # <= 4 left-over words and the tail word
 
 
 @pytest.mark.parametrize("size", (2, 3))

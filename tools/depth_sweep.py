@@ -1,0 +1,32 @@
+"""Fused-scramble throughput over depths (generic vs compile-time-depth instantiations of K1p, and the
+single-move fallbacks beyond depth 96):  python tools/depth_sweep.py"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from rubiks_cube_solver_b200 import ops
+
+dev = torch.device("cuda", 0)
+for size, a, n in ((3, 12, 4 << 20), (2, 6, 8 << 20)):
+    s = ops.N_STICKERS[size]
+    for depth in (1, 2, 7, 10, 19, 20, 21, 29, 30, 31, 32, 48, 64, 96, 97, 128, 200):
+        moves = torch.randint(0, a, (n, depth), dtype=torch.uint8, device=dev)
+        st = torch.empty((n, s), dtype=torch.uint8, device=dev)
+        so = torch.empty(n, dtype=torch.uint8, device=dev)
+        rw = torch.empty(n, dtype=torch.float32, device=dev)
+        for _ in range(2):
+            ops.scramble(size, moves, out=st, solved=so, reward=rw)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            ops.scramble(size, moves, out=st, solved=so, reward=rw)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        gbs = n * (depth + s + 5) / ms / 1e6
+        print("size %d depth %3d: %8.4f ms  %.3e tr/s  %6.0f GB/s algorithmic (%.2f of 6553)" % (
+            size, depth, ms, n * depth / ms * 1e3, gbs, gbs / 6553.3), flush=True)
+        del moves
