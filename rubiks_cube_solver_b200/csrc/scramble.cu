@@ -199,11 +199,16 @@ scramble_pairs_kernel(const uint8_t* __restrict__ moves, int n_tiles, int depth_
     const int mstride = L::move_stride(depth);
     const uint32_t move_bytes = (uint32_t)(kPairTile * depth);
 
+    // Programmatic dependent launch: the NEXT kernel of the stream may start as soon as SM resources free
+    // up; its prologue below touches only constant tables and shared memory, and it waits for this grid
+    // to complete (griddepcontrol.wait) before its first global access.
+    asm volatile("griddepcontrol.launch_dependents;");
     pair_table_fill<SIZE>(s_ptbl, tid, blockDim.x);
     if (tid < 32) s_clut[tid] = (SIZE == 3) ? kCornerColour3[tid] : kCornerColour2[tid];
     if (tid >= 64 && tid < 96) s_elut[tid - 64] = (SIZE == 3) ? kEdgeColour3[tid - 64] : 0u;   // canonical flips: 32 entries
     if (lane == 0) { bulk::mbar_init(&s_bar[0], 1); bulk::mbar_init(&s_bar[1], 1); }
     __syncthreads();
+    asm volatile("griddepcontrol.wait;" ::: "memory");                // everything earlier in the stream is complete
 
     // tiles are claimed dynamically (cube_sched.cuh): `tile` is being computed, `next` is in flight
     sched::WarpTiles tiles;
@@ -378,8 +383,20 @@ int launch_one(const uint8_t* moves, long long n, int depth, uint8_t* out, uint8
             if (grid > cube::persistent_ctas()) grid = cube::persistent_ctas();
             sched::Slot* slot = sched::claim_slot();
             if (!slot) return (int)cudaErrorUnknown;
-            kern<<<(unsigned)grid, warps * 32, smem, stream>>>(moves, (int)n_tiles, depth, out, solved, reward, counters, slot, sched::tail_div());
-            const cudaError_t e = cudaGetLastError();
+            cudaLaunchConfig_t cfg_l = {};
+            cfg_l.gridDim = dim3((unsigned)grid);
+            cfg_l.blockDim = dim3((unsigned)(warps * 32));
+            cfg_l.dynamicSmemBytes = (size_t)smem;
+            cfg_l.stream = stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            static const bool pdl = !(getenv("CUBE_PDL") && getenv("CUBE_PDL")[0] == '0');
+            cfg_l.attrs = attr;
+            cfg_l.numAttrs = pdl ? 1 : 0;
+            cudaError_t e = cudaLaunchKernelEx(&cfg_l, kern, moves, (int)n_tiles, depth, out, solved, reward, counters, slot,
+                                               sched::tail_div());
+            if (e == cudaSuccess) e = cudaGetLastError();
             if (e != cudaSuccess) return (int)e;
             done = n_tiles * kPairTile;
         }

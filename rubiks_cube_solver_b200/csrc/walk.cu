@@ -145,6 +145,7 @@ walk_private_kernel(const uint8_t* in, const uint8_t* __restrict__ moves, int n_
     const int mstride = L::move_stride(depth);
     const uint32_t move_bytes = (uint32_t)(kRowsPerTile * depth);
 
+    asm volatile("griddepcontrol.launch_dependents;");                 // programmatic dependent launch, see scramble.cu
     for (int i = tid; i < 2 * G::NCYC * CUBE_MOVE_ROWS; i += blockDim.x) {
         const int shift = (i >= G::NCYC * CUBE_MOVE_ROWS) ? 2 : 0;
         const int cm = i - (shift ? G::NCYC * CUBE_MOVE_ROWS : 0);
@@ -152,6 +153,7 @@ walk_private_kernel(const uint8_t* in, const uint8_t* __restrict__ moves, int n_
     }
     if (lane == 0) { bulk::mbar_init(&s_bar[0], 1); bulk::mbar_init(&s_bar[1], 1); }
     __syncthreads();
+    asm volatile("griddepcontrol.wait;" ::: "memory");                // everything earlier in the stream is complete
 
     // tiles are claimed dynamically (cube_sched.cuh): `tile` is being turned, `next` is in flight
     sched::WarpTiles tiles;
@@ -314,8 +316,20 @@ int launch_tiles(const uint8_t* in, const uint8_t* moves, long long n, int depth
             if (grid > cube::persistent_ctas()) grid = cube::persistent_ctas();
             sched::Slot* slot = sched::claim_slot();
             if (!slot) return (int)cudaErrorUnknown;
-            kern<<<(unsigned)grid, warps * 32, smem, stream>>>(in, moves, (int)n_tiles, depth, out, solved, reward, counters, slot, sched::tail_div());
-            const cudaError_t e = cudaGetLastError();
+            cudaLaunchConfig_t cfg_l = {};
+            cfg_l.gridDim = dim3((unsigned)grid);
+            cfg_l.blockDim = dim3((unsigned)(warps * 32));
+            cfg_l.dynamicSmemBytes = (size_t)smem;
+            cfg_l.stream = stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            static const bool pdl = !(getenv("CUBE_PDL") && getenv("CUBE_PDL")[0] == '0');
+            cfg_l.attrs = attr;
+            cfg_l.numAttrs = pdl ? 1 : 0;
+            cudaError_t e = cudaLaunchKernelEx(&cfg_l, kern, in, moves, (int)n_tiles, depth, out, solved, reward, counters, slot,
+                                               sched::tail_div());
+            if (e == cudaSuccess) e = cudaGetLastError();
             if (e != cudaSuccess) return (int)e;
             done = n_tiles * kRowsPerTile;
         }
