@@ -27,7 +27,8 @@
  *     must be reproduced.
  *   - counters, when non-NULL, is uint64[4] on the device and is only ever
  *     ADDED to: [0] += outputs that are solved, [1] += outputs produced,
- *     [2] += out-of-range actions (cube_validate_actions), [3] reserved.
+ *     [2] += out-of-range actions (cube_validate_actions), [3] += seeded rows that ran
+ *     out of raw draws (cube_moves_from_seeds).
  *     Rewards are +1.0f / -1.0f, so a reward total is 2*[0] - [1] exactly.
  */
 #ifndef CUBE_B200_H
@@ -66,6 +67,17 @@ int cube_sm_count(void);
  * Measured on 2 x B200 with the 32-byte counter all-reduce per step: no gain (99 % weak-scaling
  * efficiency either way), so nothing sets it by default. */
 int cube_set_reserved_sms(int n);
+
+/* Identically seeded scrambles -- the move indices reset(seed, k) draws (cube_env.py:62-65):
+ *   moves_out[i, :] = np.random.RandomState(seeds[i]).randint(A, size=depth)      (bit for bit)
+ * generated on the device (MT19937 seeded by init_genrand, masked rejection sampling like NumPy's
+ * legacy randint).  A shorter reset(seed, k') is the first k' entries of the row.
+ *   seeds      [n]        uint32   in   (the reference's integer seeds, < 2^32)
+ *   moves_out  [n, depth] uint8    out  depth <= 128
+ * counters[3] += rows that would need more than 227 raw draws (practically never: > 7 sigma at depth
+ * 128); such rows are padded with CUBE_NOOP. */
+int cube_moves_from_seeds(int cube_size, const uint32_t* seeds, int64_t n, int depth, uint8_t* moves_out,
+                          uint64_t* counters, void* stream);
 
 /* Fused scramble from the solved cube -- reset()'s loop `init_state(); for a in
  * action_sequence: step(a)` (cube_env.py:61-67) and the per-cube loop of

@@ -10,7 +10,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libcube_b200.so")
 
 SYMBOLS = (
-    "cube_abi_version", "cube_last_error", "cube_sm_count", "cube_set_reserved_sms", "cube_scramble", "cube_step", "cube_walk",
+    "cube_abi_version", "cube_last_error", "cube_sm_count", "cube_set_reserved_sms", "cube_moves_from_seeds", "cube_scramble", "cube_step", "cube_walk",
     "cube_solved", "cube_encode", "cube_expand", "cube_adi_targets", "cube_decode", "cube_validate_actions",
     "cube_pipeline_create", "cube_pipeline_destroy", "cube_pipeline_scramble_host",
 )
@@ -52,6 +52,7 @@ def load():
     lib.cube_last_error.restype = ctypes.c_char_p
     lib.cube_sm_count.restype = ci
     lib.cube_set_reserved_sms.argtypes = [ci]
+    lib.cube_moves_from_seeds.argtypes = [ci, vp, i64, ci, vp, vp, vp]
     lib.cube_scramble.argtypes = [ci, vp, i64, ci, vp, vp, vp, vp, vp]
     lib.cube_step.argtypes = [ci, vp, vp, i64, vp, vp, vp, vp]
     lib.cube_walk.argtypes = [ci, vp, vp, i64, ci, vp, vp, vp, vp, vp]

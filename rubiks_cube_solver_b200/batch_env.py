@@ -38,7 +38,10 @@ class BatchedCubeEnv(object):
         drawn on the device (same distribution as np.random.randint, cube_env.py:65,189)."""
         if moves is None:
             if seeds is not None:
-                moves = torch.from_numpy(self.reference_moves(self.cube_size, seeds, scramble_count))
+                if 0 < scramble_count <= 128:       # drawn on the device, bit-equal to RandomState(seed).randint
+                    moves = ops.moves_from_seeds(self.cube_size, seeds, scramble_count, device=self.device)
+                else:
+                    moves = torch.from_numpy(self.reference_moves(self.cube_size, seeds, scramble_count))
             else:
                 moves = torch.randint(0, self.action_dim, (self.n, scramble_count), dtype=torch.uint8,
                                       device=self.device, generator=generator)

@@ -124,6 +124,16 @@ int cube_solved(int cube_size, const uint8_t* states, int64_t n, uint8_t* solved
                                                  (unsigned long long*)counters, (cudaStream_t)stream));
 }
 
+int cube_moves_from_seeds(int cube_size, const uint32_t* seeds, int64_t n, int depth, uint8_t* moves_out,
+                          uint64_t* counters, void* stream)
+{
+    CUBE_CHECK_SIZE("cube_moves_from_seeds");
+    if (n < 0 || depth < 0 || depth > 128 || (n > 0 && depth > 0 && (!seeds || !moves_out)))
+        return fail(CUBE_ERR_ARG, "cube_moves_from_seeds");
+    CUBE_DONE("cube_moves_from_seeds", cube::launch_seeded_moves(cube_size, seeds, n, depth, moves_out,
+                                                                (unsigned long long*)counters, (cudaStream_t)stream));
+}
+
 int cube_adi_targets(int cube_size, const float* child_values, const uint8_t* child_solved, const float* parent_values,
                      const int32_t* scramble_count, const double* weight, int table_len, int64_t n,
                      float* target_value, int32_t* target_policy, double* error, void* stream)

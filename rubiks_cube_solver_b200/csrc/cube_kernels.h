@@ -34,6 +34,10 @@ int launch_validate(int size, const uint8_t* actions, long long count, unsigned 
 long long launch_leaf2(const uint8_t* states, long long n, uint8_t* children, void* parent_onehot, int dtype,
                        uint8_t* solved, float* reward, unsigned long long* counters, cudaStream_t stream, int* rc);
 
+// moves[i, :] = np.random.RandomState(seeds[i]).randint(A, size=depth) (cube_env.py:62-65); depth <= 128
+int launch_seeded_moves(int size, const uint32_t* seeds, long long n, int depth, uint8_t* moves,
+                        unsigned long long* counters, cudaStream_t stream);
+
 // ADI targets (cube_env.py:239-252) from child values / solved flags; weight[k] = k ** (-temperature)
 int launch_adi_targets(int size, const float* child_values, const uint8_t* child_solved, const float* parent_values,
                        const int* scramble_count, const double* weight, int table_len, long long n,

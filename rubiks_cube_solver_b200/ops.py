@@ -186,6 +186,34 @@ def expand(cube_size, states, dtype=torch.bfloat16, want_children=False, want_ch
                 reward=reward)
 
 
+def moves_from_seeds(cube_size, seeds, depth, device=None):
+    """moves[i] = np.random.RandomState(seeds[i]).randint(A, size=depth) for every seed, drawn on the
+    device (C ABI cube_moves_from_seeds): the scramble of reset(seed, depth), cube_env.py:62-65.
+    seeds: ints in [0, 2**32) (sequence or tensor).  Returns uint8 [N, depth] on the device."""
+    _geom(cube_size)
+    if not isinstance(seeds, torch.Tensor):
+        seeds = torch.tensor([int(s) for s in seeds], dtype=torch.int64)
+    seeds = seeds.to(torch.int64).reshape(-1)
+    if seeds.numel() and (int(seeds.min()) < 0 or int(seeds.max()) >= 2 ** 32):
+        raise ValueError("seeds must be in [0, 2**32): larger seeds take NumPy's init_by_array path")
+    if depth < 0 or depth > 128:
+        raise ValueError("moves_from_seeds supports 0 <= depth <= 128")
+    if device is None:
+        device = seeds.device if seeds.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    dev = torch.device(device)
+    n = seeds.numel()
+    s64 = seeds.to(dev)
+    packed = torch.where(s64 >= 2 ** 31, s64 - 2 ** 32, s64).to(torch.int32).contiguous()      # the same 32 bits
+    moves = torch.empty((n, depth), dtype=torch.uint8, device=dev)
+    counters = new_counters(dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().cube_moves_from_seeds(cube_size, _ptr(packed), n, depth, _ptr(moves), _ptr(counters),
+                                                     _stream(dev)), "cube_moves_from_seeds")
+    if n and depth and int(counters[3]):
+        raise RuntimeError("cube_moves_from_seeds: %d rows ran out of raw draws" % int(counters[3]))
+    return moves
+
+
 def adi_targets(cube_size, child_values, child_solved, parent_values, scramble_count, temperature):
     """ADI targets of cube_env.py:239-252 for a batch (C ABI cube_adi_targets).
 

@@ -32,6 +32,21 @@ def reference_scrambles(cube_size, seeds, depths):
     return out
 
 
+def reference_scrambles_device(cube_size, seeds, depths, device=None):
+    """`reference_scrambles` drawn on the device (C ABI cube_moves_from_seeds): reset(seed, d) uses the
+    first d draws of the seed's stream, so one row per seed at the largest depth is cut to every depth
+    and padded with the no-op index.  uint8 [len(depths) * len(seeds), max(depths)] on the device."""
+    depths = list(depths)
+    dmax = max(depths)
+    if dmax > 128:
+        return torch.from_numpy(reference_scrambles(cube_size, seeds, depths)).to(device)
+    base = ops.moves_from_seeds(cube_size, seeds, dmax, device=device)                  # [S, dmax]
+    d = torch.tensor(depths, device=base.device).view(-1, 1, 1)
+    k = torch.arange(dmax, device=base.device).view(1, 1, -1)
+    rows = torch.where(k < d, base.unsqueeze(0), torch.full_like(base.unsqueeze(0), NOOP))
+    return rows.reshape(len(depths) * base.shape[0], dmax).contiguous()
+
+
 def greedy_actions(policy_logits, pre_action=None):
     """model.get_action for a batch (model.py:47-76): the best action, or the second best when
     the best one is the inverse (a ^ 1) of `pre_action`.  pre_action: int64 [N] with -1 = none."""
@@ -88,7 +103,7 @@ def validation(model, cube_size, sample_scramble_count=30, sample_cube_count=10,
     (seed = 10 * cube index, train.py:180): the list `validation` stores in valid_history."""
     seeds = [i * 10 for i in range(sample_cube_count)]
     depths = list(range(1, sample_scramble_count + 1))
-    moves = reference_scrambles(cube_size, seeds, depths)
+    moves = reference_scrambles_device(cube_size, seeds, depths)
     res = greedy_solve(model, cube_size, moves, max_timesteps=max_timesteps, mask_inverse=mask_inverse,
                        model_device=model_device)
     solved = res["solved"].view(len(depths), len(seeds)).float().mean(dim=1) * 100.0

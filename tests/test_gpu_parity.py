@@ -206,6 +206,35 @@ def test_persistent_kernels_on_concurrent_streams_and_in_a_graph():
         assert (out.cpu().numpy() == O.scramble(3, fresh)).all()
 
 
+@pytest.mark.parametrize("size", SIZES)
+@pytest.mark.parametrize("depth", (1, 10, 30, 100, 128))
+def test_moves_from_seeds_equal_numpy_legacy_randint(size, depth):
+    """K0 (cube_moves_from_seeds): the device's MT19937 + masked rejection against
+    np.random.RandomState(seed).randint(A, size=depth), the draw of reset(seed, k) (cube_env.py:62-65)."""
+    A = T.N_ACTIONS[size]
+    seeds = list(range(0, 1500)) + [10 * i for i in range(200)] + [2 ** 31 - 1, 2 ** 31, 2 ** 32 - 1, 123456789]
+    got = ops.moves_from_seeds(size, seeds, depth).cpu().numpy()
+    for i, sd in enumerate(seeds):
+        assert (got[i] == np.random.RandomState(sd).randint(A, size=depth)).all(), sd
+    with pytest.raises(ValueError):
+        ops.moves_from_seeds(size, [2 ** 32], depth)
+
+
+def test_batched_reset_from_seeds_matches_config1_golden():
+    """BatchedCubeEnv.reset(seeds=...) draws its moves on the device: config 1 end to end on the GPU."""
+    from rubiks_cube_solver_b200 import rollout
+    for size in SIZES:
+        g = golden("config1_%d.npz" % size)
+        env = R.BatchedCubeEnv(1024, cube_size=size, obs_dtype=torch.float32)
+        obs, reward, done = env.reset(seeds=range(1024), scramble_count=10)
+        assert (env.sim_cube.cpu().numpy() == g["stickers"]).all()
+        assert (obs.cpu().numpy() == g["onehot"]).all()
+        assert (done.cpu().numpy().astype(bool) == g["done"]).all()
+        host = rollout.reference_scrambles(size, [0, 10, 20], [1, 5, 30])
+        devm = rollout.reference_scrambles_device(size, [0, 10, 20], [1, 5, 30]).cpu().numpy()
+        assert (host == devm).all()
+
+
 def test_scramble_empty_and_optional_outputs():
     for size in SIZES:
         s, so, rw = ops.scramble(size, torch.empty((0, 5), dtype=torch.uint8, device=dev()))
