@@ -43,6 +43,10 @@ int launch_adi_targets(int size, const float* child_values, const uint8_t* child
                        const int* scramble_count, const double* weight, int table_len, long long n,
                        float* target_value, int* target_policy, double* error, cudaStream_t stream);
 
+long long launch_leaf2_children(const uint8_t* states, long long n, uint8_t* children, void* child_onehot,
+                                void* parent_onehot, int dtype, uint8_t* solved, float* reward,
+                                unsigned long long* counters, cudaStream_t stream, int* rc);
+
 int launch_decode2(const void* onehot, int dtype, long long n, uint8_t* out, cudaStream_t stream);
 
 int sm_count();

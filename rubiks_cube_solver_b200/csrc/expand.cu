@@ -282,6 +282,22 @@ int launch_expand(int size, const uint8_t* states, long long n, uint8_t* childre
                   unsigned long long* counters, cudaStream_t stream)
 {
     if (n == 0) return 0;
+    if (size == 2 && child_onehot && dtype != 1) {
+        // 2x2x2 ADI shape: image kernel K3c for whole 32-parent tiles, generic kernel for the remainder
+        int rc = 0;
+        const long long done = launch_leaf2_children(states, n, children, child_onehot, parent_onehot, dtype, solved,
+                                                     reward, counters, stream, &rc);
+        if (rc) return rc;
+        if (done == n) return 0;
+        const int es = dtype == 0 ? 2 : 1;
+        states += done * 24;
+        n -= done;
+        if (children) children += done * 144;
+        child_onehot = static_cast<uint8_t*>(child_onehot) + done * 6 * 147 * es;
+        if (parent_onehot) parent_onehot = static_cast<uint8_t*>(parent_onehot) + done * 147 * es;
+        if (solved) solved += done * 6;
+        if (reward) reward += done * 6;
+    }
     if (size == 2 && !child_onehot && (children || parent_onehot)) {
         // the MCTS leaf shape (BASELINE config 5): register-resident kernel for whole tiles,
         // the generic kernel below for the ragged remainder
