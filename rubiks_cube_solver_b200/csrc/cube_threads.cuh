@@ -68,10 +68,11 @@ CUBE_HD bool scramble_finish(CubieState& st, int tid, const uint32_t* s_clut, co
 
 
 // ---- K1p: fused scramble, two moves per table row --------------------------------------------
-// The pair table lives in shared memory as [row][vec][lane slot] 16-byte vectors, 256 bytes per
-// row: 3x3x3 rows are two vectors (P, Q) x 8 lane slots, 2x2x2 rows one vector x 16 lane slots.
-// A lane only ever reads its own slot, so the 128-bit loads of a quarter warp touch eight
-// different 16-byte bank groups whatever rows the lanes ask for: no bank conflicts by construction.
+// The pair table lives in shared memory with 256 bytes per row, every vector replicated once per
+// lane slot: 3x3x3 rows are two 16-byte vectors (P, Q) x 8 slots; 2x2x2 rows are (selectors, T0) as
+// 8 bytes x 16 slots plus T1 as 4 bytes x 32 slots.  A lane only ever reads its own slot, so the
+// 128- / 64- / 32-bit loads of a quarter / half / whole warp touch disjoint banks whatever rows the
+// lanes ask for: no bank conflicts by construction.
 // `lanereg` = the lane's slot offset in byte 0 (bytes 1..3 zero); a row address is then ONE byte
 // permute: byte 1 <- the pair index, byte 0 <- the slot offset.
 struct CubeVec4 { uint32_t x, y, z, w; };
@@ -97,6 +98,12 @@ struct PairTableHost {
     const uint8_t* base;
     CUBE_HD uint32_t bias() const { return 0u; }
     CUBE_HD CubeVec4 ld(uint32_t addr, int off) const { return cube_ld128(base + addr + off); }
+    CUBE_HD void ld64(uint32_t addr, uint32_t& x, uint32_t& y) const
+    {
+        const uint32_t* q = reinterpret_cast<const uint32_t*>(base + addr);
+        x = q[0]; y = q[1];
+    }
+    CUBE_HD uint32_t ld32(uint32_t addr) const { return *reinterpret_cast<const uint32_t*>(base + addr); }
 };
 #if defined(__CUDACC__)
 struct PairTableShared {
@@ -109,6 +116,16 @@ struct PairTableShared {
             asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
         else
             asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+128];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+        return v;
+    }
+    __device__ __forceinline__ void ld64(uint32_t addr, uint32_t& x, uint32_t& y) const
+    {
+        asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(x), "=r"(y) : "r"(addr));
+    }
+    __device__ __forceinline__ uint32_t ld32(uint32_t addr) const
+    {
+        uint32_t v;
+        asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
         return v;
     }
 };
@@ -141,31 +158,43 @@ struct ColourLutShared {
 template <int SIZE>
 CUBE_HD uint32_t pair_lanereg(int lane)
 {
-    return (uint32_t)(lane & (SIZE == 3 ? 7 : 15)) << 4;
+    return SIZE == 3 ? (uint32_t)(lane & 7) << 4 : (uint32_t)(lane & 15) << 3;
+}
+
+// 2x2x2: the lane's T1 slot (32 x 4 bytes, bytes 128..255 of the row) relative to its (selectors, T0) slot
+CUBE_HD uint32_t pair_roff2(int lane)
+{
+    return 128u + (uint32_t)lane * 4u - ((uint32_t)(lane & 15) << 3);
 }
 
 // fill the shared-memory image from kPairWords{3,2}; thread `t` of `nthreads`
 template <int SIZE>
 CUBE_HD void pair_table_fill(uint8_t* s_ptbl, int t, int nthreads)
 {
-    const uint32_t* src = (SIZE == 3) ? kPairWords3 : kPairWords2;
     for (int i = t; i < CUBE_PAIR_ROWS * 16; i += nthreads) {
         const int row = i >> 4, slot = i & 15;
-        const uint32_t* v = src + ((SIZE == 3) ? (row * 2 + (slot >> 3)) * 4 : row * 4);
-        uint32_t* d = reinterpret_cast<uint32_t*>(s_ptbl) + i * 4;
-        d[0] = v[0]; d[1] = v[1]; d[2] = v[2]; d[3] = v[3];
+        if (SIZE == 3) {
+            const uint32_t* v = kPairWords3 + (row * 2 + (slot >> 3)) * 4;
+            uint32_t* d = reinterpret_cast<uint32_t*>(s_ptbl) + i * 4;
+            d[0] = v[0]; d[1] = v[1]; d[2] = v[2]; d[3] = v[3];
+        } else {
+            const uint32_t* v = kPairWords2 + row * 4;
+            uint32_t* d = reinterpret_cast<uint32_t*>(s_ptbl + row * 256);
+            d[2 * slot] = v[0]; d[2 * slot + 1] = v[1];
+            d[32 + 2 * slot] = v[2]; d[32 + 2 * slot + 1] = v[2];
+        }
     }
 }
 
 // two face turns: one row of the pair table (gen_tables.py pair_words_3 / pair_words_2)
 template <int SIZE, class TBL>
-CUBE_HD void pair_apply(CubieState& s, const TBL& tbl, uint32_t addr)
+CUBE_HD void pair_apply(CubieState& s, const TBL& tbl, uint32_t addr, uint32_t roff)
 {
-    const CubeVec4 P = tbl.ld(addr, 0);
-    const uint32_t n0 = cube_prmt(s.c0, s.c1, P.x) + P.y;
-    const uint32_t n1 = cube_prmt(s.c0, s.c1, cube_hi16(P.x)) + P.z;
-    s.c0 = n0; s.c1 = n1;
     if (SIZE == 3) {
+        const CubeVec4 P = tbl.ld(addr, 0);
+        const uint32_t n0 = cube_prmt(s.c0, s.c1, P.x) + P.y;
+        const uint32_t n1 = cube_prmt(s.c0, s.c1, cube_hi16(P.x)) + P.z;
+        s.c0 = n0; s.c1 = n1;
         const CubeVec4 Q = tbl.ld(addr, 128);
         const uint32_t t0 = cube_prmt(s.e1, s.e2, Q.x);
         const uint32_t t1 = cube_prmt(s.e0, s.e2, Q.y);
@@ -174,6 +203,13 @@ CUBE_HD void pair_apply(CubieState& s, const TBL& tbl, uint32_t addr)
         const uint32_t m1 = cube_prmt(s.e1, t1, cube_hi16(Q.y)) ^ Q.w;
         const uint32_t m2 = cube_prmt(s.e2, t2, cube_hi16(Q.z)) ^ (P.w & 0x20202020u);
         s.e0 = m0; s.e1 = m1; s.e2 = m2;
+    } else {
+        uint32_t sel, t0w;
+        tbl.ld64(addr, sel, t0w);
+        const uint32_t t1w = tbl.ld32(addr + roff);
+        const uint32_t n0 = cube_prmt(s.c0, s.c1, sel) + t0w;
+        const uint32_t n1 = cube_prmt(s.c0, s.c1, cube_hi16(sel)) + t1w;
+        s.c0 = n0; s.c1 = n1;
     }
 }
 
@@ -208,7 +244,7 @@ CUBE_HD uint32_t pair_rows_word(uint32_t lo, uint32_t hi, uint32_t sh, uint32_t 
 
 template <int SIZE, int DEPTH, int NS, class TBL>
 CUBE_HD void scramble_pairs_run(CubieState (&st)[NS], const int (&rows)[NS], int depth_rt, const uint8_t* s_moves,
-                                const TBL& tbl, uint32_t lanereg)
+                                const TBL& tbl, uint32_t lanereg, uint32_t roff)
 {
     // NS instances per lane advance in lockstep (independent dependency chains for the scheduler)
     const int depth = DEPTH > 0 ? DEPTH : depth_rt;
@@ -238,9 +274,9 @@ CUBE_HD void scramble_pairs_run(CubieState (&st)[NS], const int (&rows)[NS], int
             lo[NS - 1] = (s1 == 0) ? mw[wi[NS - 1] + j + 1] : hi;
         }
 #pragma unroll
-        for (int k = 0; k < NS; ++k) pair_apply<SIZE>(st[k], tbl, cube_prmt(y[k], lanereg, 0x5514u));
+        for (int k = 0; k < NS; ++k) pair_apply<SIZE>(st[k], tbl, cube_prmt(y[k], lanereg, 0x5514u), roff);
 #pragma unroll
-        for (int k = 0; k < NS; ++k) pair_apply<SIZE>(st[k], tbl, cube_prmt(y[k], lanereg, 0x5534u));
+        for (int k = 0; k < NS; ++k) pair_apply<SIZE>(st[k], tbl, cube_prmt(y[k], lanereg, 0x5534u), roff);
     };
     auto fold = [&]() {
 #pragma unroll
@@ -274,10 +310,10 @@ CUBE_HD void scramble_pairs_run(CubieState (&st)[NS], const int (&rows)[NS], int
             y[k] = w * (uint32_t)(CUBE_PAIR_BASE + 256) + bias;
         }
 #pragma unroll
-        for (int k = 0; k < NS; ++k) pair_apply<SIZE>(st[k], tbl, cube_prmt(y[k], lanereg, 0x5514u));
+        for (int k = 0; k < NS; ++k) pair_apply<SIZE>(st[k], tbl, cube_prmt(y[k], lanereg, 0x5514u), roff);
         if (tail == 3) {
 #pragma unroll
-            for (int k = 0; k < NS; ++k) pair_apply<SIZE>(st[k], tbl, cube_prmt(y[k], lanereg, 0x5534u));
+            for (int k = 0; k < NS; ++k) pair_apply<SIZE>(st[k], tbl, cube_prmt(y[k], lanereg, 0x5534u), roff);
         }
     }
 }

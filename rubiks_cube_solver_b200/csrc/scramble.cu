@@ -219,7 +219,7 @@ scramble_pairs_kernel(const uint8_t* __restrict__ moves, int n_tiles, int depth_
         bulk::load(s_moves, moves + (long long)tile * move_bytes, move_bytes, &s_bar[0]);
     }
     const int rows[2] = {(SIZE == 3) ? 2 * lane : lane, (SIZE == 3) ? 2 * lane + 1 : lane + 32};
-    const uint32_t lanereg = pair_lanereg<SIZE>(lane);
+    const uint32_t lanereg = pair_lanereg<SIZE>(lane), roff = pair_roff2(lane);
     const ColourLutShared lut{bulk::smem_addr(s_clut), bulk::smem_addr(s_elut)};
     unsigned n_solved = 0;
 
@@ -235,7 +235,7 @@ scramble_pairs_kernel(const uint8_t* __restrict__ moves, int n_tiles, int depth_
         CubieState st[2];
         cubie_init(st[0]);
         cubie_init(st[1]);
-        scramble_pairs_run<SIZE, DEPTH, 2>(st, rows, depth, s_moves + buf * mstride, tbl, lanereg);
+        scramble_pairs_run<SIZE, DEPTH, 2>(st, rows, depth, s_moves + buf * mstride, tbl, lanereg, roff);
         if (lane == 0) bulk::wait_read_all();                         // the previous store has released the out tile
         __syncwarp();
         const bool ok0 = scramble_pairs_finish<SIZE>(st[0], rows[0], lut, s_out);

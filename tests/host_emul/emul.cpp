@@ -54,10 +54,10 @@ void scramble_pairs_t(const uint8_t* moves, long long n, int depth, uint8_t* out
             cubie_init(st[1]);
             const uint32_t lr = pair_lanereg<SIZE>(lane);
             const PairTableHost s_ptbl{s_ptbl_mem};
-            if (fixed && depth == 30) scramble_pairs_run<SIZE, 30, 2>(st, rows, depth, s_moves.data(), s_ptbl, lr);
-            else if (fixed && depth == 20) scramble_pairs_run<SIZE, 20, 2>(st, rows, depth, s_moves.data(), s_ptbl, lr);
-            else if (fixed && depth == 43) scramble_pairs_run<SIZE, 43, 2>(st, rows, depth, s_moves.data(), s_ptbl, lr);
-            else scramble_pairs_run<SIZE, 0, 2>(st, rows, depth, s_moves.data(), s_ptbl, lr);
+            if (fixed && depth == 30) scramble_pairs_run<SIZE, 30, 2>(st, rows, depth, s_moves.data(), s_ptbl, lr, pair_roff2(lane));
+            else if (fixed && depth == 20) scramble_pairs_run<SIZE, 20, 2>(st, rows, depth, s_moves.data(), s_ptbl, lr, pair_roff2(lane));
+            else if (fixed && depth == 43) scramble_pairs_run<SIZE, 43, 2>(st, rows, depth, s_moves.data(), s_ptbl, lr, pair_roff2(lane));
+            else scramble_pairs_run<SIZE, 0, 2>(st, rows, depth, s_moves.data(), s_ptbl, lr, pair_roff2(lane));
             for (int k = 0; k < 2; ++k)
                 ok[k] |= (uint32_t)scramble_pairs_finish<SIZE>(st[k], rows[k], ColourLutHost{clut, kEdgeColour3}, s_out.data()) << lane;
         }
