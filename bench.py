@@ -255,6 +255,15 @@ def measure_other_configs(torch, ops, adi, dev, peak_gbs):
           n_par * (54 + 12 * (960 + 1 + 4)) + 30 * cubes * (2 * 54 + 6))
     del child, adi_moves
 
+    # 2x2x2 ADI shape: 6 children + their bf16 one-hot rows per parent (kernel K3c)
+    n = 4 * 2 ** 20
+    parents2, _, _ = ops.scramble(2, torch.randint(0, 6, (n, 14), dtype=torch.uint8, device=dev, generator=gen),
+                                  want_flags=False)
+    child2 = torch.empty((n, 6, 7, 21), dtype=torch.bfloat16, device=dev)
+    t = time_launches(torch, lambda: ops.expand(2, parents2, dtype=torch.bfloat16, child_onehot=child2), 5, warmup=2)
+    entry("adi_2x2_expand_4Mi_parents", t, n, "parents/s", n * (24 + 6 * (294 + 1 + 4)))
+    del parents2, child2
+
     # sim_state_to_state for a resident batch (cube_encode), 3x3x3 bf16
     n = 4 * 2 ** 20
     st, _, _ = ops.scramble(3, torch.randint(0, 12, (n, 15), dtype=torch.uint8, device=dev, generator=gen),
