@@ -287,7 +287,7 @@ def measure_other_configs(torch, ops, adi, dev, peak_gbs):
 
 def measure_mcts(torch, dev):
     """test.py's MCTS branch (test.py:139-147: up to numMCTSSim = 50 simulations per cube, config.yaml:29)
-    for 4096 2x2x2 cubes in lock-step through BatchedMCTS (device tree store + one leaf batch per
+    for 65 536 2x2x2 cubes in lock-step through BatchedMCTS (device tree store, one traversal kernel, one leaf batch and one update kernel per
     simulation), beside the reference-semantics per-cube search (oracle/mcts_ref.py) on one host core.
     Net: DeepCube's 2x2x2 layer shapes (147-512-128-{64-6, 64-1}, pretrained/222model.pt), random init."""
     import random
@@ -318,11 +318,11 @@ def measure_mcts(torch, dev):
     net = Net()
     gpu_net = Net().to(dev)
     gpu_net.load_state_dict(net.state_dict())
-    n_trees, num_sim, depth = 4096, 50, 8
+    n_trees, num_sim, depth = 65536, 50, 8
     gen = torch.Generator(device=dev).manual_seed(77)
     roots, _, _ = ops.scramble(2, torch.randint(0, 6, (n_trees, depth), dtype=torch.uint8, device=dev, generator=gen),
                                want_flags=False)
-    table = torch.randint(0, 6, (n_trees, num_sim + 1), generator=torch.Generator().manual_seed(3))
+    table = torch.randint(0, 6, (n_trees, 8 * (num_sim + 1)), generator=torch.Generator().manual_seed(3), dtype=torch.uint8)
     search = mcts_batch.BatchedMCTS(gpu_net, 2, num_sim=num_sim)
     search.run(roots[:256], rand_table=table[:256])            # warm-up
     torch.cuda.synchronize()
@@ -344,7 +344,7 @@ def measure_mcts(torch, dev):
     return {"simulations_per_s_batched_gpu": sims / dt, "simulations_per_s_reference_semantics_1_core": cpu_sims / cpu_dt,
             "trees": n_trees, "solved": int(res["solved"].sum()), "ms": dt * 1e3,
             "note": "one simulation = traverse + leaf expansion (6 children, net value/policy) + back-propagation "
-                    "(mcts.py:36-130); 4096 cubes scrambled 8 deep, 50 simulations each"}
+                    "(mcts.py:36-130); 65 536 cubes scrambled 8 deep, 50 simulations each"}
 
 
 def measure_drop_in_adi(torch, dev):

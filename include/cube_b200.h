@@ -138,6 +138,50 @@ int cube_adi_targets(int cube_size, const float* child_values, const uint8_t* ch
                      int table_len, int64_t n, float* target_value, int32_t* target_policy, double* error,
                      void* stream);
 
+/* ---- batched MCTS tree store (mcts.py:17-154) --------------------------------------------------
+ * B independent trees, one per cube, each a slab of n_slots node slots (one simulation adds at most
+ * one node: n_slots = numMCTSSim + 1 <= 255).  A node is children_and_data[key] of the reference
+ * (mcts.py:103-110): key = the observation, here the one-hot rows' column indices (KEY = 20 bytes for
+ * 3x3x3, 8 for 2x2x2: 7 indices + one zero byte), children keys, P, W, N, L and done flags.  All
+ * members are DEVICE pointers owned by the caller; A = 12 / 6, S = 54 / 24. */
+typedef struct cube_mcts_tree {
+    int32_t n_trees, n_slots, path_cap, rand_cap; /* B, M, capacity of one traversal path, draws per tree */
+    uint8_t* node_key;                    /* [B, M, KEY]     key of every expanded node                  */
+    uint8_t* child_key;                   /* [B, M, A, KEY]  keys of its children (mcts.py:96-101)       */
+    uint8_t* child_done;                  /* [B, M, A]       is_solved of its children                   */
+    float* P;                             /* [B, M, A]       policy (mcts.py:92)                         */
+    float* W;                             /* [B, M, A]       max-backed-up value, starts at value_min    */
+    int32_t* N;                           /* [B, M, A]       visit counts                                */
+    int32_t* L;                           /* [B, M, A]       virtual loss                                */
+    int32_t* n_nodes;                     /* [B]             expanded nodes so far                       */
+    uint8_t* active;                      /* [B]             0 once the tree has returned a solution     */
+    const uint8_t* root_state;            /* [B, S]          sticker rows of the roots                   */
+    const uint8_t* root_key;              /* [B, KEY]                                                    */
+    const uint8_t* rand_table;            /* [B, rand_cap]   pre-drawn random actions (mcts.py:69-70; a node
+                                           *                  revisited inside one traversal draws again) */
+    int32_t* rand_ptr;                    /* [B]             draws used so far                           */
+    uint8_t* path_node;                   /* [B, path_cap]   out: node slots of the last traversal       */
+    uint8_t* path_action;                 /* [B, path_cap]   out: actions of the last traversal          */
+    int32_t* path_len;                    /* [B]             out                                         */
+    uint8_t* leaf_state;                  /* [B, S]          out: sticker row of the leaf that was reached */
+    int32_t* flags;                       /* [1]  |= 1 path_cap exceeded, 2 rand_table exhausted, 4 n_slots exceeded */
+} cube_mcts_tree_t;
+
+/* MCTS.traverse (mcts.py:52-81) for every active tree: from the root to the first key that is not in
+ * the tree; fills path_*, leaf_state; adds virtual_loss to L along the way. */
+int cube_mcts_traverse(int cube_size, const cube_mcts_tree_t* tree, float cpuct, int virtual_loss, void* stream);
+
+/* The rest of MCTS.train for every active tree (mcts.py:38-50): store the expanded leaf
+ * (leaf_key [B, KEY], child_key_new [B, A, KEY], child_done_new [B, A] from cube_expand; value [B],
+ * policy [B, A] from the network; W = value_min, N = L = 0), back-propagate along the path
+ * (W = max(W, value), L -= 150, N += 1: mcts.py:122-129) and, if a child of the new leaf is solved,
+ * write path actions + that child to actions_out [B, path_cap + 1] (int8), n_actions [B],
+ * n_sims [B] = sim_index + 1 and clear `active`. */
+int cube_mcts_update(int cube_size, const cube_mcts_tree_t* tree, const uint8_t* leaf_key,
+                     const uint8_t* child_key_new, const uint8_t* child_done_new, const float* value,
+                     const float* policy, float value_min, int sim_index, int8_t* actions_out,
+                     int32_t* n_actions, int32_t* n_sims, void* stream);
+
 /* state_to_sim_state (cube_env.py:154-175 + py222 getStickers): one-hot [n, 7, 21] of
  * `dtype` -> sticker rows [n, 24].  2x2x2 only: for cube_size 3 the reference raises
  * NotImplementedError (cube_env.py:171-172) and this returns CUBE_ERR_SIZE. */

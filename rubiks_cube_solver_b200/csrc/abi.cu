@@ -134,6 +134,28 @@ int cube_moves_from_seeds(int cube_size, const uint32_t* seeds, int64_t n, int d
                                                                 (unsigned long long*)counters, (cudaStream_t)stream));
 }
 
+int cube_mcts_traverse(int cube_size, const cube_mcts_tree_t* tree, float cpuct, int virtual_loss, void* stream)
+{
+    CUBE_CHECK_SIZE("cube_mcts_traverse");
+    if (!tree || tree->n_trees < 0 || tree->n_slots < 1 || tree->n_slots > 255 || tree->path_cap < 1 || tree->rand_cap < 1)
+        return fail(CUBE_ERR_ARG, "cube_mcts_traverse");
+    CUBE_DONE("cube_mcts_traverse", cube::launch_mcts_traverse(cube_size, *tree, cpuct, virtual_loss, (cudaStream_t)stream));
+}
+
+int cube_mcts_update(int cube_size, const cube_mcts_tree_t* tree, const uint8_t* leaf_key, const uint8_t* child_key_new,
+                     const uint8_t* child_done_new, const float* value, const float* policy, float value_min,
+                     int sim_index, int8_t* actions_out, int32_t* n_actions, int32_t* n_sims, void* stream)
+{
+    CUBE_CHECK_SIZE("cube_mcts_update");
+    if (!tree || tree->n_trees < 0 || tree->n_slots < 1 || tree->n_slots > 255 ||
+        (tree->n_trees > 0 && (!leaf_key || !child_key_new || !child_done_new || !value || !policy || !actions_out ||
+                               !n_actions || !n_sims)))
+        return fail(CUBE_ERR_ARG, "cube_mcts_update");
+    CUBE_DONE("cube_mcts_update", cube::launch_mcts_update(cube_size, *tree, leaf_key, child_key_new, child_done_new, value,
+                                                           policy, value_min, sim_index, actions_out, n_actions, n_sims,
+                                                           (cudaStream_t)stream));
+}
+
 int cube_adi_targets(int cube_size, const float* child_values, const uint8_t* child_solved, const float* parent_values,
                      const int32_t* scramble_count, const double* weight, int table_len, int64_t n,
                      float* target_value, int32_t* target_policy, double* error, void* stream)

@@ -4,6 +4,7 @@
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
+#include "../../include/cube_b200.h"
 
 // counters layout (uint64[4], device): [0] += solved outputs, [1] += outputs written,
 // [2] += out-of-range actions seen by cube_validate_actions, [3] reserved
@@ -46,6 +47,13 @@ int launch_adi_targets(int size, const float* child_values, const uint8_t* child
 long long launch_leaf2_children(const uint8_t* states, long long n, uint8_t* children, void* child_onehot,
                                 void* parent_onehot, int dtype, uint8_t* solved, float* reward,
                                 unsigned long long* counters, cudaStream_t stream, int* rc);
+
+// batched MCTS (mcts.py:17-154): traverse all trees to their leaves / insert the expanded leaves,
+// back-propagate and test for solved children
+int launch_mcts_traverse(int size, const cube_mcts_tree_t& t, float cpuct, int virtual_loss, cudaStream_t stream);
+int launch_mcts_update(int size, const cube_mcts_tree_t& t, const uint8_t* leaf_key, const uint8_t* child_key_new,
+                       const uint8_t* child_done_new, const float* value, const float* policy, float value_min,
+                       int sim_index, int8_t* actions_out, int* n_actions, int* n_sims, cudaStream_t stream);
 
 int launch_decode2(const void* onehot, int dtype, long long n, uint8_t* out, cudaStream_t stream);
 
