@@ -455,7 +455,8 @@ def run_b200_arm(args):
         totals = drain()                                  # inside the timed region
         e1.record()
         barrier()
-    step_s = cdist.max_over_ranks(e0.elapsed_time(e1) * 1e-3 / args.steps, dev)
+    local_step_s = e0.elapsed_time(e1) * 1e-3 / args.steps
+    step_s = cdist.max_over_ranks(local_step_s, dev)
     total_tr = world * n * depth
     value = total_tr / step_s
     solved_total, produced_total = int(totals[0]), int(totals[1])
@@ -467,7 +468,11 @@ def run_b200_arm(args):
         peak_gbs, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
     else:
         peak_gbs, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
-    kern_s = time_launches(torch, lambda: ops.scramble(size, moves, out=states, solved=solved, reward=reward), 20)
+    # Every timed step is exactly one launch of the dominant kernel on the current stream, so its
+    # average duration IS this rank's share of the timed region (CUDA events e0 .. e1 above); a short
+    # isolated run (20 launches, nothing else on the device) is reported next to it.
+    kern_s = local_step_s
+    isolated_s = time_launches(torch, lambda: ops.scramble(size, moves, out=states, solved=solved, reward=reward), 20)
     alg_bytes = n * (depth + S + 1 + 4)
     traffic = None
     prof = os.path.join(ROOT, "profiles", "scramble3_dram_bytes_per_launch.json")
@@ -479,9 +484,11 @@ def run_b200_arm(args):
     roofline = {"bound": "hbm", "kernel": "scramble_pairs_kernel<3,30>", "achieved": alg_bytes / kern_s / 1e9,
                 "peak": peak_gbs, "unit": "GB/s", "frac": alg_bytes / kern_s / 1e9 / peak_gbs, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
-                "kernel_ms": kern_s * 1e3, "transitions_per_s_kernel_only": n * depth / kern_s,
-                "note": "K1p is bound by the shared-memory data pipe (pair-table rows, 88 % of peak) and the ALU pipe (PRMT), not by HBM (SURVEY.md 8d, "
-                        "DESIGN.md): the HBM fraction is reported as the contract asks; see profiles/"}
+                "kernel_ms": kern_s * 1e3, "kernel_ms_isolated": isolated_s * 1e3,
+                "transitions_per_s_kernel_only": n * depth / kern_s,
+                "note": "K1p is bound by the shared-memory data pipe (pair-table rows, 87 % of peak) and the ALU pipe "
+                        "(PRMT), not by HBM (SURVEY.md 8d, DESIGN.md): the HBM fraction is reported as the contract "
+                        "asks; see profiles/"}
 
     # end to end through the host-buffer C-ABI pipeline (pinned host memory, copies inside the timed region)
     pipe = ops.HostScramblePipeline(size, depth, chunk_instances=args.e2e_chunk, n_stages=3, device=dev)
