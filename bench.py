@@ -137,12 +137,14 @@ def run_reference_arm(args):
 
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler(object):
-    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+    """Samples SM clock and throttle reasons through NVML while the timed region runs.  The thread is
+    started BEFORE the warm-up and only records while `recording` is set, so neither its start-up nor
+    an NVML query lands on the (still empty) launch queue at the start of the timed region."""
     REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
                0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
                0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
 
-    def __init__(self, index, period=0.004):
+    def __init__(self, index, period=0.003):
         self.samples, self.reasons, self.period, self._stop = [], set(), period, threading.Event()
         self.max_mhz, self._h, self._nv = None, None, None
         try:
@@ -154,19 +156,28 @@ class ClockSampler(object):
         except Exception:                                   # noqa: BLE001 - NVML optional
             self._h = None
         self._t = threading.Thread(target=self._run, daemon=True)
+        self.recording = False
+
+    def sample_now(self):
+        nv = self._nv
+        if self._h is None:
+            return
+        try:
+            self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+            bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+            for b, name in self.REASONS.items():
+                if bits & b and name != "gpu_idle":
+                    self.reasons.add(name)
+        except Exception:                                   # noqa: BLE001
+            pass
 
     def _run(self):
-        nv = self._nv
-        while not self._stop.is_set():
-            try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
-                bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
-                for b, name in self.REASONS.items():
-                    if bits & b and name != "gpu_idle":
-                        self.reasons.add(name)
-            except Exception:                               # noqa: BLE001
-                pass
-            self._stop.wait(self.period)
+        # The first periodic sample comes one period in: an NVML query right at the start of the timed
+        # region stalls the (still empty) launch queue for ~0.1 ms.  bench.py takes one more sample by
+        # hand after the last launch, while the GPU is still working through the queued steps.
+        while not self._stop.wait(self.period):
+            if self.recording:
+                self.sample_now()
 
     def __enter__(self):
         if self._h is not None:
@@ -442,19 +453,24 @@ def run_b200_arm(args):
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
+    clocks = ClockSampler(local)
+    clocks.__enter__()                                    # thread up and idle before anything is timed
     for _ in range(max(3, args.warmup)):
         step()
     drain()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clocks:
-        barrier()
-        e0.record()
-        for _ in range(args.steps):
-            step()
-        totals = drain()                                  # inside the timed region
-        e1.record()
-        barrier()
+    barrier()
+    clocks.recording = True
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    totals = drain()                                      # inside the timed region
+    e1.record()
+    clocks.sample_now()                                   # the queued steps are still running
+    barrier()                                             # ... and keep sampling until they are done
+    clocks.recording = False
+    clocks.__exit__(None, None, None)
     local_step_s = e0.elapsed_time(e1) * 1e-3 / args.steps
     step_s = cdist.max_over_ranks(local_step_s, dev)
     total_tr = world * n * depth
