@@ -155,6 +155,8 @@ class ClockSampler(object):
             self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
         except Exception:                                   # noqa: BLE001 - NVML optional
             self._h = None
+        if os.environ.get("CUBE_BENCH_NO_NVML") == "1":      # A/B switch: does sampling perturb the timing?
+            self._h = None
         self._t = threading.Thread(target=self._run, daemon=True)
         self.recording = False
 
