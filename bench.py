@@ -243,6 +243,23 @@ def measure_other_configs(torch, ops, adi, dev, peak_gbs):
         entry("step_%dx%d_resident_%dMi" % (size, size, n >> 20), t, n, "transitions/s", n * (2 * s_ + 6))
         del states, act, so, rw
 
+    # configs[2] read literally as "scramble, then one step": K1p (8 Mi x depth 30) followed by K2p on the
+    # states it produced, 31 transitions per instance, both launches inside the timed region
+    n, d = 8 * 2 ** 20, 30
+    moves = torch.randint(0, 12, (n, d), dtype=torch.uint8, device=dev, generator=gen)
+    act = torch.randint(0, 12, (n,), dtype=torch.uint8, device=dev, generator=gen)
+    st = torch.empty((n, 54), dtype=torch.uint8, device=dev)
+    so = torch.empty(n, dtype=torch.uint8, device=dev)
+    rw = torch.empty(n, dtype=torch.float32, device=dev)
+
+    def scramble_then_step():
+        ops.scramble(3, moves, out=st, solved=so, reward=rw)
+        ops.step(3, st, act, solved=so, reward=rw)
+
+    t = time_launches(torch, scramble_then_step, 20)
+    entry("config3_3x3_scramble_then_step_8Mi", t, n * (d + 1), "transitions/s", n * (d + 54 + 5) + n * (2 * 54 + 6))
+    del moves, act, st, so, rw
+
     # config 4: 3x3x3 ADI expansion, 4 Mi parents -> bf16 [N,12,480] + solved + reward
     n = 4 * 2 ** 20
     parents, _, _ = ops.scramble(3, torch.randint(0, 12, (n, 30), dtype=torch.uint8, device=dev, generator=gen),
