@@ -684,3 +684,34 @@ def test_batched_mcts_matches_oracle_more_cases(size):
         root = tree.nodes[tree.key(env.cube)]
         assert out["root_N"][i].tolist() == [int(v) for v in root[3]], i
         assert out["root_W"][i].tolist() == [float(v) for v in root[2]], i
+
+
+def test_new_entry_points_edge_cases():
+    """Empty and degenerate inputs of the entry points added in round 1."""
+    from rubiks_cube_solver_b200 import mcts_batch
+    from oracle.gen_golden import ExactSearchNet
+    d = dev()
+    for size in SIZES:
+        a = T.N_ACTIONS[size]
+        assert ops.moves_from_seeds(size, [], 10).shape == (0, 10)
+        assert ops.moves_from_seeds(size, [3, 4], 0).shape == (2, 0)
+        with pytest.raises(ValueError):
+            ops.moves_from_seeds(size, [1], 129)
+        tv, tp, err = ops.adi_targets(size, torch.empty((0, a), device=d), torch.empty((0, a), dtype=torch.uint8, device=d),
+                                      torch.empty(0, device=d), torch.empty(0, dtype=torch.int32, device=d), 1.0)
+        assert tv.numel() == 0 and tp.numel() == 0 and err.numel() == 0
+        # one tree, already one move from solved: the very first simulation returns [the solving move]
+        net = ExactSearchNet(T.STATE_DIM[size], a).to(d)
+        root = O.scramble(size, np.array([[2]]))
+        out = mcts_batch.BatchedMCTS(net, size, num_sim=5).run(cu(root), seeds=[0])
+        assert out["solved"].tolist() == [True] and out["n_sims"].tolist() == [1]
+        assert out["actions"][0, :1].tolist() == [3] and int(out["n_actions"][0]) == 1
+        with pytest.raises(ValueError):
+            mcts_batch.BatchedMCTS(net, size, num_sim=300)
+    # the C ABI rejects bad arguments without touching the device
+    lib = _lib.load()
+    assert lib.cube_moves_from_seeds(3, None, 5, 10, None, None, None) == _lib.CUBE_ERR_ARG
+    assert lib.cube_moves_from_seeds(4, None, 0, 10, None, None, None) == _lib.CUBE_ERR_SIZE
+    assert lib.cube_adi_targets(3, None, None, None, None, None, 0, 7, None, None, None, None) == _lib.CUBE_ERR_ARG
+    assert lib.cube_mcts_traverse(3, None, ctypes.c_float(1.0), 150, None) == _lib.CUBE_ERR_ARG
+    assert lib.cube_set_reserved_sms(-1) == _lib.CUBE_ERR_ARG and lib.cube_set_reserved_sms(0) == 0
