@@ -1,3 +1,5 @@
+"""End-to-end (host buffers) fused scramble over chunk sizes / stage counts, next to the raw PCIe copy
+ceilings of the same box:  python tools/e2e_sweep.py"""
 import sys, time
 sys.path.insert(0, '/root/repo')
 import torch

@@ -1,3 +1,5 @@
+"""Per-launch gaps of chained scramble launches (events between launches break the dependent-launch
+chain on purpose): how much of a short timed region is launch latency."""
 import sys, time
 sys.path.insert(0, '/root/repo')
 import torch

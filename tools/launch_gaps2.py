@@ -1,3 +1,5 @@
+"""Fixed overhead of a 5-step timed region with / without the NVML sampler thread and a second sync
+(used to move the sampler thread's start-up out of bench.py's timed region)."""
 import sys, time, threading
 sys.path.insert(0, '/root/repo')
 import torch, bench

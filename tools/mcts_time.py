@@ -1,3 +1,4 @@
+"""Time bench.py's batched-MCTS entry alone:  python tools/mcts_time.py"""
 import sys, json
 sys.path.insert(0, '/root/repo')
 import torch, bench
