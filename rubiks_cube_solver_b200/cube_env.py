@@ -187,15 +187,17 @@ class CubeEnv(_EnvBase):
         batch = adi.generate_samples(self.cube_size, torch.from_numpy(moves.astype(np.uint8)).to(self._sim_device),
                                      model, temperature, model_device=self.device)
         obs = self._obs_from_u8(batch["state_u8"].cpu().numpy())
-        tv = batch["target_value"].cpu().numpy()
-        tp = batch["target_policy"].cpu().numpy()
-        err = batch["error"].cpu().numpy()
+        tv = batch["target_value"].cpu().tolist()           # Python floats of the float32 values, like .item()
+        tp = batch["target_policy"].cpu().tolist()
+        err = batch["error"].cpu().tolist()
         depth = sample_scramble_count
+        append = replay_buffer.append
+        i = 0
         for c in range(sample_cube_count):
-            for k in range(depth):
-                i = c * depth + k
-                replay_buffer.append({'state': obs[i], 'target_value': float(tv[i]), 'target_policy': int(tp[i]),
-                                      'scramble_count': k + 1, 'error': float(err[i])})
+            for k in range(1, depth + 1):
+                append({'state': obs[i], 'target_value': tv[i], 'target_policy': tp[i], 'scramble_count': k,
+                        'error': err[i]})
+                i += 1
         # the env is left on the last cube's final state, as the reference loop leaves it
         self.sim_cube = batch["final_stickers"][-1].cpu().numpy().astype(np.int64)
         self.cube = obs[-1]
