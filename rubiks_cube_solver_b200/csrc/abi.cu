@@ -46,6 +46,13 @@ int reserved_sms()
     return g_reserved_sms;
 }
 
+int device_slot()
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
+    return dev & 63;
+}
+
 int persistent_ctas()
 {
     const int n = sm_count() - reserved_sms();

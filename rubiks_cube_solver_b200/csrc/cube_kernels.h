@@ -58,6 +58,8 @@ int launch_mcts_update(int size, const cube_mcts_tree_t& t, const uint8_t* leaf_
 int launch_decode2(const void* onehot, int dtype, long long n, uint8_t* out, cudaStream_t stream);
 
 int sm_count();
+// index of the current device for per-device launch state (cudaFuncSetAttribute is per device), 0..63
+int device_slot();
 // CTAs of a persistent (one-per-SM) grid: sm_count() minus the SMs the caller reserved for other
 // kernels (cube_set_reserved_sms / CUBE_RESERVED_SMS), e.g. one for NCCL's reduction kernel
 int persistent_ctas();

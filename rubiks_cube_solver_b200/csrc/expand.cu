@@ -263,10 +263,11 @@ int launch_one(const uint8_t* states, long long n, uint8_t* children, void* chil
     // the phases of a tile are separated by barriers, so overlap comes from having many CTAs
     // per SM in different phases, scheduled by the hardware
     const long long grid = n_tiles < 0x7fffffffLL ? n_tiles : 0x7fffffffLL;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {};                       // per device: function attributes are per device
+    bool& done = configured[cube::device_slot()];
+    if (!done) {
         cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        configured = true;
+        done = true;
     }
     kern<<<(unsigned)grid, kThreads, 0, stream>>>(states, n, children, (uint8_t*)child_onehot,
                                                   (uint8_t*)parent_onehot, solved, reward, counters);

@@ -325,7 +325,10 @@ int launch_classic(const uint8_t* moves, long long n, int depth, uint8_t* out, u
     if (staged) {
         auto kern_full = scramble_tile_kernel<SIZE, true>;
         auto kern_tail = scramble_tile_kernel<SIZE, false>;
-        static int configured_smem = -1;
+        static int configured_dev[64];
+        static bool init_done = false;
+        if (!init_done) { for (int i = 0; i < 64; ++i) configured_dev[i] = -1; init_done = true; }
+        int& configured_smem = configured_dev[cube::device_slot()];
         if (smem > configured_smem) {
             cudaError_t e = cudaFuncSetAttribute(kern_full, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
             if (e == cudaSuccess) e = cudaFuncSetAttribute(kern_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -372,8 +375,10 @@ int launch_one(const uint8_t* moves, long long n, int depth, uint8_t* out, uint8
             // straight-line specialisations: the reference's default depth (config.yaml:7) and BASELINE config 2's
             auto kern = depth == 30 ? scramble_pairs_kernel<SIZE, 30>
                       : depth == 20 ? scramble_pairs_kernel<SIZE, 20> : scramble_pairs_kernel<SIZE, 0>;
-            static int configured_smem[3] = {-1, -1, -1};
-            int& cfg = configured_smem[depth == 30 ? 1 : depth == 20 ? 2 : 0];
+            static int configured_smem[64][3];
+            static bool init_done = false;
+            if (!init_done) { for (int i = 0; i < 64; ++i) for (int j = 0; j < 3; ++j) configured_smem[i][j] = -1; init_done = true; }
+            int& cfg = configured_smem[cube::device_slot()][depth == 30 ? 1 : depth == 20 ? 2 : 0];
             if (smem > cfg) {
                 cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
                 if (e != cudaSuccess) return (int)e;

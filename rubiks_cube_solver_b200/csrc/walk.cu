@@ -273,7 +273,8 @@ template <int SIZE>
 int launch_classic(const uint8_t* in, const uint8_t* moves, long long n, int depth, uint8_t* out, uint8_t* solved,
                    float* reward, unsigned long long* counters, cudaStream_t stream)
 {
-    static bool configured = false;
+    static bool configured_dev[64] = {};                   // per device: function attributes are per device
+    bool& configured = configured_dev[cube::device_slot()];
     if (!configured) {
         cudaFuncSetAttribute(walk_tile_kernel<SIZE, true>, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
@@ -306,7 +307,10 @@ int launch_tiles(const uint8_t* in, const uint8_t* moves, long long n, int depth
             if (n_tiles > 0x3fffffff) n_tiles = 0x3fffffff;
             const int smem = L::bytes(depth, warps);
             auto kern = walk_private_kernel<SIZE>;
-            static int configured_smem = -1;
+            static int configured_dev[64];
+            static bool init_done = false;
+            if (!init_done) { for (int i = 0; i < 64; ++i) configured_dev[i] = -1; init_done = true; }
+            int& configured_smem = configured_dev[cube::device_slot()];
             if (smem > configured_smem) {
                 const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
                 if (e != cudaSuccess) return (int)e;

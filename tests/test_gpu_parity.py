@@ -715,3 +715,23 @@ def test_new_entry_points_edge_cases():
     assert lib.cube_adi_targets(3, None, None, None, None, None, 0, 7, None, None, None, None) == _lib.CUBE_ERR_ARG
     assert lib.cube_mcts_traverse(3, None, ctypes.c_float(1.0), 150, None) == _lib.CUBE_ERR_ARG
     assert lib.cube_set_reserved_sms(-1) == _lib.CUBE_ERR_ARG and lib.cube_set_reserved_sms(0) == 0
+
+
+def test_two_devices_in_one_process():
+    """Launch state (dynamic shared-memory opt-in, scheduler slots, SM count) is kept per device."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    rng = np.random.RandomState(2)
+    for size in SIZES:
+        a = T.N_ACTIONS[size]
+        moves = rng.randint(a, size=(64 * 50 + 7, 30)).astype(np.uint8)
+        want = O.scramble(size, moves)
+        act = rng.randint(a, size=moves.shape[0]).astype(np.uint8)
+        for d in (1, 0, 1):
+            device = torch.device("cuda", d)
+            st, so, _ = ops.scramble(size, torch.from_numpy(moves).to(device))
+            assert st.device == device and (st.cpu().numpy() == want).all()
+            stepped, _, _ = ops.step(size, st, torch.from_numpy(act).to(device))
+            assert (stepped.cpu().numpy() == O.apply_moves(size, want, act)).all()
+            res = ops.expand(size, stepped[:100].contiguous(), dtype=torch.bfloat16, want_children=True)
+            assert (res["children"].cpu().numpy() == O.expand(size, O.apply_moves(size, want, act)[:100])[0]).all()
