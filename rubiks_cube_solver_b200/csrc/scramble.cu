@@ -363,7 +363,7 @@ int launch_one(const uint8_t* moves, long long n, int depth, uint8_t* out, uint8
     using L = PairSmem<SIZE>;
     using G = CubeGeom<SIZE>;
     long long done = 0;
-    const char* force = getenv("CUBE_SCRAMBLE_CLASSIC");               // A/B switch for profiling
+    static const char* const force = getenv("CUBE_SCRAMBLE_CLASSIC");               // A/B switch for profiling
     if (depth >= 1 && depth <= kMaxPairDepth && n >= kPairTile && !(force && force[0] == '1')) {
         int warps = (kSmemLimit - 256 - L::kPerWarp) / L::per_warp(depth);
         if (warps > PairCfg<SIZE>::kMaxWarps) warps = PairCfg<SIZE>::kMaxWarps;

@@ -297,7 +297,7 @@ int launch_tiles(const uint8_t* in, const uint8_t* moves, long long n, int depth
     using L = WalkSmem<SIZE>;
     using G = CubeGeom<SIZE>;
     long long done = 0;
-    const char* force = getenv("CUBE_WALK_CLASSIC");                   // A/B switch for profiling
+    static const char* const force = getenv("CUBE_WALK_CLASSIC");                   // A/B switch for profiling
     if (depth >= 1 && depth <= kMaxPrivateDepth && out && n >= kRowsPerTile && !(force && force[0] == '1')) {
         int warps = (227 * 1024 - L::kPerWarp) / L::per_warp(depth);
         if (warps > kMaxWalkWarps) warps = kMaxWalkWarps;
