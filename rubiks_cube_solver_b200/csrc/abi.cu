@@ -1,5 +1,6 @@
 // extern "C" boundary of libcube_b200.so: argument checks, then the launchers.
 // See include/cube_b200.h for the contract of every entry point.
+#include <atomic>
 #include <cstdlib>
 #include <cstdio>
 #include <cuda_runtime.h>
@@ -61,16 +62,16 @@ int persistent_ctas()
 
 int sm_count()
 {
-    static int cached_dev = -1, cached = 0;
+    static std::atomic<int> cached[64];   // per device, 0 = not asked yet (host threads may drive different devices)
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    if (dev != cached_dev) {
-        int v = 0;
+    std::atomic<int>& c = cached[dev & 63];
+    int v = c.load(std::memory_order_relaxed);
+    if (v == 0) {
         if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v < 1) v = 148;
-        cached = v;
-        cached_dev = dev;
+        c.store(v, std::memory_order_relaxed);
     }
-    return cached;
+    return v;
 }
 
 }  // namespace cube

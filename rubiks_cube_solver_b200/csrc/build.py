@@ -34,8 +34,14 @@ def build(force=False, verbose=False):
     srcs = [s for s in SOURCES if os.path.exists(os.path.join(HERE, s))]
     if not force and not stale():
         return LIB
-    cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + srcs
-    subprocess.check_call(cmd, cwd=HERE)
+    tmp = LIB + ".tmp%d" % os.getpid()                     # never leave a half-written library in the tree
+    cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + srcs
+    try:
+        subprocess.check_call(cmd, cwd=HERE)
+        os.replace(tmp, LIB)
+    finally:
+        if os.path.exists(tmp):
+            os.remove(tmp)
     return LIB
 
 

@@ -49,6 +49,15 @@ __device__ __forceinline__ void load(void* dst_smem, const void* src_gmem, uint3
                  : "memory");
 }
 
+// global -> shared through a 2-D tensor map (box at element coordinates {c0, c1}; the map fixes the box,
+// the swizzle and the byte count), completion counted on `bar`
+__device__ __forceinline__ void load_tile_2d(void* dst_smem, const void* tensor_map, int c0, int c1, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_addr(dst_smem)), "l"(tensor_map), "r"(c0), "r"(c1), "r"(smem_addr(bar))
+                 : "memory");
+}
+
 // shared -> global, tracked by the thread's bulk group
 __device__ __forceinline__ void store(void* dst_gmem, const void* src_smem, uint32_t bytes)
 {

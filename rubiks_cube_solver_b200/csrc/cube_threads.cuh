@@ -1,6 +1,7 @@
 // Per-thread bodies of the cube kernels, host+device (CUBE_HD) so that the test-only
 // emulation harness (tests/host_emul/) can run exactly this code on the CPU.
 #pragma once
+#include <cstdlib>
 #include "cube_common.cuh"
 
 // ---- K1: fused scramble -------------------------------------------------------------------
@@ -84,6 +85,7 @@ CUBE_HD CubeVec4 cube_ld128(const uint8_t* p)
     return CubeVec4{v.x, v.y, v.z, v.w};
 #else
     CubeVec4 v;
+    if (reinterpret_cast<uintptr_t>(p) & 15) abort();    // the device's 128-bit load would fault
     const uint32_t* q = reinterpret_cast<const uint32_t*>(p);
     v.x = q[0]; v.y = q[1]; v.z = q[2]; v.w = q[3];
     return v;
@@ -315,6 +317,73 @@ CUBE_HD void scramble_pairs_run(CubieState (&st)[NS], const int (&rows)[NS], int
 #pragma unroll
             for (int k = 0; k < NS; ++k) pair_apply<SIZE>(st[k], tbl, cube_prmt(y[k], lanereg, 0x5534u), roff);
         }
+    }
+}
+
+// Swizzled move tile.  In the flat tile image a lane's move words are `rows * depth` bytes apart: when
+// that stride shares a large power of two with the 32 banks (depth 32: 16 words, depth 64: 32 words) every
+// move-word load of the warp serialises 16- or 32-fold.  For depths that are multiples of 8 (3x3x3) / 16
+// (2x2x2) the kernel stages the tile with ONE 2-D tensor copy whose shared-memory side uses the copy
+// engine's 128-byte swizzle: the 16-byte unit at flat offset f lands at f ^ (((f >> 7) & 7) << 4).  The
+// moves are then read sixteen at a time with 128-bit loads; the eight lanes of a quarter warp, 2*depth
+// bytes apart, fall into (nearly always) eight different bank groups.  `tile` is the buffer (1024-byte
+// aligned in the shared window), `lane` the lane: 3x3x3 rows 2l, 2l+1 are the contiguous slice at
+// lane * 2 * depth, 2x2x2 rows l, l+32 sit at lane * depth and (lane + 32) * depth.  A group of four words
+// adds <= 16 to a twist field and the fold after it leaves <= 10, so a field never exceeds 26.
+CUBE_HD uint32_t cube_swz128(uint32_t f) { return f ^ ((f >> 3) & 0x70u); }
+
+template <int SIZE, int NS, class TBL>
+CUBE_HD void scramble_pairs_run_swizzled(CubieState (&st)[NS], const uint8_t* tile, int lane, int depth, const TBL& tbl,
+                                         uint32_t lanereg, uint32_t roff)
+{
+    const uint32_t bias = tbl.bias();
+    constexpr uint32_t K = (uint32_t)(CUBE_PAIR_BASE + 256);
+    static_assert(NS == 2, "two rows per lane");
+    auto word = [&](uint32_t w0, uint32_t w1) {
+        const uint32_t y[2] = {w0 * K + bias, w1 * K + bias};
+#pragma unroll
+        for (int k = 0; k < NS; ++k) pair_apply<SIZE>(st[k], tbl, cube_prmt(y[k], lanereg, 0x5514u), roff);
+#pragma unroll
+        for (int k = 0; k < NS; ++k) pair_apply<SIZE>(st[k], tbl, cube_prmt(y[k], lanereg, 0x5534u), roff);
+    };
+    auto fold = [&]() {
+#pragma unroll
+        for (int k = 0; k < NS; ++k) {
+            st[k].c0 = cubie_fold_twist(st[k].c0);
+            st[k].c1 = cubie_fold_twist(st[k].c1);
+        }
+    };
+    auto unit = [&](uint32_t f) { return cube_ld128(tile + cube_swz128(f)); };
+    if (SIZE == 3 && (depth & 8)) {
+        // depth = 16a + 8: row 1 starts in the middle of 16-byte unit a of the lane's slice.  Row 0's words
+        // 4g..4g+3 are unit g; row 1's are the upper half of unit a+g and the lower half of unit a+g+1
+        // (carried over in `p`).
+        const int a = depth >> 4;
+        const uint32_t f0 = (uint32_t)(lane * 2 * depth);
+        CubeVec4 p = unit(f0 + 16 * a);
+        const uint32_t last0[2] = {p.x, p.y};
+        for (int g = 0; g < a; ++g) {
+            const CubeVec4 v = unit(f0 + 16 * g), q = unit(f0 + 16 * (a + g + 1));
+            word(v.x, p.z);
+            word(v.y, p.w);
+            word(v.z, q.x);
+            word(v.w, q.y);
+            p = q;
+            fold();
+        }
+        word(last0[0], p.z);
+        word(last0[1], p.w);
+        return;
+    }
+    const uint32_t f0 = (uint32_t)((SIZE == 3 ? 2 * lane : lane) * depth);
+    const uint32_t f1 = (uint32_t)((SIZE == 3 ? 2 * lane + 1 : lane + 32) * depth);
+    for (int g = 0; g < depth; g += 16) {                // rows 16-byte aligned (depth % 16 == 0)
+        const CubeVec4 v = unit(f0 + g), q = unit(f1 + g);
+        word(v.x, q.x);
+        word(v.y, q.y);
+        word(v.z, q.z);
+        word(v.w, q.w);
+        fold();
     }
 }
 

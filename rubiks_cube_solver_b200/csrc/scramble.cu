@@ -18,6 +18,8 @@
 // The kernel is bound by the ALU pipe (PRMT/LOP3) and the shared-memory pipe (six
 // table words per move), not by HBM -- see DESIGN.md.
 #include <cstdlib>
+#include <cstring>
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include "cube_bulk.cuh"
 #include "cube_kernels.h"
@@ -165,13 +167,23 @@ struct PairSmem {
     static constexpr int kEdgeLut = kCornerLut + 256;
     static constexpr int kPerWarp = kEdgeLut + 256;
     static constexpr int kOutBytes = kPairTile * G::S;                // 3456 / 1536: multiples of 16
-    __host__ __device__ static constexpr int move_stride(int depth) { return kPairTile * depth + 16; }
-    __host__ __device__ static constexpr int per_warp(int depth) { return 16 + kOutBytes + 2 * move_stride(depth); }
+    // flat tile image (+16: the last row's word loads run past it), or the swizzled tile (`swz`: the copy
+    // engine's 128-byte swizzle wants 1024-byte aligned buffers)
+    __host__ __device__ static constexpr int round1k(int x) { return (x + 1023) & ~1023; }
+    __host__ __device__ static constexpr int move_stride(int depth, bool swz = false)
+    {
+        return swz ? round1k(kPairTile * depth) : kPairTile * depth + 16;
+    }
+    __host__ __device__ static constexpr int moves_at(bool swz = false) { return swz ? round1k(16 + kOutBytes) : 16 + kOutBytes; }
+    __host__ __device__ static constexpr int per_warp(int depth, bool swz = false)
+    {
+        return moves_at(swz) + 2 * move_stride(depth, swz);
+    }
     // never below 65 792 + 256 bytes: a garbage move byte (> 12) makes a garbage pair row (<= 255) whose
     // two vectors must still be inside the CTA's allocation (255 * 256 + 240 + 128 + 16)
-    __host__ __device__ static constexpr int bytes(int depth, int warps)
+    __host__ __device__ static constexpr int bytes(int depth, int warps, bool priv = false)
     {
-        return kPerWarp + warps * per_warp(depth) < 66048 ? 66048 : kPerWarp + warps * per_warp(depth);
+        return kPerWarp + warps * per_warp(depth, priv) < 66048 ? 66048 : kPerWarp + warps * per_warp(depth, priv);
     }
 };
 
@@ -179,25 +191,38 @@ template <int SIZE, int DEPTH>
 __global__ void __launch_bounds__(PairCfg<SIZE>::kMaxWarps * 32, 1)
 scramble_pairs_kernel(const uint8_t* __restrict__ moves, int n_tiles, int depth_rt, uint8_t* __restrict__ out,
                       uint8_t* __restrict__ solved, float* __restrict__ reward, unsigned long long* __restrict__ counters,
-                      sched::Slot* slot, int tail_div)
+                      sched::Slot* slot, int tail_div, const __grid_constant__ CUtensorMap move_map)
 {
     using L = PairSmem<SIZE>;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int depth = DEPTH > 0 ? DEPTH : depth_rt;
+    // DEPTH < 0: any depth that is a multiple of 8 (3x3x3) / 16 (2x2x2), staged as a swizzled tile through
+    // `move_map` (see scramble_pairs_run_swizzled): the flat image bank-conflicts at those depths
+    constexpr bool kPriv = DEPTH < 0;
+    constexpr uint32_t kAlign = kPriv ? 1024u : 256u;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // everything is laid out from a 256-byte boundary of the shared window (see PairTableShared)
     const uint32_t window = bulk::smem_addr(smem_raw);
-    uint8_t* smem = smem_raw + ((256u - (window & 255u)) & 255u);
+    uint8_t* smem = smem_raw + ((kAlign - (window & (kAlign - 1u))) & (kAlign - 1u));
     uint8_t* s_ptbl = smem + L::kTable;
     const PairTableShared tbl{(bulk::smem_addr(s_ptbl) >> 8) * 0x01000100u};
     uint32_t* s_clut = reinterpret_cast<uint32_t*>(smem + L::kCornerLut);
     uint32_t* s_elut = reinterpret_cast<uint32_t*>(smem + L::kEdgeLut);
-    uint8_t* mine = smem + L::kPerWarp + warp * L::per_warp(depth);
+    uint8_t* mine = smem + L::kPerWarp + warp * L::per_warp(depth, kPriv);
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(mine);             // [2] mbarriers
     uint8_t* s_out = mine + 16;                                       // [kOutBytes]
-    uint8_t* s_moves = s_out + L::kOutBytes;                          // [2][move_stride]
-    const int mstride = L::move_stride(depth);
+    uint8_t* s_moves = mine + L::moves_at(kPriv);                     // [2][move_stride]
+    const int mstride = L::move_stride(depth, kPriv);
     const uint32_t move_bytes = (uint32_t)(kPairTile * depth);
+    // stage tile `t`'s move bytes in buffer `b` (warp-uniform arguments): one 1-D bulk copy for the flat
+    // image, one 2-D tensor copy (rows of 128 bytes, 128-byte swizzle) for the swizzled tile
+    auto stage = [&](int t, int b) {
+        if (lane == 0) {
+            bulk::mbar_expect_tx(&s_bar[b], move_bytes);
+            if (!kPriv) bulk::load(s_moves + b * mstride, moves + (long long)t * move_bytes, move_bytes, &s_bar[b]);
+            else bulk::load_tile_2d(s_moves + b * mstride, &move_map, 0, t * (depth >> 1), &s_bar[b]);
+        }
+    };
 
     // Programmatic dependent launch: the NEXT kernel of the stream may start as soon as SM resources free
     // up; its prologue below touches only constant tables and shared memory, and it waits for this grid
@@ -214,10 +239,7 @@ scramble_pairs_kernel(const uint8_t* __restrict__ moves, int n_tiles, int depth_
     sched::WarpTiles tiles;
     tiles.init(slot, n_tiles, (int)(blockDim.x >> 5), warp, lane, tail_div);
     int tile = tiles.pop(lane);
-    if (lane == 0 && tile < n_tiles) {
-        bulk::mbar_expect_tx(&s_bar[0], move_bytes);
-        bulk::load(s_moves, moves + (long long)tile * move_bytes, move_bytes, &s_bar[0]);
-    }
+    if (tile < n_tiles) stage(tile, 0);
     const int rows[2] = {(SIZE == 3) ? 2 * lane : lane, (SIZE == 3) ? 2 * lane + 1 : lane + 32};
     const uint32_t lanereg = pair_lanereg<SIZE>(lane), roff = pair_roff2(lane);
     const ColourLutShared lut{bulk::smem_addr(s_clut), bulk::smem_addr(s_elut)};
@@ -226,16 +248,14 @@ scramble_pairs_kernel(const uint8_t* __restrict__ moves, int n_tiles, int depth_
     for (int it = 0; tile < n_tiles; ++it) {
         const int buf = it & 1;
         const int next = tiles.pop(lane);
-        if (lane == 0 && next < n_tiles) {                            // prefetch the next tile's moves
-            bulk::mbar_expect_tx(&s_bar[buf ^ 1], move_bytes);
-            bulk::load(s_moves + (buf ^ 1) * mstride, moves + (long long)next * move_bytes, move_bytes, &s_bar[buf ^ 1]);
-        }
+        if (next < n_tiles) stage(next, buf ^ 1);                     // prefetch the next tile's moves
         bulk::mbar_wait(&s_bar[buf], (uint32_t)(it >> 1) & 1u);
 
         CubieState st[2];
         cubie_init(st[0]);
         cubie_init(st[1]);
-        scramble_pairs_run<SIZE, DEPTH, 2>(st, rows, depth, s_moves + buf * mstride, tbl, lanereg, roff);
+        if (kPriv) scramble_pairs_run_swizzled<SIZE, 2>(st, s_moves + buf * mstride, lane, depth, tbl, lanereg, roff);
+        else scramble_pairs_run<SIZE, (DEPTH > 0 ? DEPTH : 0), 2>(st, rows, depth, s_moves + buf * mstride, tbl, lanereg, roff);
         if (lane == 0) bulk::wait_read_all();                         // the previous store has released the out tile
         __syncwarp();
         const bool ok0 = scramble_pairs_finish<SIZE>(st[0], rows[0], lut, s_out);
@@ -356,6 +376,34 @@ int launch_classic(const uint8_t* moves, long long n, int depth, uint8_t* out, u
 
 constexpr int kSmemLimit = 227 * 1024;
 
+// Tensor map of a move array for the swizzled tiles of K1p: the bytes as rows of 128, a box = one tile of
+// 64 move rows (depth / 2 rows of 128 bytes), 128-byte swizzle on the shared-memory side.  The encoder is a
+// driver entry point, fetched through the runtime so that the library does not link libcuda.
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+bool encode_move_map(CUtensorMap* map, const uint8_t* moves, long long n_tiles, int depth)
+{
+    static const EncodeTiledFn encode = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        (void)cudaGetLastError();
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    if (!encode) return false;
+    const cuuint64_t dims[2] = {128, (cuuint64_t)(n_tiles * (depth / 2))};
+    const cuuint64_t strides[1] = {128};
+    const cuuint32_t box[2] = {128, (cuuint32_t)(depth / 2)};
+    const cuuint32_t elem[2] = {1, 1};
+    return encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(moves), dims, strides, box, elem,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int SIZE>
 int launch_one(const uint8_t* moves, long long n, int depth, uint8_t* out, uint8_t* solved, float* reward,
                unsigned long long* counters, cudaStream_t stream)
@@ -365,20 +413,30 @@ int launch_one(const uint8_t* moves, long long n, int depth, uint8_t* out, uint8
     long long done = 0;
     static const char* const force = getenv("CUBE_SCRAMBLE_CLASSIC");               // A/B switch for profiling
     if (depth >= 1 && depth <= kMaxPairDepth && n >= kPairTile && !(force && force[0] == '1')) {
-        int warps = (kSmemLimit - 256 - L::kPerWarp) / L::per_warp(depth);
+        // depths whose flat row stride bank-conflicts on the move words are staged as swizzled tiles
+        static const bool swz_ok = !(getenv("CUBE_PAIR_SWIZZLE") && getenv("CUBE_PAIR_SWIZZLE")[0] == '0');
+        static_assert(L::kPerWarp % 1024 == 0, "the per-warp areas of the swizzled variant start on 1 KB");
+        alignas(64) CUtensorMap move_map;
+        memset(&move_map, 0, sizeof(move_map));
+        long long tiles_all = n / kPairTile;
+        if (tiles_all > 0x3fffffff) tiles_all = 0x3fffffff;           // 32-bit tile counters; the rest goes below
+        const bool priv = swz_ok && depth % (SIZE == 3 ? 8 : 16) == 0 && tiles_all * (depth / 2) < 0x7fffffffLL &&
+                          encode_move_map(&move_map, moves, tiles_all, depth);
+        const int slack = priv ? 1024 : 256;                          // alignment of the carve-up in the window
+        int warps = (kSmemLimit - slack - L::kPerWarp) / L::per_warp(depth, priv);
         if (warps > PairCfg<SIZE>::kMaxWarps) warps = PairCfg<SIZE>::kMaxWarps;
         warps &= ~3;                                                   // the same number on every scheduler
         if (warps >= 4) {
-            long long n_tiles = n / kPairTile;
-            if (n_tiles > 0x3fffffff) n_tiles = 0x3fffffff;           // 32-bit tile counters; the rest goes below
-            const int smem = L::bytes(depth, warps) + 256;
+            const long long n_tiles = tiles_all;
+            const int smem = L::bytes(depth, warps, priv) + slack;
             // straight-line specialisations: the reference's default depth (config.yaml:7) and BASELINE config 2's
             auto kern = depth == 30 ? scramble_pairs_kernel<SIZE, 30>
-                      : depth == 20 ? scramble_pairs_kernel<SIZE, 20> : scramble_pairs_kernel<SIZE, 0>;
-            static int configured_smem[64][3];
+                      : depth == 20 ? scramble_pairs_kernel<SIZE, 20>
+                      : priv ? scramble_pairs_kernel<SIZE, -1> : scramble_pairs_kernel<SIZE, 0>;
+            static int configured_smem[64][4];
             static bool init_done = false;
-            if (!init_done) { for (int i = 0; i < 64; ++i) for (int j = 0; j < 3; ++j) configured_smem[i][j] = -1; init_done = true; }
-            int& cfg = configured_smem[cube::device_slot()][depth == 30 ? 1 : depth == 20 ? 2 : 0];
+            if (!init_done) { for (int i = 0; i < 64; ++i) for (int j = 0; j < 4; ++j) configured_smem[i][j] = -1; init_done = true; }
+            int& cfg = configured_smem[cube::device_slot()][depth == 30 ? 1 : depth == 20 ? 2 : priv ? 3 : 0];
             if (smem > cfg) {
                 cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
                 if (e != cudaSuccess) return (int)e;
@@ -400,7 +458,7 @@ int launch_one(const uint8_t* moves, long long n, int depth, uint8_t* out, uint8
             cfg_l.attrs = attr;
             cfg_l.numAttrs = pdl ? 1 : 0;
             cudaError_t e = cudaLaunchKernelEx(&cfg_l, kern, moves, (int)n_tiles, depth, out, solved, reward, counters, slot,
-                                               sched::tail_div());
+                                               sched::tail_div(), move_map);
             if (e == cudaSuccess) e = cudaGetLastError();
             if (e != cudaSuccess) return (int)e;
             done = n_tiles * kPairTile;

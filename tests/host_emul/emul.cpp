@@ -35,7 +35,7 @@ void scramble_t(const uint8_t* moves, long long n, int depth, uint8_t* out, uint
 
 // K1p: persistent pair-table kernel, one 64-row tile at a time with the kernel's lane -> row map
 template <int SIZE>
-void scramble_pairs_t(const uint8_t* moves, long long n, int depth, uint8_t* out, uint8_t* solved, bool fixed)
+void scramble_pairs_t(const uint8_t* moves, long long n, int depth, uint8_t* out, uint8_t* solved, bool fixed, bool priv)
 {
     using G = CubeGeom<SIZE>;
     const uint32_t* clut = SIZE == 3 ? kCornerColour3 : kCornerColour2;
@@ -43,9 +43,15 @@ void scramble_pairs_t(const uint8_t* moves, long long n, int depth, uint8_t* out
     uint8_t* s_ptbl_mem = tbl.data() + ((16 - (reinterpret_cast<uintptr_t>(tbl.data()) & 15)) & 15);
     for (int t = 0; t < 96; ++t) pair_table_fill<SIZE>(s_ptbl_mem, t, 96);
     std::vector<uint8_t> s_moves(64 * depth + 16), s_out(64 * G::S);
+    std::vector<uint8_t> s_priv(64 * depth + 16);
     for (long long base = 0; base + 64 <= n; base += 64) {
         std::memset(s_moves.data(), 0xee, s_moves.size());
         std::memcpy(s_moves.data(), moves + base * depth, (size_t)64 * depth);
+        if (priv) {                                                  // the copy engine's 128-byte swizzle
+            std::memset(s_priv.data(), 0xee, s_priv.size());
+            for (int f = 0; f < 64 * depth; f += 16)
+                std::memcpy(s_priv.data() + cube_swz128((uint32_t)f), moves + base * depth + f, 16);
+        }
         uint32_t ok[2] = {0, 0};
         for (int lane = 0; lane < 32; ++lane) {                      // one lane = two rows in lockstep
             const int rows[2] = {(SIZE == 3) ? 2 * lane : lane, (SIZE == 3) ? 2 * lane + 1 : lane + 32};
@@ -54,7 +60,8 @@ void scramble_pairs_t(const uint8_t* moves, long long n, int depth, uint8_t* out
             cubie_init(st[1]);
             const uint32_t lr = pair_lanereg<SIZE>(lane);
             const PairTableHost s_ptbl{s_ptbl_mem};
-            if (fixed && depth == 30) scramble_pairs_run<SIZE, 30, 2>(st, rows, depth, s_moves.data(), s_ptbl, lr, pair_roff2(lane));
+            if (priv) scramble_pairs_run_swizzled<SIZE, 2>(st, s_priv.data(), lane, depth, s_ptbl, lr, pair_roff2(lane));
+            else if (fixed && depth == 30) scramble_pairs_run<SIZE, 30, 2>(st, rows, depth, s_moves.data(), s_ptbl, lr, pair_roff2(lane));
             else if (fixed && depth == 20) scramble_pairs_run<SIZE, 20, 2>(st, rows, depth, s_moves.data(), s_ptbl, lr, pair_roff2(lane));
             else if (fixed && depth == 43) scramble_pairs_run<SIZE, 43, 2>(st, rows, depth, s_moves.data(), s_ptbl, lr, pair_roff2(lane));
             else scramble_pairs_run<SIZE, 0, 2>(st, rows, depth, s_moves.data(), s_ptbl, lr, pair_roff2(lane));
@@ -192,12 +199,13 @@ void emul_scramble(int size, const uint8_t* moves, long long n, int depth, uint8
 {
     if (size == 3) scramble_t<3>(moves, n, depth, out, solved); else scramble_t<2>(moves, n, depth, out, solved);
 }
-// fixed != 0: use the compile-time-depth instantiation when one exists (30, 20; 43 only here, to
-// exercise the unrolled fold schedule)
+// fixed == 1: use the compile-time-depth instantiation when one exists (30, 20; 43 only here, to
+// exercise the unrolled fold schedule); fixed == 2: the swizzled move tile (depth % 8 == 0 for
+// 3x3x3, % 16 == 0 for 2x2x2)
 void emul_scramble_pairs(int size, const uint8_t* moves, long long n, int depth, uint8_t* out, uint8_t* solved, int fixed)
 {
-    if (size == 3) scramble_pairs_t<3>(moves, n, depth, out, solved, fixed != 0);
-    else scramble_pairs_t<2>(moves, n, depth, out, solved, fixed != 0);
+    if (size == 3) scramble_pairs_t<3>(moves, n, depth, out, solved, fixed == 1, fixed == 2);
+    else scramble_pairs_t<2>(moves, n, depth, out, solved, fixed == 1, fixed == 2);
 }
 void emul_walk(int size, const uint8_t* in, const uint8_t* moves, long long n, int depth, uint8_t* out,
                uint8_t* solved)

@@ -122,6 +122,27 @@ def test_scramble_vs_oracle_depths(size, depth):
 
 
 @pytest.mark.parametrize("size", SIZES)
+@pytest.mark.parametrize("depth", (8, 16, 24, 32, 48, 64, 72, 96))
+def test_scramble_private_move_layout(size, depth):
+    """Depths whose flat tile image bank-conflicts run K1p with lane-private move slices (one or two bulk
+    copies per lane).  Several tiles per warp, so both move buffers and their barriers' phases are reused;
+    a ragged tail; rows that come back to solved."""
+    rng = np.random.RandomState(depth + 1000 * size)
+    n = 148 * 32 * 64 * 3 + 77
+    moves = rng.randint(T.N_ACTIONS[size], size=(n, depth)).astype(np.uint8)
+    h = depth // 2
+    back = rng.choice(n, 500, replace=False)
+    moves[back, h:] = moves[back, :h][:, ::-1] ^ 1
+    counters = ops.new_counters(dev())
+    states, solved, reward = ops.scramble(size, cu(moves), counters=counters)
+    want, want_solved, want_reward, cnt = C.scramble(size, moves)
+    assert (states.cpu().numpy() == want).all()
+    assert (solved.cpu().numpy().astype(bool) == want_solved).all()
+    assert (reward.cpu().numpy() == want_reward).all()
+    assert counters.tolist()[:2] == [cnt, n] and want_solved[back].all()
+
+
+@pytest.mark.parametrize("size", SIZES)
 @pytest.mark.parametrize("n", (1, 2, 255, 256, 257, 513, 100003))
 def test_scramble_ragged_sizes(size, n):
     rng = np.random.RandomState(n)

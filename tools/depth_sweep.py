@@ -11,7 +11,7 @@ from rubiks_cube_solver_b200 import ops
 dev = torch.device("cuda", 0)
 for size, a, n in ((3, 12, 4 << 20), (2, 6, 8 << 20)):
     s = ops.N_STICKERS[size]
-    for depth in (1, 2, 7, 10, 19, 20, 21, 29, 30, 31, 32, 48, 64, 96, 97, 128, 200):
+    for depth in (1, 2, 7, 8, 10, 16, 19, 20, 21, 24, 29, 30, 31, 32, 40, 48, 64, 96, 97, 128, 200):
         moves = torch.randint(0, a, (n, depth), dtype=torch.uint8, device=dev)
         st = torch.empty((n, s), dtype=torch.uint8, device=dev)
         so = torch.empty(n, dtype=torch.uint8, device=dev)
