@@ -262,18 +262,28 @@ CUBE_HD void scramble_pairs_run(CubieState (&st)[NS], const int (&rows)[NS], int
     }
     auto word = [&](int j) {
         uint32_t y[NS];
-        static_assert(NS <= 2, "static shifts are written out for two instances per lane");
-        {
-            constexpr int s0 = (NS == 2) ? pair_static_shift<SIZE, DEPTH>(0) : -1;
-            const uint32_t hi = (s0 == 0) ? 0u : mw[wi[0] + j + 1];
-            y[0] = pair_rows_word<s0>(lo[0], hi, sh[0], bias);                  // bytes 1, 3 = pair rows
-            lo[0] = (s0 == 0) ? mw[wi[0] + j + 1] : hi;
-        }
-        if (NS == 2) {
-            constexpr int s1 = pair_static_shift<SIZE, DEPTH>(1);
-            const uint32_t hi = (s1 == 0) ? 0u : mw[wi[NS - 1] + j + 1];
-            y[NS - 1] = pair_rows_word<s1>(lo[NS - 1], hi, sh[NS - 1], bias);
-            lo[NS - 1] = (s1 == 0) ? mw[wi[NS - 1] + j + 1] : hi;
+        static_assert(SIZE == 2 || NS <= 2, "3x3x3: static shifts are written out for two instances per lane");
+        if (SIZE == 3 || NS <= 2) {
+            {
+                constexpr int s0 = (NS == 2) ? pair_static_shift<SIZE, DEPTH>(0) : -1;
+                const uint32_t hi = (s0 == 0) ? 0u : mw[wi[0] + j + 1];
+                y[0] = pair_rows_word<s0>(lo[0], hi, sh[0], bias);                  // bytes 1, 3 = pair rows
+                lo[0] = (s0 == 0) ? mw[wi[0] + j + 1] : hi;
+            }
+            if (NS == 2) {
+                constexpr int s1 = pair_static_shift<SIZE, DEPTH>(1);
+                const uint32_t hi = (s1 == 0) ? 0u : mw[wi[NS - 1] + j + 1];
+                y[NS - 1] = pair_rows_word<s1>(lo[NS - 1], hi, sh[NS - 1], bias);
+                lo[NS - 1] = (s1 == 0) ? mw[wi[NS - 1] + j + 1] : hi;
+            }
+        } else {
+            constexpr int s = pair_static_shift<2, DEPTH>(0);                       // 2x2x2: the same for every row
+#pragma unroll
+            for (int k = 0; k < NS; ++k) {
+                const uint32_t hi = (s == 0) ? 0u : mw[wi[k] + j + 1];
+                y[k] = pair_rows_word<s>(lo[k], hi, sh[k], bias);
+                lo[k] = (s == 0) ? mw[wi[k] + j + 1] : hi;
+            }
         }
 #pragma unroll
         for (int k = 0; k < NS; ++k) pair_apply<SIZE>(st[k], tbl, cube_prmt(y[k], lanereg, 0x5514u), roff);
@@ -328,7 +338,7 @@ CUBE_HD void scramble_pairs_run(CubieState (&st)[NS], const int (&rows)[NS], int
 // moves are then read sixteen at a time with 128-bit loads; the eight lanes of a quarter warp, 2*depth
 // bytes apart, fall into (nearly always) eight different bank groups.  `tile` is the buffer (1024-byte
 // aligned in the shared window), `lane` the lane: 3x3x3 rows 2l, 2l+1 are the contiguous slice at
-// lane * 2 * depth, 2x2x2 rows l, l+32 sit at lane * depth and (lane + 32) * depth.  A group of four words
+// lane * 2 * depth, 2x2x2 rows l + 32k sit at (lane + 32k) * depth.  A group of four words
 // adds <= 16 to a twist field and the fold after it leaves <= 10, so a field never exceeds 26.
 CUBE_HD uint32_t cube_swz128(uint32_t f) { return f ^ ((f >> 3) & 0x70u); }
 
@@ -338,9 +348,11 @@ CUBE_HD void scramble_pairs_run_swizzled(CubieState (&st)[NS], const uint8_t* ti
 {
     const uint32_t bias = tbl.bias();
     constexpr uint32_t K = (uint32_t)(CUBE_PAIR_BASE + 256);
-    static_assert(NS == 2, "two rows per lane");
-    auto word = [&](uint32_t w0, uint32_t w1) {
-        const uint32_t y[2] = {w0 * K + bias, w1 * K + bias};
+    static_assert(SIZE == 2 || NS == 2, "3x3x3: two rows per lane");
+    auto word = [&](const uint32_t (&w)[NS]) {
+        uint32_t y[NS];
+#pragma unroll
+        for (int k = 0; k < NS; ++k) y[k] = w[k] * K + bias;
 #pragma unroll
         for (int k = 0; k < NS; ++k) pair_apply<SIZE>(st[k], tbl, cube_prmt(y[k], lanereg, 0x5514u), roff);
 #pragma unroll
@@ -362,27 +374,44 @@ CUBE_HD void scramble_pairs_run_swizzled(CubieState (&st)[NS], const uint8_t* ti
         const uint32_t f0 = (uint32_t)(lane * 2 * depth);
         CubeVec4 p = unit(f0 + 16 * a);
         const uint32_t last0[2] = {p.x, p.y};
+        auto word2 = [&](uint32_t w0, uint32_t w1) {
+            uint32_t w[NS];
+            w[0] = w0; w[NS - 1] = w1;
+            word(w);
+        };
         for (int g = 0; g < a; ++g) {
             const CubeVec4 v = unit(f0 + 16 * g), q = unit(f0 + 16 * (a + g + 1));
-            word(v.x, p.z);
-            word(v.y, p.w);
-            word(v.z, q.x);
-            word(v.w, q.y);
+            word2(v.x, p.z);
+            word2(v.y, p.w);
+            word2(v.z, q.x);
+            word2(v.w, q.y);
             p = q;
             fold();
         }
-        word(last0[0], p.z);
-        word(last0[1], p.w);
+        word2(last0[0], p.z);
+        word2(last0[1], p.w);
         return;
     }
-    const uint32_t f0 = (uint32_t)((SIZE == 3 ? 2 * lane : lane) * depth);
-    const uint32_t f1 = (uint32_t)((SIZE == 3 ? 2 * lane + 1 : lane + 32) * depth);
+    uint32_t f[NS];
+#pragma unroll
+    for (int k = 0; k < NS; ++k) f[k] = (uint32_t)((SIZE == 3 ? 2 * lane + k : lane + 32 * k) * depth);
     for (int g = 0; g < depth; g += 16) {                // rows 16-byte aligned (depth % 16 == 0)
-        const CubeVec4 v = unit(f0 + g), q = unit(f1 + g);
-        word(v.x, q.x);
-        word(v.y, q.y);
-        word(v.z, q.z);
-        word(v.w, q.w);
+        CubeVec4 v[NS];
+#pragma unroll
+        for (int k = 0; k < NS; ++k) v[k] = unit(f[k] + g);
+        uint32_t w[NS];
+#pragma unroll
+        for (int k = 0; k < NS; ++k) w[k] = v[k].x;
+        word(w);
+#pragma unroll
+        for (int k = 0; k < NS; ++k) w[k] = v[k].y;
+        word(w);
+#pragma unroll
+        for (int k = 0; k < NS; ++k) w[k] = v[k].z;
+        word(w);
+#pragma unroll
+        for (int k = 0; k < NS; ++k) w[k] = v[k].w;
+        word(w);
         fold();
     }
 }

@@ -152,21 +152,27 @@ scramble_tile_kernel(const uint8_t* __restrict__ moves, long long n, long long t
 // parity (54-byte rows alternate between word-aligned and two bytes off); the 64 sticker rows are
 // assembled in the warp's output tile and leave by one bulk store.  The 43 KB table is loaded once
 // per CTA.  A tile of 64 rows keeps every bulk copy a multiple of 16 bytes for any depth.
-constexpr int kPairTile = 64;
 constexpr int kMaxPairDepth = 96;
 constexpr int kPairTableBytes = CUBE_PAIR_ROWS * 256;
-template <int SIZE> struct PairCfg;
-template <> struct PairCfg<3> { static constexpr int kMaxWarps = 24; };    // 768 threads: 85 registers each
-template <> struct PairCfg<2> { static constexpr int kMaxWarps = 32; };
+// kNS instances per lane in lockstep = tiles of 32 * kNS rows.  2x2x2 (two state registers per instance)
+// walks four: the per-tile work (claim, staging, barrier, stores, verdict words) is ~150 instructions per
+// lane, a quarter of that kernel's instruction count with two.
+// (Chosen for shallow sequences only: the 128-row tiles of a deep one leave room for too few warps.)
+template <int SIZE, int NS> struct PairCfg;
+template <> struct PairCfg<3, 2> { static constexpr int kMaxWarps = 24; };    // 768 threads: 85 registers each
+template <> struct PairCfg<2, 2> { static constexpr int kMaxWarps = 32; };
+template <> struct PairCfg<2, 4> { static constexpr int kMaxWarps = 20; };    // 640 threads: 102 registers each
+constexpr int kMinWarpsFour = 16;         // 2x2x2 walks four instances per lane when at least this many warps fit
 
-template <int SIZE>
+template <int SIZE, int NS>
 struct PairSmem {
     using G = CubeGeom<SIZE>;
+    static constexpr int kPairTile = 32 * NS;
     static constexpr int kTable = 0;                                  // + up to 255 bytes: 256-byte aligned in the window
     static constexpr int kCornerLut = kPairTableBytes + 256;          // (relative to the aligned table start: + 0)
     static constexpr int kEdgeLut = kCornerLut + 256;
     static constexpr int kPerWarp = kEdgeLut + 256;
-    static constexpr int kOutBytes = kPairTile * G::S;                // 3456 / 1536: multiples of 16
+    static constexpr int kOutBytes = kPairTile * G::S;                // 3456 / 3072: multiples of 16
     // flat tile image (+16: the last row's word loads run past it), or the swizzled tile (`swz`: the copy
     // engine's 128-byte swizzle wants 1024-byte aligned buffers)
     __host__ __device__ static constexpr int round1k(int x) { return (x + 1023) & ~1023; }
@@ -187,13 +193,14 @@ struct PairSmem {
     }
 };
 
-template <int SIZE, int DEPTH>
-__global__ void __launch_bounds__(PairCfg<SIZE>::kMaxWarps * 32, 1)
+template <int SIZE, int DEPTH, int NS>
+__global__ void __launch_bounds__(PairCfg<SIZE, NS>::kMaxWarps * 32, 1)
 scramble_pairs_kernel(const uint8_t* __restrict__ moves, int n_tiles, int depth_rt, uint8_t* __restrict__ out,
                       uint8_t* __restrict__ solved, float* __restrict__ reward, unsigned long long* __restrict__ counters,
                       sched::Slot* slot, int tail_div, const __grid_constant__ CUtensorMap move_map)
 {
-    using L = PairSmem<SIZE>;
+    using L = PairSmem<SIZE, NS>;
+    constexpr int kPairTile = L::kPairTile;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int depth = DEPTH > 0 ? DEPTH : depth_rt;
     // DEPTH < 0: any depth that is a multiple of 8 (3x3x3) / 16 (2x2x2), staged as a swizzled tile through
@@ -220,7 +227,7 @@ scramble_pairs_kernel(const uint8_t* __restrict__ moves, int n_tiles, int depth_
         if (lane == 0) {
             bulk::mbar_expect_tx(&s_bar[b], move_bytes);
             if (!kPriv) bulk::load(s_moves + b * mstride, moves + (long long)t * move_bytes, move_bytes, &s_bar[b]);
-            else bulk::load_tile_2d(s_moves + b * mstride, &move_map, 0, t * (depth >> 1), &s_bar[b]);
+            else bulk::load_tile_2d(s_moves + b * mstride, &move_map, 0, t * (kPairTile * depth >> 7), &s_bar[b]);
         }
     };
 
@@ -240,7 +247,9 @@ scramble_pairs_kernel(const uint8_t* __restrict__ moves, int n_tiles, int depth_
     tiles.init(slot, n_tiles, (int)(blockDim.x >> 5), warp, lane, tail_div);
     int tile = tiles.pop(lane);
     if (tile < n_tiles) stage(tile, 0);
-    const int rows[2] = {(SIZE == 3) ? 2 * lane : lane, (SIZE == 3) ? 2 * lane + 1 : lane + 32};
+    int rows[NS];
+#pragma unroll
+    for (int k = 0; k < NS; ++k) rows[k] = (SIZE == 3) ? 2 * lane + k : lane + 32 * k;
     const uint32_t lanereg = pair_lanereg<SIZE>(lane), roff = pair_roff2(lane);
     const ColourLutShared lut{bulk::smem_addr(s_clut), bulk::smem_addr(s_elut)};
     unsigned n_solved = 0;
@@ -251,17 +260,21 @@ scramble_pairs_kernel(const uint8_t* __restrict__ moves, int n_tiles, int depth_
         if (next < n_tiles) stage(next, buf ^ 1);                     // prefetch the next tile's moves
         bulk::mbar_wait(&s_bar[buf], (uint32_t)(it >> 1) & 1u);
 
-        CubieState st[2];
-        cubie_init(st[0]);
-        cubie_init(st[1]);
-        if (kPriv) scramble_pairs_run_swizzled<SIZE, 2>(st, s_moves + buf * mstride, lane, depth, tbl, lanereg, roff);
-        else scramble_pairs_run<SIZE, (DEPTH > 0 ? DEPTH : 0), 2>(st, rows, depth, s_moves + buf * mstride, tbl, lanereg, roff);
+        CubieState st[NS];
+#pragma unroll
+        for (int k = 0; k < NS; ++k) cubie_init(st[k]);
+        if (kPriv) scramble_pairs_run_swizzled<SIZE, NS>(st, s_moves + buf * mstride, lane, depth, tbl, lanereg, roff);
+        else scramble_pairs_run<SIZE, (DEPTH > 0 ? DEPTH : 0), NS>(st, rows, depth, s_moves + buf * mstride, tbl, lanereg, roff);
         if (lane == 0) bulk::wait_read_all();                         // the previous store has released the out tile
         __syncwarp();
-        const bool ok0 = scramble_pairs_finish<SIZE>(st[0], rows[0], lut, s_out);
-        const bool ok1 = scramble_pairs_finish<SIZE>(st[1], rows[1], lut, s_out);
-        const unsigned m0 = __ballot_sync(0xffffffffu, ok0), m1 = __ballot_sync(0xffffffffu, ok1);
-        n_solved += (unsigned)(__popc(m0) + __popc(m1));
+        uint32_t m[NS];
+        bool ok[NS];
+#pragma unroll
+        for (int k = 0; k < NS; ++k) {
+            ok[k] = scramble_pairs_finish<SIZE>(st[k], rows[k], lut, s_out);
+            m[k] = __ballot_sync(0xffffffffu, ok[k]);
+            n_solved += (unsigned)__popc(m[k]);
+        }
 
         bulk::fence_smem_writes();                                    // rows -> visible to the copy engine
         __syncwarp();
@@ -269,14 +282,22 @@ scramble_pairs_kernel(const uint8_t* __restrict__ moves, int n_tiles, int depth_
             bulk::store(out + (long long)tile * L::kOutBytes, s_out, (uint32_t)L::kOutBytes);
             bulk::commit();
         }
-        // verdicts leave coalesced: 64 solved bytes (lanes 0-15) and 64 rewards
-        if (solved && lane < 16)
-            reinterpret_cast<uint32_t*>(solved + (long long)tile * kPairTile)[lane] = pair_solved_word<SIZE>(m0, m1, lane);
-        if (reward) {
-            float2 v;
-            v.x = pair_row_bit<SIZE>(m0, m1, 2 * lane) ? 1.0f : -1.0f;
-            v.y = pair_row_bit<SIZE>(m0, m1, 2 * lane + 1) ? 1.0f : -1.0f;
-            reinterpret_cast<float2*>(reward + (long long)tile * kPairTile)[lane] = v;
+        // verdicts leave coalesced: one solved byte and one reward per row
+        if (SIZE == 3) {                                              // rows 2l, 2l+1: words built from the two ballots
+            if (solved && lane < 16)
+                reinterpret_cast<uint32_t*>(solved + (long long)tile * kPairTile)[lane] = pair_solved_word<SIZE>(m[0], m[NS - 1], lane);
+            if (reward) {
+                float2 v;
+                v.x = pair_row_bit<SIZE>(m[0], m[NS - 1], 2 * lane) ? 1.0f : -1.0f;
+                v.y = pair_row_bit<SIZE>(m[0], m[NS - 1], 2 * lane + 1) ? 1.0f : -1.0f;
+                reinterpret_cast<float2*>(reward + (long long)tile * kPairTile)[lane] = v;
+            }
+        } else {                                                      // rows l + 32k: the lane's own verdicts, 32 in a row
+#pragma unroll
+            for (int k = 0; k < NS; ++k) {
+                if (solved) solved[(long long)tile * kPairTile + 32 * k + lane] = ok[k] ? 1 : 0;
+                if (reward) reward[(long long)tile * kPairTile + 32 * k + lane] = ok[k] ? 1.0f : -1.0f;
+            }
         }
         tile = next;
     }
@@ -377,13 +398,13 @@ int launch_classic(const uint8_t* moves, long long n, int depth, uint8_t* out, u
 constexpr int kSmemLimit = 227 * 1024;
 
 // Tensor map of a move array for the swizzled tiles of K1p: the bytes as rows of 128, a box = one tile of
-// 64 move rows (depth / 2 rows of 128 bytes), 128-byte swizzle on the shared-memory side.  The encoder is a
+// 64 / 128 move rows (`tile_rows` = tile * depth / 128 rows of 128 bytes), 128-byte swizzle on the shared-memory side.  The encoder is a
 // driver entry point, fetched through the runtime so that the library does not link libcuda.
 using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-bool encode_move_map(CUtensorMap* map, const uint8_t* moves, long long n_tiles, int depth)
+bool encode_move_map(CUtensorMap* map, const uint8_t* moves, long long n_tiles, int tile_rows)
 {
     static const EncodeTiledFn encode = [] {
         void* p = nullptr;
@@ -395,74 +416,92 @@ bool encode_move_map(CUtensorMap* map, const uint8_t* moves, long long n_tiles, 
         return reinterpret_cast<EncodeTiledFn>(p);
     }();
     if (!encode) return false;
-    const cuuint64_t dims[2] = {128, (cuuint64_t)(n_tiles * (depth / 2))};
+    const cuuint64_t dims[2] = {128, (cuuint64_t)(n_tiles * tile_rows)};
     const cuuint64_t strides[1] = {128};
-    const cuuint32_t box[2] = {128, (cuuint32_t)(depth / 2)};
+    const cuuint32_t box[2] = {128, (cuuint32_t)tile_rows};
     const cuuint32_t elem[2] = {1, 1};
     return encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(moves), dims, strides, box, elem,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// K1p on the whole tiles of a batch with NS instances per lane.  Returns the number of instances handled
+// (a multiple of 32 * NS; 0 = not applicable: fewer than `min_warps` warps fit, too few rows), or -cudaError.
+template <int SIZE, int NS>
+long long launch_pairs(const uint8_t* moves, long long n, int depth, uint8_t* out, uint8_t* solved, float* reward,
+                       unsigned long long* counters, cudaStream_t stream, int min_warps)
+{
+    using L = PairSmem<SIZE, NS>;
+    constexpr int kPairTile = L::kPairTile;
+    if (n < kPairTile) return 0;
+    // depths whose flat row stride bank-conflicts on the move words are staged as swizzled tiles
+    static const bool swz_ok = !(getenv("CUBE_PAIR_SWIZZLE") && getenv("CUBE_PAIR_SWIZZLE")[0] == '0');
+    static_assert(L::kPerWarp % 1024 == 0, "the per-warp areas of the swizzled variant start on 1 KB");
+    long long n_tiles = n / kPairTile;
+    if (n_tiles > 0x3fffffff) n_tiles = 0x3fffffff;                   // 32-bit tile counters; the caller handles the rest
+    const int tile_rows = kPairTile * depth / 128;                    // of the tensor map, when swizzled
+    bool priv = swz_ok && depth % (SIZE == 3 ? 8 : 16) == 0 && n_tiles * tile_rows < 0x7fffffffLL;
+    auto warps_for = [&](bool p) {
+        int w = (kSmemLimit - (p ? 1024 : 256) - L::kPerWarp) / L::per_warp(depth, p);
+        if (w > PairCfg<SIZE, NS>::kMaxWarps) w = PairCfg<SIZE, NS>::kMaxWarps;
+        return w & ~3;                                                // the same number on every scheduler
+    };
+    if (warps_for(priv) < min_warps) return 0;
+    alignas(64) CUtensorMap move_map;
+    memset(&move_map, 0, sizeof(move_map));
+    if (priv && !encode_move_map(&move_map, moves, n_tiles, tile_rows)) priv = false;
+    const int slack = priv ? 1024 : 256;                              // alignment of the carve-up in the window
+    const int warps = warps_for(priv);
+    if (warps < min_warps) return 0;
+    const int smem = L::bytes(depth, warps, priv) + slack;
+    // straight-line specialisations: the reference's default depth (config.yaml:7) and BASELINE config 2's
+    auto kern = depth == 30 ? scramble_pairs_kernel<SIZE, 30, NS>
+              : depth == 20 ? scramble_pairs_kernel<SIZE, 20, NS>
+              : priv ? scramble_pairs_kernel<SIZE, -1, NS> : scramble_pairs_kernel<SIZE, 0, NS>;
+    static int configured_smem[64][4];
+    static bool init_done = false;
+    if (!init_done) { for (int i = 0; i < 64; ++i) for (int j = 0; j < 4; ++j) configured_smem[i][j] = -1; init_done = true; }
+    int& cfg = configured_smem[cube::device_slot()][depth == 30 ? 1 : depth == 20 ? 2 : priv ? 3 : 0];
+    if (smem > cfg) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return -(long long)e;
+        cfg = smem;
+    }
+    long long grid = (n_tiles + warps - 1) / warps;
+    if (grid > cube::persistent_ctas()) grid = cube::persistent_ctas();
+    sched::Slot* slot = sched::claim_slot();
+    if (!slot) return -(long long)cudaErrorUnknown;
+    cudaLaunchConfig_t cfg_l = {};
+    cfg_l.gridDim = dim3((unsigned)grid);
+    cfg_l.blockDim = dim3((unsigned)(warps * 32));
+    cfg_l.dynamicSmemBytes = (size_t)smem;
+    cfg_l.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    static const bool pdl = !(getenv("CUBE_PDL") && getenv("CUBE_PDL")[0] == '0');
+    cfg_l.attrs = attr;
+    cfg_l.numAttrs = pdl ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg_l, kern, moves, (int)n_tiles, depth, out, solved, reward, counters, slot,
+                                       sched::tail_div(), move_map);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) return -(long long)e;
+    return n_tiles * kPairTile;
+}
+
 template <int SIZE>
 int launch_one(const uint8_t* moves, long long n, int depth, uint8_t* out, uint8_t* solved, float* reward,
                unsigned long long* counters, cudaStream_t stream)
 {
-    using L = PairSmem<SIZE>;
     using G = CubeGeom<SIZE>;
     long long done = 0;
     static const char* const force = getenv("CUBE_SCRAMBLE_CLASSIC");               // A/B switch for profiling
-    if (depth >= 1 && depth <= kMaxPairDepth && n >= kPairTile && !(force && force[0] == '1')) {
-        // depths whose flat row stride bank-conflicts on the move words are staged as swizzled tiles
-        static const bool swz_ok = !(getenv("CUBE_PAIR_SWIZZLE") && getenv("CUBE_PAIR_SWIZZLE")[0] == '0');
-        static_assert(L::kPerWarp % 1024 == 0, "the per-warp areas of the swizzled variant start on 1 KB");
-        alignas(64) CUtensorMap move_map;
-        memset(&move_map, 0, sizeof(move_map));
-        long long tiles_all = n / kPairTile;
-        if (tiles_all > 0x3fffffff) tiles_all = 0x3fffffff;           // 32-bit tile counters; the rest goes below
-        const bool priv = swz_ok && depth % (SIZE == 3 ? 8 : 16) == 0 && tiles_all * (depth / 2) < 0x7fffffffLL &&
-                          encode_move_map(&move_map, moves, tiles_all, depth);
-        const int slack = priv ? 1024 : 256;                          // alignment of the carve-up in the window
-        int warps = (kSmemLimit - slack - L::kPerWarp) / L::per_warp(depth, priv);
-        if (warps > PairCfg<SIZE>::kMaxWarps) warps = PairCfg<SIZE>::kMaxWarps;
-        warps &= ~3;                                                   // the same number on every scheduler
-        if (warps >= 4) {
-            const long long n_tiles = tiles_all;
-            const int smem = L::bytes(depth, warps, priv) + slack;
-            // straight-line specialisations: the reference's default depth (config.yaml:7) and BASELINE config 2's
-            auto kern = depth == 30 ? scramble_pairs_kernel<SIZE, 30>
-                      : depth == 20 ? scramble_pairs_kernel<SIZE, 20>
-                      : priv ? scramble_pairs_kernel<SIZE, -1> : scramble_pairs_kernel<SIZE, 0>;
-            static int configured_smem[64][4];
-            static bool init_done = false;
-            if (!init_done) { for (int i = 0; i < 64; ++i) for (int j = 0; j < 4; ++j) configured_smem[i][j] = -1; init_done = true; }
-            int& cfg = configured_smem[cube::device_slot()][depth == 30 ? 1 : depth == 20 ? 2 : priv ? 3 : 0];
-            if (smem > cfg) {
-                cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-                if (e != cudaSuccess) return (int)e;
-                cfg = smem;
-            }
-            long long grid = (n_tiles + warps - 1) / warps;
-            if (grid > cube::persistent_ctas()) grid = cube::persistent_ctas();
-            sched::Slot* slot = sched::claim_slot();
-            if (!slot) return (int)cudaErrorUnknown;
-            cudaLaunchConfig_t cfg_l = {};
-            cfg_l.gridDim = dim3((unsigned)grid);
-            cfg_l.blockDim = dim3((unsigned)(warps * 32));
-            cfg_l.dynamicSmemBytes = (size_t)smem;
-            cfg_l.stream = stream;
-            cudaLaunchAttribute attr[1];
-            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-            attr[0].val.programmaticStreamSerializationAllowed = 1;
-            static const bool pdl = !(getenv("CUBE_PDL") && getenv("CUBE_PDL")[0] == '0');
-            cfg_l.attrs = attr;
-            cfg_l.numAttrs = pdl ? 1 : 0;
-            cudaError_t e = cudaLaunchKernelEx(&cfg_l, kern, moves, (int)n_tiles, depth, out, solved, reward, counters, slot,
-                                               sched::tail_div(), move_map);
-            if (e == cudaSuccess) e = cudaGetLastError();
-            if (e != cudaSuccess) return (int)e;
-            done = n_tiles * kPairTile;
-        }
+    static const bool four_ok = !(getenv("CUBE_PAIR_FOUR") && getenv("CUBE_PAIR_FOUR")[0] == '0');
+    if (depth >= 1 && depth <= kMaxPairDepth && !(force && force[0] == '1')) {
+        if (SIZE == 2 && four_ok)
+            done = launch_pairs<2, 4>(moves, n, depth, out, solved, reward, counters, stream, kMinWarpsFour);
+        if (done == 0) done = launch_pairs<SIZE, 2>(moves, n, depth, out, solved, reward, counters, stream, 4);
+        if (done < 0) return (int)-done;
     }
     if (done == n) return 0;
     return launch_classic<SIZE>(moves + done * depth, n - done, depth, out + done * G::S, solved ? solved + done : nullptr,

@@ -33,46 +33,55 @@ void scramble_t(const uint8_t* moves, long long n, int depth, uint8_t* out, uint
     }
 }
 
-// K1p: persistent pair-table kernel, one 64-row tile at a time with the kernel's lane -> row map
-template <int SIZE>
+// K1p: persistent pair-table kernel, one tile of 32 * NS rows at a time with the kernel's lane -> row map
+// (rows beyond the last whole tile are left untouched: the library hands them to the tile-per-CTA kernel)
+template <int SIZE, int NS>
 void scramble_pairs_t(const uint8_t* moves, long long n, int depth, uint8_t* out, uint8_t* solved, bool fixed, bool priv)
 {
     using G = CubeGeom<SIZE>;
+    constexpr int T = 32 * NS;
     const uint32_t* clut = SIZE == 3 ? kCornerColour3 : kCornerColour2;
     std::vector<uint8_t> tbl(65792 + 256, 0xa5);
     uint8_t* s_ptbl_mem = tbl.data() + ((16 - (reinterpret_cast<uintptr_t>(tbl.data()) & 15)) & 15);
     for (int t = 0; t < 96; ++t) pair_table_fill<SIZE>(s_ptbl_mem, t, 96);
-    std::vector<uint8_t> s_moves(64 * depth + 16), s_out(64 * G::S);
-    std::vector<uint8_t> s_priv(64 * depth + 16);
-    for (long long base = 0; base + 64 <= n; base += 64) {
+    std::vector<uint8_t> s_moves(T * depth + 16), s_out(T * G::S);
+    std::vector<uint8_t> s_priv(T * depth + 16);
+    for (long long base = 0; base + T <= n; base += T) {
         std::memset(s_moves.data(), 0xee, s_moves.size());
-        std::memcpy(s_moves.data(), moves + base * depth, (size_t)64 * depth);
+        std::memcpy(s_moves.data(), moves + base * depth, (size_t)T * depth);
         if (priv) {                                                  // the copy engine's 128-byte swizzle
             std::memset(s_priv.data(), 0xee, s_priv.size());
-            for (int f = 0; f < 64 * depth; f += 16)
+            for (int f = 0; f < T * depth; f += 16)
                 std::memcpy(s_priv.data() + cube_swz128((uint32_t)f), moves + base * depth + f, 16);
         }
-        uint32_t ok[2] = {0, 0};
-        for (int lane = 0; lane < 32; ++lane) {                      // one lane = two rows in lockstep
-            const int rows[2] = {(SIZE == 3) ? 2 * lane : lane, (SIZE == 3) ? 2 * lane + 1 : lane + 32};
-            CubieState st[2];
-            cubie_init(st[0]);
-            cubie_init(st[1]);
+        uint32_t ok[NS] = {};
+        for (int lane = 0; lane < 32; ++lane) {                      // one lane = NS rows in lockstep
+            int rows[NS];
+            CubieState st[NS];
+            for (int k = 0; k < NS; ++k) {
+                rows[k] = (SIZE == 3) ? 2 * lane + k : lane + 32 * k;
+                cubie_init(st[k]);
+            }
             const uint32_t lr = pair_lanereg<SIZE>(lane);
             const PairTableHost s_ptbl{s_ptbl_mem};
-            if (priv) scramble_pairs_run_swizzled<SIZE, 2>(st, s_priv.data(), lane, depth, s_ptbl, lr, pair_roff2(lane));
-            else if (fixed && depth == 30) scramble_pairs_run<SIZE, 30, 2>(st, rows, depth, s_moves.data(), s_ptbl, lr, pair_roff2(lane));
-            else if (fixed && depth == 20) scramble_pairs_run<SIZE, 20, 2>(st, rows, depth, s_moves.data(), s_ptbl, lr, pair_roff2(lane));
-            else if (fixed && depth == 43) scramble_pairs_run<SIZE, 43, 2>(st, rows, depth, s_moves.data(), s_ptbl, lr, pair_roff2(lane));
-            else scramble_pairs_run<SIZE, 0, 2>(st, rows, depth, s_moves.data(), s_ptbl, lr, pair_roff2(lane));
-            for (int k = 0; k < 2; ++k)
+            if (priv) scramble_pairs_run_swizzled<SIZE, NS>(st, s_priv.data(), lane, depth, s_ptbl, lr, pair_roff2(lane));
+            else if (fixed && depth == 30) scramble_pairs_run<SIZE, 30, NS>(st, rows, depth, s_moves.data(), s_ptbl, lr, pair_roff2(lane));
+            else if (fixed && depth == 20) scramble_pairs_run<SIZE, 20, NS>(st, rows, depth, s_moves.data(), s_ptbl, lr, pair_roff2(lane));
+            else if (fixed && depth == 43) scramble_pairs_run<SIZE, 43, NS>(st, rows, depth, s_moves.data(), s_ptbl, lr, pair_roff2(lane));
+            else scramble_pairs_run<SIZE, 0, NS>(st, rows, depth, s_moves.data(), s_ptbl, lr, pair_roff2(lane));
+            for (int k = 0; k < NS; ++k)
                 ok[k] |= (uint32_t)scramble_pairs_finish<SIZE>(st[k], rows[k], ColourLutHost{clut, kEdgeColour3}, s_out.data()) << lane;
         }
-        for (int k = 0; k < 16; ++k) {                               // the kernel's verdict exchange
-            const uint32_t w = pair_solved_word<SIZE>(ok[0], ok[1], k);
-            std::memcpy(solved + base + 4 * k, &w, 4);
+        if (SIZE == 3) {
+            for (int k = 0; k < T / 4; ++k) {                        // the kernel's verdict exchange
+                const uint32_t w = pair_solved_word<SIZE>(ok[0], ok[NS - 1], k);
+                std::memcpy(solved + base + 4 * k, &w, 4);
+            }
+        } else {
+            for (int k = 0; k < NS; ++k)
+                for (int lane = 0; lane < 32; ++lane) solved[base + 32 * k + lane] = (ok[k] >> lane) & 1u;
         }
-        std::memcpy(out + base * G::S, s_out.data(), (size_t)64 * G::S);
+        std::memcpy(out + base * G::S, s_out.data(), (size_t)T * G::S);
     }
 }
 
@@ -199,13 +208,15 @@ void emul_scramble(int size, const uint8_t* moves, long long n, int depth, uint8
 {
     if (size == 3) scramble_t<3>(moves, n, depth, out, solved); else scramble_t<2>(moves, n, depth, out, solved);
 }
-// fixed == 1: use the compile-time-depth instantiation when one exists (30, 20; 43 only here, to
-// exercise the unrolled fold schedule); fixed == 2: the swizzled move tile (depth % 8 == 0 for
-// 3x3x3, % 16 == 0 for 2x2x2)
+// fixed & 3 == 1: use the compile-time-depth instantiation when one exists (30, 20; 43 only here, to
+// exercise the unrolled fold schedule); == 2: the swizzled move tile (depth % 8 == 0 for 3x3x3,
+// % 16 == 0 for 2x2x2); fixed & 4: four instances per lane, 128-row tiles (2x2x2 only)
 void emul_scramble_pairs(int size, const uint8_t* moves, long long n, int depth, uint8_t* out, uint8_t* solved, int fixed)
 {
-    if (size == 3) scramble_pairs_t<3>(moves, n, depth, out, solved, fixed == 1, fixed == 2);
-    else scramble_pairs_t<2>(moves, n, depth, out, solved, fixed == 1, fixed == 2);
+    const bool fix = (fixed & 3) == 1, swz = (fixed & 3) == 2;
+    if (size == 3) scramble_pairs_t<3, 2>(moves, n, depth, out, solved, fix, swz);
+    else if (fixed & 4) scramble_pairs_t<2, 4>(moves, n, depth, out, solved, fix, swz);
+    else scramble_pairs_t<2, 2>(moves, n, depth, out, solved, fix, swz);
 }
 void emul_walk(int size, const uint8_t* in, const uint8_t* moves, long long n, int depth, uint8_t* out,
                uint8_t* solved)

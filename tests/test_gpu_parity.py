@@ -155,10 +155,12 @@ def test_scramble_ragged_sizes(size, n):
 
 @pytest.mark.parametrize("size", SIZES)
 @pytest.mark.parametrize("n,depth", [(n, d) for n in (63, 64, 65, 129) for d in (2, 95, 96, 97)]
-                         + [(64 * 148 * 24 + 1, 30), (64 * 148 * 32 + 65, 20)])
+                         + [(n, d) for n in (127, 128, 191, 257) for d in (1, 20, 30, 31, 32, 33)]
+                         + [(64 * 148 * 24 + 1, 30), (64 * 148 * 32 + 65, 20), (128 * 148 * 20 * 3 + 127, 20)])
 def test_scramble_tile_and_depth_boundaries(size, n, depth):
-    """K1p handles whole 64-row tiles at depth 1..96; the single-move kernels take the ragged tail,
-    deeper sequences and everything around: the seams must not show."""
+    """K1p handles whole tiles (64 rows; 128 for shallow 2x2x2 sequences, four instances per lane) at depth
+    1..96; the single-move kernels take the ragged tail, deeper sequences and everything around: the
+    seams must not show."""
     rng = np.random.RandomState(n % 1000 + depth)
     moves = rng.randint(T.N_ACTIONS[size], size=(n, depth)).astype(np.uint8)
     if depth % 2 == 0:

@@ -61,15 +61,19 @@ def test_scramble_emulation(emul, size, depth):
 @pytest.mark.parametrize("size", (2, 3))
 @pytest.mark.parametrize("depth,fixed", [(d, 0) for d in (1, 2, 3, 4, 5, 7, 8, 9, 20, 30, 31, 32, 43, 61, 96)]
                          + [(20, 1), (30, 1), (43, 1)]
-                         + [(d, 2) for d in (8, 16, 24, 32, 48, 64, 72, 96)])
+                         + [(d, 2) for d in (8, 16, 24, 32, 48, 64, 72, 96)]
+                         + [(d, 4) for d in (1, 2, 3, 5, 8, 9, 19, 21, 30, 31)] + [(20, 5), (30, 5), (16, 6), (32, 6)])
 def test_scramble_pairs_emulation(emul, size, depth, fixed):
     """K1p (two moves per table row, persistent 64-row tiles): rows that return to solved, the
     no-move index 12 in the stream, odd depths (padded tail pair) and the fold schedule.
-    fixed = 2: the lane-private move layout the kernel uses where the flat image bank-conflicts."""
-    if fixed == 2 and size == 2 and depth % 16:
-        pytest.skip("2x2x2 uses the private layout for multiples of 16 only")
+    fixed & 3 = 2: the swizzled move tile the kernel uses where the flat image bank-conflicts;
+    fixed & 4: four instances per lane (2x2x2, 128-row tiles)."""
+    if fixed & 3 == 2 and size == 2 and depth % 16:
+        pytest.skip("2x2x2 uses the swizzled tile for multiples of 16 only")
+    if fixed & 4 and size == 3:
+        pytest.skip("four instances per lane: 2x2x2 only")
     rng = np.random.RandomState(depth * 11 + size)
-    n = 192
+    n = 384 if fixed & 4 else 192
     A = T.N_ACTIONS[size]
     moves = rng.randint(A, size=(n, depth)).astype(np.uint8)
     if depth >= 2:

@@ -9,7 +9,10 @@ import torch
 from rubiks_cube_solver_b200 import ops
 
 dev = torch.device("cuda", 0)
+only = [int(v) for v in sys.argv[1:]]                      # optional: the cube sizes to sweep
 for size, a, n in ((3, 12, 4 << 20), (2, 6, 8 << 20)):
+    if only and size not in only:
+        continue
     s = ops.N_STICKERS[size]
     for depth in (1, 2, 7, 8, 10, 16, 19, 20, 21, 24, 29, 30, 31, 32, 40, 48, 64, 96, 97, 128, 200):
         moves = torch.randint(0, a, (n, depth), dtype=torch.uint8, device=dev)
