@@ -262,19 +262,27 @@ CUBE_HD void scramble_pairs_run(CubieState (&st)[NS], const int (&rows)[NS], int
     }
     auto word = [&](int j) {
         uint32_t y[NS];
-        static_assert(SIZE == 2 || NS <= 2, "3x3x3: static shifts are written out for two instances per lane");
+        static_assert(NS == 1 || NS % 2 == 0, "instances come in pairs");
         if (SIZE == 3 || NS <= 2) {
+            // 3x3x3: instances 2h, 2h+1 are the rows 2l, 2l+1 of the h-th 64 rows of the tile; 64 rows are a
+            // whole number of words for an even depth, so the static shift depends on the row's parity only
             {
-                constexpr int s0 = (NS == 2) ? pair_static_shift<SIZE, DEPTH>(0) : -1;
-                const uint32_t hi = (s0 == 0) ? 0u : mw[wi[0] + j + 1];
-                y[0] = pair_rows_word<s0>(lo[0], hi, sh[0], bias);                  // bytes 1, 3 = pair rows
-                lo[0] = (s0 == 0) ? mw[wi[0] + j + 1] : hi;
+                constexpr int s0 = (NS >= 2) ? pair_static_shift<SIZE, DEPTH>(0) : -1;
+#pragma unroll
+                for (int h = 0; h < NS; h += 2) {
+                    const uint32_t hi = (s0 == 0) ? 0u : mw[wi[h] + j + 1];
+                    y[h] = pair_rows_word<s0>(lo[h], hi, sh[h], bias);              // bytes 1, 3 = pair rows
+                    lo[h] = (s0 == 0) ? mw[wi[h] + j + 1] : hi;
+                }
             }
-            if (NS == 2) {
+            if (NS >= 2) {
                 constexpr int s1 = pair_static_shift<SIZE, DEPTH>(1);
-                const uint32_t hi = (s1 == 0) ? 0u : mw[wi[NS - 1] + j + 1];
-                y[NS - 1] = pair_rows_word<s1>(lo[NS - 1], hi, sh[NS - 1], bias);
-                lo[NS - 1] = (s1 == 0) ? mw[wi[NS - 1] + j + 1] : hi;
+#pragma unroll
+                for (int h = 1; h < NS; h += 2) {
+                    const uint32_t hi = (s1 == 0) ? 0u : mw[wi[h] + j + 1];
+                    y[h] = pair_rows_word<s1>(lo[h], hi, sh[h], bias);
+                    lo[h] = (s1 == 0) ? mw[wi[h] + j + 1] : hi;
+                }
             }
         } else {
             constexpr int s = pair_static_shift<2, DEPTH>(0);                       // 2x2x2: the same for every row

@@ -157,7 +157,9 @@ constexpr int kPairTableBytes = CUBE_PAIR_ROWS * 256;
 // kNS instances per lane in lockstep = tiles of 32 * kNS rows.  2x2x2 (two state registers per instance)
 // walks four: the per-tile work (claim, staging, barrier, stores, verdict words) is ~150 instructions per
 // lane, a quarter of that kernel's instruction count with two.
-// (Chosen for shallow sequences only: the 128-row tiles of a deep one leave room for too few warps.)
+// (Chosen for shallow sequences only: the 128-row tiles of a deep one leave room for too few warps.
+// 3x3x3 with four instances per lane and 12 warps was measured: depth 30 -1.6 %, depth 20 +2 %, depth 10
+// +4 % -- that kernel is bound by the shared-memory pipe, not by instruction issue; not instantiated.)
 template <int SIZE, int NS> struct PairCfg;
 template <> struct PairCfg<3, 2> { static constexpr int kMaxWarps = 24; };    // 768 threads: 85 registers each
 template <> struct PairCfg<2, 2> { static constexpr int kMaxWarps = 32; };
@@ -249,7 +251,7 @@ scramble_pairs_kernel(const uint8_t* __restrict__ moves, int n_tiles, int depth_
     if (tile < n_tiles) stage(tile, 0);
     int rows[NS];
 #pragma unroll
-    for (int k = 0; k < NS; ++k) rows[k] = (SIZE == 3) ? 2 * lane + k : lane + 32 * k;
+    for (int k = 0; k < NS; ++k) rows[k] = (SIZE == 3) ? 64 * (k >> 1) + 2 * lane + (k & 1) : lane + 32 * k;
     const uint32_t lanereg = pair_lanereg<SIZE>(lane), roff = pair_roff2(lane);
     const ColourLutShared lut{bulk::smem_addr(s_clut), bulk::smem_addr(s_elut)};
     unsigned n_solved = 0;
@@ -263,7 +265,7 @@ scramble_pairs_kernel(const uint8_t* __restrict__ moves, int n_tiles, int depth_
         CubieState st[NS];
 #pragma unroll
         for (int k = 0; k < NS; ++k) cubie_init(st[k]);
-        if (kPriv) scramble_pairs_run_swizzled<SIZE, NS>(st, s_moves + buf * mstride, lane, depth, tbl, lanereg, roff);
+        if constexpr (kPriv) scramble_pairs_run_swizzled<SIZE, NS>(st, s_moves + buf * mstride, lane, depth, tbl, lanereg, roff);
         else scramble_pairs_run<SIZE, (DEPTH > 0 ? DEPTH : 0), NS>(st, rows, depth, s_moves + buf * mstride, tbl, lanereg, roff);
         if (lane == 0) bulk::wait_read_all();                         // the previous store has released the out tile
         __syncwarp();
@@ -283,14 +285,19 @@ scramble_pairs_kernel(const uint8_t* __restrict__ moves, int n_tiles, int depth_
             bulk::commit();
         }
         // verdicts leave coalesced: one solved byte and one reward per row
-        if (SIZE == 3) {                                              // rows 2l, 2l+1: words built from the two ballots
-            if (solved && lane < 16)
-                reinterpret_cast<uint32_t*>(solved + (long long)tile * kPairTile)[lane] = pair_solved_word<SIZE>(m[0], m[NS - 1], lane);
+        if (SIZE == 3) {                                              // rows 2l, 2l+1 of every 64: words built from two ballots
+            if (solved && lane < kPairTile / 4) {
+                const uint32_t a = (NS == 4 && lane >= 16) ? m[NS - 2] : m[0], b = (NS == 4 && lane >= 16) ? m[NS - 1] : m[1];
+                reinterpret_cast<uint32_t*>(solved + (long long)tile * kPairTile)[lane] = pair_solved_word<SIZE>(a, b, lane & 15);
+            }
             if (reward) {
-                float2 v;
-                v.x = pair_row_bit<SIZE>(m[0], m[NS - 1], 2 * lane) ? 1.0f : -1.0f;
-                v.y = pair_row_bit<SIZE>(m[0], m[NS - 1], 2 * lane + 1) ? 1.0f : -1.0f;
-                reinterpret_cast<float2*>(reward + (long long)tile * kPairTile)[lane] = v;
+#pragma unroll
+                for (int h = 0; h < NS; h += 2) {
+                    float2 v;
+                    v.x = pair_row_bit<SIZE>(m[h], m[h + 1], 2 * lane) ? 1.0f : -1.0f;
+                    v.y = pair_row_bit<SIZE>(m[h], m[h + 1], 2 * lane + 1) ? 1.0f : -1.0f;
+                    reinterpret_cast<float2*>(reward + (long long)tile * kPairTile + 32 * h)[lane] = v;
+                }
             }
         } else {                                                      // rows l + 32k: the lane's own verdicts, 32 in a row
 #pragma unroll
@@ -440,7 +447,8 @@ long long launch_pairs(const uint8_t* moves, long long n, int depth, uint8_t* ou
     long long n_tiles = n / kPairTile;
     if (n_tiles > 0x3fffffff) n_tiles = 0x3fffffff;                   // 32-bit tile counters; the caller handles the rest
     const int tile_rows = kPairTile * depth / 128;                    // of the tensor map, when swizzled
-    bool priv = swz_ok && depth % (SIZE == 3 ? 8 : 16) == 0 && n_tiles * tile_rows < 0x7fffffffLL;
+    constexpr bool kCanSwizzle = SIZE == 2 || NS == 2;                // 3x3x3 with four instances per lane: flat only
+    bool priv = kCanSwizzle && swz_ok && depth % (SIZE == 3 ? 8 : 16) == 0 && n_tiles * tile_rows < 0x7fffffffLL;
     auto warps_for = [&](bool p) {
         int w = (kSmemLimit - (p ? 1024 : 256) - L::kPerWarp) / L::per_warp(depth, p);
         if (w > PairCfg<SIZE, NS>::kMaxWarps) w = PairCfg<SIZE, NS>::kMaxWarps;
@@ -457,7 +465,7 @@ long long launch_pairs(const uint8_t* moves, long long n, int depth, uint8_t* ou
     // straight-line specialisations: the reference's default depth (config.yaml:7) and BASELINE config 2's
     auto kern = depth == 30 ? scramble_pairs_kernel<SIZE, 30, NS>
               : depth == 20 ? scramble_pairs_kernel<SIZE, 20, NS>
-              : priv ? scramble_pairs_kernel<SIZE, -1, NS> : scramble_pairs_kernel<SIZE, 0, NS>;
+              : priv ? scramble_pairs_kernel<SIZE, (kCanSwizzle ? -1 : 0), NS> : scramble_pairs_kernel<SIZE, 0, NS>;
     static int configured_smem[64][4];
     static bool init_done = false;
     if (!init_done) { for (int i = 0; i < 64; ++i) for (int j = 0; j < 4; ++j) configured_smem[i][j] = -1; init_done = true; }

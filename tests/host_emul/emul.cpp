@@ -59,12 +59,15 @@ void scramble_pairs_t(const uint8_t* moves, long long n, int depth, uint8_t* out
             int rows[NS];
             CubieState st[NS];
             for (int k = 0; k < NS; ++k) {
-                rows[k] = (SIZE == 3) ? 2 * lane + k : lane + 32 * k;
+                rows[k] = (SIZE == 3) ? 64 * (k >> 1) + 2 * lane + (k & 1) : lane + 32 * k;
                 cubie_init(st[k]);
             }
             const uint32_t lr = pair_lanereg<SIZE>(lane);
             const PairTableHost s_ptbl{s_ptbl_mem};
-            if (priv) scramble_pairs_run_swizzled<SIZE, NS>(st, s_priv.data(), lane, depth, s_ptbl, lr, pair_roff2(lane));
+            if constexpr (SIZE == 2 || NS == 2) {
+                if (priv) scramble_pairs_run_swizzled<SIZE, NS>(st, s_priv.data(), lane, depth, s_ptbl, lr, pair_roff2(lane));
+            }
+            if (priv) {}
             else if (fixed && depth == 30) scramble_pairs_run<SIZE, 30, NS>(st, rows, depth, s_moves.data(), s_ptbl, lr, pair_roff2(lane));
             else if (fixed && depth == 20) scramble_pairs_run<SIZE, 20, NS>(st, rows, depth, s_moves.data(), s_ptbl, lr, pair_roff2(lane));
             else if (fixed && depth == 43) scramble_pairs_run<SIZE, 43, NS>(st, rows, depth, s_moves.data(), s_ptbl, lr, pair_roff2(lane));
@@ -74,7 +77,8 @@ void scramble_pairs_t(const uint8_t* moves, long long n, int depth, uint8_t* out
         }
         if (SIZE == 3) {
             for (int k = 0; k < T / 4; ++k) {                        // the kernel's verdict exchange
-                const uint32_t w = pair_solved_word<SIZE>(ok[0], ok[NS - 1], k);
+                const int h = 2 * (k >> 4);
+                const uint32_t w = pair_solved_word<SIZE>(ok[h % NS], ok[(h + 1) % NS], k & 15);
                 std::memcpy(solved + base + 4 * k, &w, 4);
             }
         } else {
