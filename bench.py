@@ -524,7 +524,7 @@ def run_b200_arm(args):
             traffic = json.load(open(prof)).get("dram_bytes_per_launch")
         except Exception:                                   # noqa: BLE001
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "scramble_pairs_kernel<3,30>", "achieved": alg_bytes / kern_s / 1e9,
+    roofline = {"bound": "hbm", "kernel": "scramble_pairs_kernel<3,30,2>", "achieved": alg_bytes / kern_s / 1e9,
                 "peak": peak_gbs, "unit": "GB/s", "frac": alg_bytes / kern_s / 1e9 / peak_gbs, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                 "kernel_ms": kern_s * 1e3, "kernel_ms_isolated": isolated_s * 1e3,

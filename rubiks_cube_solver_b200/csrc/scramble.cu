@@ -159,7 +159,8 @@ constexpr int kPairTableBytes = CUBE_PAIR_ROWS * 256;
 // lane, a quarter of that kernel's instruction count with two.
 // (Chosen for shallow sequences only: the 128-row tiles of a deep one leave room for too few warps.
 // 3x3x3 with four instances per lane and 12 warps was measured: depth 30 -1.6 %, depth 20 +2 %, depth 10
-// +4 % -- that kernel is bound by the shared-memory pipe, not by instruction issue; not instantiated.)
+// +4 % -- that kernel is bound by the shared-memory pipe, not by instruction issue; not instantiated.
+// 2x2x2 with eight per lane (256-row tiles, 8 warps): depth 20 -10 %.)
 template <int SIZE, int NS> struct PairCfg;
 template <> struct PairCfg<3, 2> { static constexpr int kMaxWarps = 24; };    // 768 threads: 85 registers each
 template <> struct PairCfg<2, 2> { static constexpr int kMaxWarps = 32; };

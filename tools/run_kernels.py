@@ -1,6 +1,6 @@
 """Launch each hot kernel a few times at its BASELINE size (for ncu captures and quick timing).
 
-    python tools/run_kernels.py [scramble3|scramble2|step3|step2|expand3|leaf2|all] [--iters N]
+    python tools/run_kernels.py [scramble3|scramble3_d32|scramble2|step3|step2|expand3|leaf2|all] [--iters N]
 """
 import os
 import sys
@@ -38,6 +38,13 @@ def main():
         so = torch.empty(n, dtype=torch.uint8, device=dev)
         rw = torch.empty(n, dtype=torch.float32, device=dev)
         timed("scramble3", lambda: ops.scramble(3, moves, out=st, solved=so, reward=rw), n * d)
+    if which == "scramble3_d32":                   # a depth whose move tile is staged swizzled
+        n, d = 8 * 2 ** 20, 32
+        moves = torch.randint(0, 12, (n, d), dtype=torch.uint8, device=dev, generator=gen)
+        st = torch.empty((n, 54), dtype=torch.uint8, device=dev)
+        so = torch.empty(n, dtype=torch.uint8, device=dev)
+        rw = torch.empty(n, dtype=torch.float32, device=dev)
+        timed("scramble3_d32", lambda: ops.scramble(3, moves, out=st, solved=so, reward=rw), n * d)
     if which in ("scramble2", "all"):
         n, d = 16 * 2 ** 20, 20
         moves = torch.randint(0, 6, (n, d), dtype=torch.uint8, device=dev, generator=gen)
