@@ -152,7 +152,7 @@ scramble_tile_kernel(const uint8_t* __restrict__ moves, long long n, long long t
 // parity (54-byte rows alternate between word-aligned and two bytes off); the 64 sticker rows are
 // assembled in the warp's output tile and leave by one bulk store.  The 43 KB table is loaded once
 // per CTA.  A tile of 64 rows keeps every bulk copy a multiple of 16 bytes for any depth.
-constexpr int kMaxPairDepth = 96;
+constexpr int kMaxPairDepth = 320;       // four warps' double-buffered move tiles still fit
 constexpr int kPairTableBytes = CUBE_PAIR_ROWS * 256;
 // kNS instances per lane in lockstep = tiles of 32 * kNS rows.  2x2x2 (two state registers per instance)
 // walks four: the per-tile work (claim, staging, barrier, stores, verdict words) is ~150 instructions per

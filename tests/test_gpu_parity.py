@@ -94,7 +94,7 @@ def test_decode_golden():
 
 # ------------------------------------------------------------------ oracle, seeded inputs
 @pytest.mark.parametrize("size", SIZES)
-@pytest.mark.parametrize("depth", (0, 1, 3, 4, 7, 8, 9, 20, 30, 31, 32, 61, 100, 128, 129, 200))
+@pytest.mark.parametrize("depth", (0, 1, 3, 4, 7, 8, 9, 20, 30, 31, 32, 61, 100, 128, 129, 200, 255, 320, 321, 400))
 def test_scramble_vs_oracle_depths(size, depth):
     rng = np.random.RandomState(depth + 100 * size)
     n = 3000
@@ -122,13 +122,13 @@ def test_scramble_vs_oracle_depths(size, depth):
 
 
 @pytest.mark.parametrize("size", SIZES)
-@pytest.mark.parametrize("depth", (8, 16, 24, 32, 48, 64, 72, 96))
-def test_scramble_private_move_layout(size, depth):
-    """Depths whose flat tile image bank-conflicts run K1p with lane-private move slices (one or two bulk
-    copies per lane).  Several tiles per warp, so both move buffers and their barriers' phases are reused;
+@pytest.mark.parametrize("depth", (8, 16, 24, 32, 48, 64, 72, 96, 128, 200, 320))
+def test_scramble_swizzled_move_tiles(size, depth):
+    """Depths whose flat tile image bank-conflicts stage K1p's move tiles by a 2-D tensor copy with the
+    128-byte swizzle.  Several tiles per warp, so both move buffers and their barriers' phases are reused;
     a ragged tail; rows that come back to solved."""
     rng = np.random.RandomState(depth + 1000 * size)
-    n = 148 * 32 * 64 * 3 + 77
+    n = 148 * (32 if depth <= 96 else 8) * 64 * 3 + 77
     moves = rng.randint(T.N_ACTIONS[size], size=(n, depth)).astype(np.uint8)
     h = depth // 2
     back = rng.choice(n, 500, replace=False)
@@ -154,12 +154,12 @@ def test_scramble_ragged_sizes(size, n):
 
 
 @pytest.mark.parametrize("size", SIZES)
-@pytest.mark.parametrize("n,depth", [(n, d) for n in (63, 64, 65, 129) for d in (2, 95, 96, 97)]
+@pytest.mark.parametrize("n,depth", [(n, d) for n in (63, 64, 65, 129) for d in (2, 95, 96, 97, 319, 320, 321)]
                          + [(n, d) for n in (127, 128, 191, 257) for d in (1, 20, 30, 31, 32, 33)]
                          + [(64 * 148 * 24 + 1, 30), (64 * 148 * 32 + 65, 20), (128 * 148 * 20 * 3 + 127, 20)])
 def test_scramble_tile_and_depth_boundaries(size, n, depth):
     """K1p handles whole tiles (64 rows; 128 for shallow 2x2x2 sequences, four instances per lane) at depth
-    1..96; the single-move kernels take the ragged tail, deeper sequences and everything around: the
+    1..320; the single-move kernels take the ragged tail, deeper sequences and everything around: the
     seams must not show."""
     rng = np.random.RandomState(n % 1000 + depth)
     moves = rng.randint(T.N_ACTIONS[size], size=(n, depth)).astype(np.uint8)

@@ -59,9 +59,9 @@ def test_scramble_emulation(emul, size, depth):
 
 
 @pytest.mark.parametrize("size", (2, 3))
-@pytest.mark.parametrize("depth,fixed", [(d, 0) for d in (1, 2, 3, 4, 5, 7, 8, 9, 20, 30, 31, 32, 43, 61, 96)]
+@pytest.mark.parametrize("depth,fixed", [(d, 0) for d in (1, 2, 3, 4, 5, 7, 8, 9, 20, 30, 31, 32, 43, 61, 96, 100, 201, 318)]
                          + [(20, 1), (30, 1), (43, 1)]
-                         + [(d, 2) for d in (8, 16, 24, 32, 48, 64, 72, 96)]
+                         + [(d, 2) for d in (8, 16, 24, 32, 48, 64, 72, 96, 128, 200, 320)]
                          + [(d, 4) for d in (1, 2, 3, 5, 8, 9, 10, 14, 19, 21, 30, 31)] + [(20, 5), (30, 5), (16, 6), (32, 6)])
 def test_scramble_pairs_emulation(emul, size, depth, fixed):
     """K1p (two moves per table row, persistent 64-row tiles): rows that return to solved, the

@@ -14,7 +14,7 @@ for size, a, n in ((3, 12, 4 << 20), (2, 6, 8 << 20)):
     if only and size not in only:
         continue
     s = ops.N_STICKERS[size]
-    for depth in (1, 2, 7, 8, 10, 16, 19, 20, 21, 24, 29, 30, 31, 32, 40, 48, 64, 96, 97, 128, 200):
+    for depth in (1, 2, 7, 8, 10, 16, 19, 20, 21, 24, 29, 30, 31, 32, 40, 48, 64, 96, 97, 128, 160, 200, 256, 320, 321):
         moves = torch.randint(0, a, (n, depth), dtype=torch.uint8, device=dev)
         st = torch.empty((n, s), dtype=torch.uint8, device=dev)
         so = torch.empty(n, dtype=torch.uint8, device=dev)
