@@ -284,13 +284,15 @@ int launch_expand(int size, const uint8_t* states, long long n, uint8_t* childre
 {
     if (n == 0) return 0;
     if (size == 2 && child_onehot && dtype != 1) {
-        // 2x2x2 ADI shape: image kernel K3c for whole 32-parent tiles, generic kernel for the remainder
+        // 2x2x2 ADI shape: image kernel K3c for whole tiles of parents, generic kernel for the remainder
+        // (f32: the generic kernel already streams at the HBM peak, 1.03 measured; K3c with 8 parents per
+        // CTA reached 0.98)
         int rc = 0;
         const long long done = launch_leaf2_children(states, n, children, child_onehot, parent_onehot, dtype, solved,
                                                      reward, counters, stream, &rc);
         if (rc) return rc;
         if (done == n) return 0;
-        const int es = dtype == 0 ? 2 : 1;
+        const int es = dtype == 0 ? 2 : (dtype == 1 ? 4 : 1);
         states += done * 24;
         n -= done;
         if (children) children += done * 144;

@@ -87,6 +87,13 @@ def main():
         child = torch.empty((n, 6, 7, 21), dtype=torch.bfloat16, device=dev)
         timed("expand2", lambda: ops.expand(2, parents, dtype=torch.bfloat16, child_onehot=child), n)
         print("   expand2 algorithmic bytes/parent %d" % (24 + 6 * (294 + 5)))
+    if which == "expand2_f32":                     # what the drop-in env / ADI feed the reference's float32 net
+        n = 2 * 2 ** 20
+        parents, _, _ = ops.scramble(2, torch.randint(0, 6, (n, 14), dtype=torch.uint8, device=dev, generator=gen),
+                                     want_flags=False)
+        child = torch.empty((n, 6, 7, 21), dtype=torch.float32, device=dev)
+        timed("expand2_f32", lambda: ops.expand(2, parents, dtype=torch.float32, child_onehot=child), n)
+        print("   expand2_f32 algorithmic bytes/parent %d" % (24 + 6 * (588 + 5)))
 
 
 if __name__ == "__main__":
