@@ -214,6 +214,29 @@ int cube_pipeline_scramble_host(cube_pipeline_t* p, const uint8_t* moves_host, i
                                 uint8_t* states_out_host, uint8_t* solved_host, float* reward_host,
                                 int64_t* solved_count);
 
+/* ---- single-cube host front end (the drop-in CubeEnv's per-call path) ---------------------
+ * The reference's callers drive ONE cube per call (env.reset / env.step / get_obs:
+ * cube_env.py:56-111, used by train.py:155,186-191, mcts.py:80, test.py:123).  A handle owns a
+ * page of mapped pinned memory that the kernels read and write directly, so a call is two
+ * launches and one stream synchronisation, with no copy calls: ~25 us instead of ~120 us
+ * through device tensors.  Blocking; all buffers are HOST buffers; any out pointer may be NULL.
+ *   stickers_host      [S]   uint8  in
+ *   stickers_out_host  [S]   uint8  out
+ *   onehot_u8_host     [D]   uint8  out  (the observation as 0/1 bytes, D = 147 / 480)
+ *   solved_host              int    out  (1 = solved: done, reward +1; else -1) */
+typedef struct cube_env_host cube_env_host_t;
+
+int cube_env_host_create(int cube_size, int max_depth, cube_env_host_t** out);
+int cube_env_host_destroy(cube_env_host_t* h);
+/* step (cube_env.py:71-111): one face turn of the given cube */
+int cube_env_host_step(cube_env_host_t* h, const uint8_t* stickers_host, int action, uint8_t* stickers_out_host,
+                       uint8_t* onehot_u8_host, int* solved_host, void* stream);
+/* reset (cube_env.py:56-69): `depth` <= max_depth moves applied to the solved cube */
+int cube_env_host_scramble(cube_env_host_t* h, const uint8_t* moves_host, int depth, uint8_t* stickers_out_host,
+                           uint8_t* onehot_u8_host, int* solved_host, void* stream);
+/* sim_state_to_state / get_obs (cube_env.py:113-147) */
+int cube_env_host_encode(cube_env_host_t* h, const uint8_t* stickers_host, uint8_t* onehot_u8_host, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -13,6 +13,7 @@ SYMBOLS = (
     "cube_abi_version", "cube_last_error", "cube_sm_count", "cube_set_reserved_sms", "cube_moves_from_seeds", "cube_scramble", "cube_step", "cube_walk",
     "cube_solved", "cube_encode", "cube_expand", "cube_adi_targets", "cube_mcts_traverse", "cube_mcts_update", "cube_decode", "cube_validate_actions",
     "cube_pipeline_create", "cube_pipeline_destroy", "cube_pipeline_scramble_host",
+    "cube_env_host_create", "cube_env_host_destroy", "cube_env_host_step", "cube_env_host_scramble", "cube_env_host_encode",
 )
 
 CUBE_ERR_SIZE, CUBE_ERR_ARG, CUBE_ERR_ALIGN, CUBE_ERR_ACTION = -1, -2, -3, -4
@@ -67,6 +68,11 @@ def load():
     lib.cube_pipeline_create.argtypes = [ci, ci, i64, ci, ctypes.POINTER(vp)]
     lib.cube_pipeline_destroy.argtypes = [vp]
     lib.cube_pipeline_scramble_host.argtypes = [vp, vp, i64, vp, vp, vp, ctypes.POINTER(i64)]
+    lib.cube_env_host_create.argtypes = [ci, ci, ctypes.POINTER(vp)]
+    lib.cube_env_host_destroy.argtypes = [vp]
+    lib.cube_env_host_step.argtypes = [vp, vp, ci, vp, vp, ctypes.POINTER(ci), vp]
+    lib.cube_env_host_scramble.argtypes = [vp, vp, ci, vp, vp, ctypes.POINTER(ci), vp]
+    lib.cube_env_host_encode.argtypes = [vp, vp, vp, vp]
     for name in SYMBOLS:
         if name not in ("cube_last_error",):
             getattr(lib, name).restype = ci

@@ -81,6 +81,17 @@ class CubeEnv(_EnvBase):
         arr = np.ascontiguousarray(sim_state, dtype=np.uint8).reshape(1, -1)
         return torch.from_numpy(arr).to(self._sim_device)
 
+    def _host(self):
+        # the calling thread's single-cube session (mapped pinned page, C ABI cube_env_host_*): shared
+        # by all envs of this size and device, so a deepcopy of the env copies no handle
+        return ops.host_cube(self.cube_size, self._sim_device.index)
+
+    def _sim_u8(self, sim_state):
+        arr = np.ascontiguousarray(sim_state, dtype=np.uint8).reshape(-1)
+        if arr.shape[0] != ops.N_STICKERS[self.cube_size]:
+            raise ValueError("a sticker array of %d entries is expected" % ops.N_STICKERS[self.cube_size])
+        return arr
+
     def _obs_from_u8(self, onehot_u8):
         if self.cube_size == 2:
             return onehot_u8.astype(np.float64)               # np.zeros(state_dim), cube_env.py:141
@@ -103,11 +114,16 @@ class CubeEnv(_EnvBase):
         np.random.set_state(origin_state)
         if len(action_sequence) == 0:
             raise UnboundLocalError("local variable 'state' referenced before assignment")   # cube_env.py:69
-        moves = torch.from_numpy(action_sequence.astype(np.uint8).reshape(1, -1)).to(self._sim_device)
-        states, _, _ = ops.scramble(self.cube_size, moves)
-        onehot = ops.encode(self.cube_size, states, dtype=torch.uint8)
-        self.sim_cube = states[0].cpu().numpy().astype(np.int64)
-        self.cube = self._obs_from_u8(onehot[0].cpu().numpy())
+        host = self._host()
+        if len(action_sequence) <= host.max_depth:
+            stickers, onehot, _ = host.scramble(np.ascontiguousarray(action_sequence, dtype=np.uint8))
+        else:                                               # absurdly deep: through device tensors
+            moves = torch.from_numpy(action_sequence.astype(np.uint8).reshape(1, -1)).to(self._sim_device)
+            states, _, _ = ops.scramble(self.cube_size, moves)
+            onehot = ops.encode(self.cube_size, states, dtype=torch.uint8)[0].cpu().numpy()
+            stickers = states[0].cpu().numpy()
+        self.sim_cube = stickers.astype(np.int64)
+        self.cube = self._obs_from_u8(onehot)
         return self.cube
 
     def step(self, action):
@@ -115,13 +131,9 @@ class CubeEnv(_EnvBase):
             raise NotImplementedError
         self.action_to_sim_action[self.cube_size][action]     # IndexError / TypeError like the reference's list lookup
         a = int(action) % self.action_dim
-        states = self._upload(self.sim_cube)
-        act = torch.tensor([a], dtype=torch.uint8, device=self._sim_device)
-        states, solved, _ = ops.step(self.cube_size, states, act)
-        onehot = ops.encode(self.cube_size, states, dtype=torch.uint8)
-        self.sim_cube = states[0].cpu().numpy().astype(np.int64)
-        self.cube = self._obs_from_u8(onehot[0].cpu().numpy())
-        done = bool(solved[0].item())
+        stickers, onehot, done = self._host().step(self._sim_u8(self.sim_cube), a)
+        self.sim_cube = stickers.astype(np.int64)
+        self.cube = self._obs_from_u8(onehot)
         reward = 1.0 if done else -1.0
         if self.show_cube:
             raise NotImplementedError("rendering is out of scope (matplotlib GUI)")
@@ -139,8 +151,7 @@ class CubeEnv(_EnvBase):
     def sim_state_to_state(self, sim_state):
         if self.cube_size not in (2, 3):
             raise NotImplementedError
-        onehot = ops.encode(self.cube_size, self._upload(sim_state), dtype=torch.uint8)
-        return self._obs_from_u8(onehot[0].cpu().numpy())
+        return self._obs_from_u8(self._host().encode(self._sim_u8(sim_state)))
 
     def state_to_sim_state(self, state):
         if self.cube_size == 2:

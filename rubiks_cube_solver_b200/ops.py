@@ -6,7 +6,9 @@ one-hot ``[N, R, C]`` (7x21 / 20x24).  Every function launches asynchronously on
 the current CUDA stream of the tensors' device and returns tensors on that device.
 """
 import ctypes
+import threading
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -258,6 +260,85 @@ def decode(cube_size, onehot):
         _lib.check(_lib.load().cube_decode(cube_size, _ptr(onehot), ONEHOT_DTYPES[onehot.dtype], n, _ptr(out),
                                            _stream(onehot.device)), "cube_decode")
     return out
+
+
+class HostCube(object):
+    """One cube per call through host (NumPy) buffers -- C ABI cube_env_host_*: the per-call path of the
+    drop-in CubeEnv (reset / step / get_obs, cube_env.py:56-147).  Two launches and one stream
+    synchronisation per call, no copy calls (the kernels work on a mapped pinned page).  Bound to one
+    device; not thread-safe (use one per thread, see `host_cube`)."""
+
+    def __init__(self, cube_size, device=None, max_depth=1024):
+        self.s, _, (r, c) = _geom(cube_size)
+        self.shape = (r, c)
+        self.cube_size, self.max_depth = cube_size, max_depth
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self._idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        handle = ctypes.c_void_p()
+        lib = _lib.load()
+        with torch.cuda.device(self._idx):
+            _lib.check(lib.cube_env_host_create(cube_size, max_depth, ctypes.byref(handle)), "cube_env_host_create")
+        self._h = handle
+        self._step, self._scramble, self._encode = lib.cube_env_host_step, lib.cube_env_host_scramble, lib.cube_env_host_encode
+        self._solved = ctypes.c_int(0)
+        self._solved_ref = ctypes.byref(self._solved)
+
+    def _run(self, fn, *args):
+        if torch.cuda.current_device() != self._idx:
+            with torch.cuda.device(self._idx):
+                rc = fn(self._h, *args)
+        else:
+            rc = fn(self._h, *args)
+        if rc:
+            _lib.check(rc, fn.__name__)
+
+    def step(self, stickers, action):
+        """stickers: uint8 [S] NumPy array, action: int.  Returns (stickers uint8 [S], onehot uint8 [R, C], solved)."""
+        out = np.empty(self.s, dtype=np.uint8)
+        onehot = np.empty(self.shape, dtype=np.uint8)
+        self._run(self._step, stickers.ctypes.data, int(action), out.ctypes.data, onehot.ctypes.data, self._solved_ref, None)
+        return out, onehot, bool(self._solved.value)
+
+    def scramble(self, moves):
+        """moves: uint8 [depth] NumPy array applied to the solved cube.  Same returns as `step`."""
+        if len(moves) > self.max_depth:
+            raise ValueError("more than max_depth = %d moves" % self.max_depth)
+        out = np.empty(self.s, dtype=np.uint8)
+        onehot = np.empty(self.shape, dtype=np.uint8)
+        self._run(self._scramble, moves.ctypes.data, len(moves), out.ctypes.data, onehot.ctypes.data, self._solved_ref, None)
+        return out, onehot, bool(self._solved.value)
+
+    def encode(self, stickers):
+        onehot = np.empty(self.shape, dtype=np.uint8)
+        self._run(self._encode, stickers.ctypes.data, onehot.ctypes.data, None)
+        return onehot
+
+    def close(self):
+        if self._h:
+            _lib.load().cube_env_host_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001 - interpreter shutdown
+            pass
+
+
+_host_cubes = threading.local()
+
+
+def host_cube(cube_size, device_index):
+    """The calling thread's HostCube for (cube_size, device): envs share it, so `copy.deepcopy(env)`
+    (mcts.py:37,96,101) copies no handle."""
+    cache = getattr(_host_cubes, "cache", None)
+    if cache is None:
+        cache = _host_cubes.cache = {}
+    key = (cube_size, device_index)
+    hc = cache.get(key)
+    if hc is None:
+        hc = cache[key] = HostCube(cube_size, torch.device("cuda", device_index))
+    return hc
 
 
 class HostScramblePipeline(object):

@@ -758,3 +758,33 @@ def test_two_devices_in_one_process():
             assert (stepped.cpu().numpy() == O.apply_moves(size, want, act)).all()
             res = ops.expand(size, stepped[:100].contiguous(), dtype=torch.bfloat16, want_children=True)
             assert (res["children"].cpu().numpy() == O.expand(size, O.apply_moves(size, want, act)[:100])[0]).all()
+
+
+@pytest.mark.parametrize("size", SIZES)
+def test_host_cube_single_cube_calls(size):
+    """C ABI cube_env_host_* (mapped pinned page, one synchronisation per call): step / scramble / encode
+    of one cube against the oracle, the no-move index, depth 0, and the argument checks."""
+    rng = np.random.RandomState(size)
+    A, S = T.N_ACTIONS[size], T.N_STICKERS[size]
+    hc = ops.HostCube(size, max_depth=64)
+    moves = rng.randint(A, size=40).astype(np.uint8)
+    st, oh, solved = hc.scramble(moves)
+    want = O.scramble(size, moves[None, :])[0]
+    assert st.dtype == np.uint8 and (st == want).all() and not solved
+    assert (oh == O.encode(size, want[None])[0]).all() and (hc.encode(st) == oh).all()
+    cur = st
+    for a in rng.randint(A, size=30):
+        cur, oh, solved = hc.step(cur, int(a))
+        want = O.scramble(size, np.array([[a]]), init=want[None])[0]
+        assert (cur == want).all() and (oh == O.encode(size, want[None])[0]).all()
+        assert solved == bool(O.is_solved(size, want[None])[0])
+    back = np.concatenate([moves[:6], moves[:6][::-1] ^ 1]).astype(np.uint8)
+    st, oh, solved = hc.scramble(back)
+    assert solved and (st == O.scramble(size, np.zeros((1, 0), dtype=np.uint8))[0]).all()
+    st0, _, solved0 = hc.scramble(np.zeros(0, dtype=np.uint8))                 # depth 0: the solved cube
+    assert solved0 and (st0 == st).all()
+    same, _, _ = hc.step(cur, 12)                                              # CUBE_NOOP
+    assert (same == cur).all()
+    with pytest.raises(ValueError):
+        hc.scramble(np.zeros(65, dtype=np.uint8))
+    hc.close()
