@@ -311,8 +311,28 @@ def measure_other_configs(torch, ops, adi, dev, peak_gbs):
                                                 want_child_onehot=False, want_parent_onehot=True), 10)
     entry("config5_2x2_mcts_leaf_expand_1Mi", t, n, "leaves/s", n * (24 + 294 + 144 + 6 + 24))   # + reward f32 x6
     out["drop_in_get_random_samples"] = measure_drop_in_adi(torch, dev)
+    out["drop_in_env_step_latency"] = measure_drop_in_step(torch, dev)
     out["mcts_2x2_batched_search"] = measure_mcts(torch, dev)
     return out
+
+
+def measure_drop_in_step(torch, dev):
+    """One cube per call through the drop-in CubeEnv (C ABI cube_env_host_step: mapped pinned page, two launches,
+    one synchronisation), the way train.py:155 / mcts.py:80 / test.py:123 drive the reference's env."""
+    import numpy as np
+    from rubiks_cube_solver_b200.env import make_env
+    res = {"unit": "us/call"}
+    for size in (2, 3):
+        env = make_env(dev, size)
+        env.reset(seed=1, scramble_count=10)
+        acts = np.random.RandomState(0).randint(env.action_dim, size=1050)
+        for a in acts[:50]:
+            env.step(int(a))
+        t0 = time.perf_counter()
+        for a in acts[50:]:
+            env.step(int(a))
+        res["step_%dx%dx%d" % (size, size, size)] = (time.perf_counter() - t0) / 1000 * 1e6
+    return res
 
 
 def measure_mcts(torch, dev):
