@@ -43,6 +43,16 @@ def _stream(device):
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+def sm_count():
+    """SMs of the current device (C ABI cube_sm_count)."""
+    return _lib.load().cube_sm_count()
+
+
+def set_reserved_sms(n):
+    """Leave n SMs free of the persistent kernels' CTAs (C ABI cube_set_reserved_sms), e.g. one for NCCL."""
+    _lib.check(_lib.load().cube_set_reserved_sms(int(n)), "cube_set_reserved_sms")
+
+
 def new_counters(device):
     """uint64[4] device counters: [solved, produced, bad actions, reserved] (kept as int64)."""
     return torch.zeros(4, dtype=torch.int64, device=device)

@@ -788,3 +788,22 @@ def test_host_cube_single_cube_calls(size):
     with pytest.raises(ValueError):
         hc.scramble(np.zeros(65, dtype=np.uint8))
     hc.close()
+
+
+@pytest.mark.parametrize("size,depth", [(3, 30), (3, 32), (3, 24), (3, 128), (2, 20), (2, 32), (2, 33), (2, 96)])
+def test_scramble_many_tiles_per_warp(size, depth):
+    """Two persistent CTAs (cube_set_reserved_sms): every warp walks many tiles, so both move buffers, the
+    barriers' phase bits, the out-tile hand-over to the bulk store and the dynamic tail are exercised far
+    beyond what a full-width launch of a test-sized batch reaches."""
+    rng = np.random.RandomState(7 * depth + size)
+    n = 64 * 900 + 17
+    moves = rng.randint(T.N_ACTIONS[size], size=(n, depth)).astype(np.uint8)
+    ops.set_reserved_sms(ops.sm_count() - 2)
+    try:
+        states, solved, reward = ops.scramble(size, cu(moves))
+        torch.cuda.synchronize()
+    finally:
+        ops.set_reserved_sms(0)
+    want, ws, wr, _ = C.scramble(size, moves)
+    assert (states.cpu().numpy() == want).all()
+    assert (solved.cpu().numpy().astype(bool) == ws).all() and (reward.cpu().numpy() == wr).all()
