@@ -217,8 +217,8 @@ int cube_pipeline_scramble_host(cube_pipeline_t* p, const uint8_t* moves_host, i
 /* ---- single-cube host front end (the drop-in CubeEnv's per-call path) ---------------------
  * The reference's callers drive ONE cube per call (env.reset / env.step / get_obs:
  * cube_env.py:56-111, used by train.py:155,186-191, mcts.py:80, test.py:123).  A handle owns a
- * page of mapped pinned memory that the kernels read and write directly, so a call is two
- * launches and one stream synchronisation, with no copy calls: ~25 us instead of ~120 us
+ * page of mapped pinned memory that the kernels read and write directly, so a call is one or
+ * two launches and one stream synchronisation, with no copy calls: ~20 us instead of ~120 us
  * through device tensors.  Blocking; all buffers are HOST buffers; any out pointer may be NULL.
  *   stickers_host      [S]   uint8  in
  *   stickers_out_host  [S]   uint8  out

@@ -17,6 +17,7 @@
 // different sector per lane).  Several CTAs per SM overlap load, compute and store.
 // The kernel is bound by the ALU pipe (PRMT/LOP3) and the shared-memory pipe (six
 // table words per move), not by HBM -- see DESIGN.md.
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
 #include <cuda.h>
@@ -374,17 +375,15 @@ int launch_classic(const uint8_t* moves, long long n, int depth, uint8_t* out, u
     if (staged) {
         auto kern_full = scramble_tile_kernel<SIZE, true>;
         auto kern_tail = scramble_tile_kernel<SIZE, false>;
-        static int configured_dev[64];
-        static bool init_done = false;
-        if (!init_done) { for (int i = 0; i < 64; ++i) configured_dev[i] = -1; init_done = true; }
-        int& configured_smem = configured_dev[cube::device_slot()];
-        if (smem > configured_smem) {
+        static std::atomic<int> configured_dev[64];         // per device, 0 = never configured; host threads may race here
+        std::atomic<int>& configured_smem = configured_dev[cube::device_slot()];
+        if (smem > configured_smem.load(std::memory_order_relaxed)) {
             cudaError_t e = cudaFuncSetAttribute(kern_full, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
             if (e == cudaSuccess) e = cudaFuncSetAttribute(kern_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
             if (e != cudaSuccess) return (int)e;
             // largest shared-memory carve-out, so occupancy is set by registers, not by the default split
             cudaFuncSetAttribute(kern_full, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            configured_smem = smem;
+            configured_smem.store(smem, std::memory_order_relaxed);
         }
         const long long full_tiles = n / kTile;
         if (full_tiles > 0)
@@ -467,14 +466,12 @@ long long launch_pairs(const uint8_t* moves, long long n, int depth, uint8_t* ou
     auto kern = depth == 30 ? scramble_pairs_kernel<SIZE, 30, NS>
               : depth == 20 ? scramble_pairs_kernel<SIZE, 20, NS>
               : priv ? scramble_pairs_kernel<SIZE, (kCanSwizzle ? -1 : 0), NS> : scramble_pairs_kernel<SIZE, 0, NS>;
-    static int configured_smem[64][4];
-    static bool init_done = false;
-    if (!init_done) { for (int i = 0; i < 64; ++i) for (int j = 0; j < 4; ++j) configured_smem[i][j] = -1; init_done = true; }
-    int& cfg = configured_smem[cube::device_slot()][depth == 30 ? 1 : depth == 20 ? 2 : priv ? 3 : 0];
-    if (smem > cfg) {
+    static std::atomic<int> configured_smem[64][4];       // per device and kernel, 0 = never configured
+    std::atomic<int>& cfg = configured_smem[cube::device_slot()][depth == 30 ? 1 : depth == 20 ? 2 : priv ? 3 : 0];
+    if (smem > cfg.load(std::memory_order_relaxed)) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return -(long long)e;
-        cfg = smem;
+        cfg.store(smem, std::memory_order_relaxed);
     }
     long long grid = (n_tiles + warps - 1) / warps;
     if (grid > cube::persistent_ctas()) grid = cube::persistent_ctas();

@@ -13,6 +13,7 @@
 // depth = 1 is `step`; depth > 1 walks several moves without leaving shared
 // memory; depth = 0 with no output is `cube_solved`.
 // HBM traffic per instance: 2*S + depth + 1 + 4 bytes.
+#include <atomic>
 #include <cstdlib>
 #include <cuda_runtime.h>
 #include "cube_bulk.cuh"
@@ -307,14 +308,12 @@ int launch_tiles(const uint8_t* in, const uint8_t* moves, long long n, int depth
             if (n_tiles > 0x3fffffff) n_tiles = 0x3fffffff;
             const int smem = L::bytes(depth, warps);
             auto kern = walk_private_kernel<SIZE>;
-            static int configured_dev[64];
-            static bool init_done = false;
-            if (!init_done) { for (int i = 0; i < 64; ++i) configured_dev[i] = -1; init_done = true; }
-            int& configured_smem = configured_dev[cube::device_slot()];
-            if (smem > configured_smem) {
+            static std::atomic<int> configured_dev[64];     // per device, 0 = never configured
+            std::atomic<int>& configured_smem = configured_dev[cube::device_slot()];
+            if (smem > configured_smem.load(std::memory_order_relaxed)) {
                 const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
                 if (e != cudaSuccess) return (int)e;
-                configured_smem = smem;
+                configured_smem.store(smem, std::memory_order_relaxed);
             }
             long long grid = (n_tiles + warps - 1) / warps;
             if (grid > cube::persistent_ctas()) grid = cube::persistent_ctas();

@@ -27,5 +27,12 @@ for size in (2, 3):
     for i in range(200):
         env.reset(seed=i, scramble_count=20)
     t2 = time.perf_counter()
-    print("size %d: step %.1f us/call, reset(seed, 20) %.1f us/call" % (
-        size, (t1 - t0) / calls * 1e6, (t2 - t1) / 200 * 1e6), flush=True)
+    from rubiks_cube_solver_b200 import ops
+    hc = ops.host_cube(size, torch.cuda.current_device())
+    st = np.ascontiguousarray(env.sim_cube, dtype=np.uint8)
+    t3 = time.perf_counter()
+    for a in acts:
+        st, oh, done = hc.step(st, int(a))
+    t4 = time.perf_counter()
+    print("size %d: env.step %.1f us/call (HostCube.step alone %.1f), reset(seed, 20) %.1f us/call" % (
+        size, (t1 - t0) / calls * 1e6, (t4 - t3) / calls * 1e6, (t2 - t1) / 200 * 1e6), flush=True)
