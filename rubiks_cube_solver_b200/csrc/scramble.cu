@@ -271,13 +271,11 @@ scramble_pairs_kernel(const uint8_t* __restrict__ moves, int n_tiles, int depth_
         else scramble_pairs_run<SIZE, (DEPTH > 0 ? DEPTH : 0), NS>(st, rows, depth, s_moves + buf * mstride, tbl, lanereg, roff);
         if (lane == 0) bulk::wait_read_all();                         // the previous store has released the out tile
         __syncwarp();
-        uint32_t m[NS];
         bool ok[NS];
 #pragma unroll
         for (int k = 0; k < NS; ++k) {
             ok[k] = scramble_pairs_finish<SIZE>(st[k], rows[k], lut, s_out);
-            m[k] = __ballot_sync(0xffffffffu, ok[k]);
-            n_solved += (unsigned)__popc(m[k]);
+            n_solved += ok[k] ? 1u : 0u;                              // per lane; summed over the warp after the last tile
         }
 
         bulk::fence_smem_writes();                                    // rows -> visible to the copy engine
@@ -286,22 +284,15 @@ scramble_pairs_kernel(const uint8_t* __restrict__ moves, int n_tiles, int depth_
             bulk::store(out + (long long)tile * L::kOutBytes, s_out, (uint32_t)L::kOutBytes);
             bulk::commit();
         }
-        // verdicts leave coalesced: one solved byte and one reward per row
-        if (SIZE == 3) {                                              // rows 2l, 2l+1 of every 64: words built from two ballots
-            if (solved && lane < kPairTile / 4) {
-                const uint32_t a = (NS == 4 && lane >= 16) ? m[NS - 2] : m[0], b = (NS == 4 && lane >= 16) ? m[NS - 1] : m[1];
-                reinterpret_cast<uint32_t*>(solved + (long long)tile * kPairTile)[lane] = pair_solved_word<SIZE>(a, b, lane & 15);
-            }
-            if (reward) {
+        // verdicts leave coalesced, straight from the lane's own flags: one solved byte and one reward per row
+        if (SIZE == 3) {                                              // rows 2l, 2l+1 of every 64 are neighbours
 #pragma unroll
-                for (int h = 0; h < NS; h += 2) {
-                    float2 v;
-                    v.x = pair_row_bit<SIZE>(m[h], m[h + 1], 2 * lane) ? 1.0f : -1.0f;
-                    v.y = pair_row_bit<SIZE>(m[h], m[h + 1], 2 * lane + 1) ? 1.0f : -1.0f;
-                    reinterpret_cast<float2*>(reward + (long long)tile * kPairTile + 32 * h)[lane] = v;
-                }
+            for (int h = 0; h < NS; h += 2) {
+                const long long r0 = (long long)tile * kPairTile + 32 * h + 2 * lane;
+                if (solved) *reinterpret_cast<uint16_t*>(solved + r0) = (uint16_t)((ok[h] ? 1u : 0u) | (ok[h + 1] ? 0x100u : 0u));
+                if (reward) *reinterpret_cast<float2*>(reward + r0) = make_float2(ok[h] ? 1.0f : -1.0f, ok[h + 1] ? 1.0f : -1.0f);
             }
-        } else {                                                      // rows l + 32k: the lane's own verdicts, 32 in a row
+        } else {                                                      // rows l + 32k: 32 in a row per store
 #pragma unroll
             for (int k = 0; k < NS; ++k) {
                 if (solved) solved[(long long)tile * kPairTile + 32 * k + lane] = ok[k] ? 1 : 0;
@@ -310,6 +301,7 @@ scramble_pairs_kernel(const uint8_t* __restrict__ moves, int n_tiles, int depth_
         }
         tile = next;
     }
+    n_solved = __reduce_add_sync(0xffffffffu, n_solved);
     if (lane == 0 && n_solved && counters) atomicAdd(&counters[0], (unsigned long long)n_solved);
     if (blockIdx.x == 0 && tid == 0 && counters) atomicAdd(&counters[1], (unsigned long long)n_tiles * kPairTile);
     if (lane == 0) bulk::wait_read_all();                             // shared memory must outlive the copies' reads
