@@ -145,14 +145,16 @@ scramble_tile_kernel(const uint8_t* __restrict__ moves, long long n, long long t
 
 
 // ---- K1p: persistent pair-table kernel (the default for depth 1..kMaxPairDepth) ----------------
-// One CTA per SM; every WARP owns a private pipeline over tiles of 64 instances and never
+// One CTA per SM; every WARP owns a private pipeline over tiles of 64 (or 128) instances and never
 // synchronises with another warp after the prologue.  The tile's move bytes arrive by one bulk copy
-// (double-buffered: tile i+1 is in flight while tile i is computed); each lane walks TWO instances
-// in lockstep through the PAIR table (one conflict-free 2 x 128-bit row per two moves, see
-// cube_threads.cuh) -- rows 2l and 2l+1 for 3x3x3, so that each finishing pass writes rows of one
-// parity (54-byte rows alternate between word-aligned and two bytes off); the 64 sticker rows are
-// assembled in the warp's output tile and leave by one bulk store.  The 43 KB table is loaded once
-// per CTA.  A tile of 64 rows keeps every bulk copy a multiple of 16 bytes for any depth.
+// (double-buffered: tile i+1 is in flight while tile i is computed) -- a flat 1-D copy, or a 2-D tensor
+// copy with the 128-byte swizzle for the depths whose flat image bank-conflicts (DEPTH < 0); each lane
+// walks TWO (2x2x2, shallow: FOUR) instances in lockstep through the PAIR table (one conflict-free
+// 2 x 128-bit row per two moves, see cube_threads.cuh) -- rows 2l and 2l+1 for 3x3x3, so that each
+// finishing pass writes rows of one parity (54-byte rows alternate between word-aligned and two bytes
+// off); the sticker rows are assembled in the warp's output tile and leave by one bulk store, the
+// verdicts straight from the lanes' own flags.  The 43 KB table is loaded once per CTA.  Tiles of 64
+// rows keep every bulk copy a multiple of 16 bytes for any depth.
 constexpr int kMaxPairDepth = 320;       // four warps' double-buffered move tiles still fit
 constexpr int kPairTableBytes = CUBE_PAIR_ROWS * 256;
 // kNS instances per lane in lockstep = tiles of 32 * kNS rows.  2x2x2 (two state registers per instance)
