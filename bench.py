@@ -455,6 +455,8 @@ def run_b200_arm(args):
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     R.load_library()
+    # one process per GPU: keep this rank's host threads and pinned buffers on the GPU's own NUMA node
+    numa = cdist.bind_host_to_gpu_node(local) if world > 1 and not args.no_numa_bind else {"numa_node": None}
 
     n, depth, size = args.instances_per_gpu, DEPTH, CUBE_SIZE
     S = ops.N_STICKERS[size]
@@ -584,7 +586,8 @@ def run_b200_arm(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": WORKLOAD, "cube_size": size, "depth": depth, "instances_per_gpu": n,
                    "instances_total": world * n, "sm_count": R.load_library().cube_sm_count(), "l2": "inputs (252 MB/GPU) and outputs (495 MB/GPU) exceed the 126 MB L2",
-                   "collective": ("int64[4] all-reduce(SUM) per step, asynchronous" if args.reduce_every_step else "one all-reduce(SUM) of the per-step int64[4] solved/produced counter rows at the end of the timed region")},
+                   "collective": ("int64[4] all-reduce(SUM) per step, asynchronous" if args.reduce_every_step else "one all-reduce(SUM) of the per-step int64[4] solved/produced counter rows at the end of the timed region"),
+                   "host_numa_binding_rank0": numa},
         "solved_total": solved_total, "reward_total": 2 * solved_total - produced_total,
         "e2e": e2e, "roofline": roofline, "gpu_launches": args.steps, "clocks": clocks.summary(),
     }
@@ -645,6 +648,7 @@ def main():
     ap.add_argument("--reduce-every-step", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-other", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true", help="N > 1: do not pin each rank to its GPU's NUMA node")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
