@@ -173,3 +173,12 @@ def test_rollout_host_helpers():
     # best action is the inverse of the previous one -> second best (model.py:60-74)
     pre = torch.tensor([0, 1, -1])
     assert rollout.greedy_actions(logits, pre).tolist() == [2, 2, 3]
+
+
+def test_numa_binding_helper_is_best_effort():
+    """dist.bind_host_to_gpu_node never raises (no GPU / hidden sysfs) and parses sysfs cpu lists."""
+    from rubiks_cube_solver_b200 import dist as cdist
+    assert cdist._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert cdist._parse_cpulist("") == set()
+    info = cdist.bind_host_to_gpu_node(0)
+    assert isinstance(info, dict) and info.get("numa_node") is None or isinstance(info.get("numa_node"), int)
