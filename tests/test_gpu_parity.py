@@ -192,11 +192,13 @@ def test_walk_tile_and_depth_boundaries(size, n, depth):
     assert counters.tolist()[:2] == [int(ws.sum()), n]
 
 
-def test_persistent_kernels_on_concurrent_streams_and_in_a_graph():
+@pytest.mark.parametrize("depth", (30, 32))
+def test_persistent_kernels_on_concurrent_streams_and_in_a_graph(depth):
     """The tile scheduler's counters come from a ring of slots that every kernel re-arms: launches that
-    overlap on different streams must not see each other, and a captured launch must replay."""
+    overlap on different streams must not see each other, and a captured launch must replay (depth 32:
+    the swizzled variant, whose tensor map of the move array is a kernel parameter baked into the graph)."""
     rng = np.random.RandomState(9)
-    n, depth = 64 * 600 + 5, 30
+    n = 64 * 600 + 5
     streams = [torch.cuda.Stream() for _ in range(4)]
     jobs = []
     for i, st in enumerate(streams * 3):
