@@ -18,41 +18,80 @@
 
 namespace {
 
-__device__ __forceinline__ uint32_t mt_next_seed_word(uint32_t prev, uint32_t j)
+// x >> K on the FMA pipe (IMAD.HI) instead of the ALU pipe (SHF): the recurrence and the tempering are
+// shift / xor / multiply chains.  Measured: 8 Mi seeds x depth 30 take 1.3 ms either way (3 390 warp
+// instructions per 32 seeds, ALU pipe 63 %, issue 59 %, `math_pipe_throttle` and `dispatch_stall` on top:
+// profiles/r01_k0_seeded_moves_ncu_summary.json) -- the 397 sequential seed-state steps and ~50 draw
+// iterations of ~35 instructions are what the generator costs; the fused scramble behind it takes 0.18 ms.
+template <int K>
+__device__ __forceinline__ uint32_t shr(uint32_t x)
 {
-    return 1812433253u * (prev ^ (prev >> 30)) + j;
+    return __umulhi(x, 1u << (32 - K));
 }
 
-__global__ void __launch_bounds__(128)
+__device__ __forceinline__ uint32_t mt_next_seed_word(uint32_t prev, uint32_t j)
+{
+    return 1812433253u * (prev ^ shr<30>(prev)) + j;
+}
+
+constexpr int kSeedThreads = 128;
+
+// j as a constant-bank operand of the multiply-add (IMAD r, g, M, c[j]): with the loop index in a register
+// an unrolled step needs an extra ALU add for "+ j"
+struct SeedIndex { uint32_t v[400]; };
+constexpr SeedIndex make_seed_index()
+{
+    SeedIndex t{};
+    for (int j = 0; j < 400; ++j) t.v[j] = (uint32_t)j;
+    return t;
+}
+__constant__ SeedIndex kSeedIndex = make_seed_index();
+
+__global__ void __launch_bounds__(kSeedThreads)
 seeded_moves_kernel(const uint32_t* __restrict__ seeds, long long n, int depth, uint32_t max_value, uint32_t mask,
                     uint8_t* __restrict__ moves, unsigned long long* __restrict__ counters)
 {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint32_t seed = seeds[i];
-    uint32_t z = seed;
-    for (uint32_t j = 1; j <= 397; ++j) z = mt_next_seed_word(z, j);            // mt[397]
-    uint32_t x = seed, xn = mt_next_seed_word(seed, 1), idx = 0;                // mt[0], mt[1]
-    uint8_t* row = moves + i * depth;
-    int produced = 0;
-    while (produced < depth && idx < 227) {
-        const uint32_t y = (x & 0x80000000u) | (xn & 0x7fffffffu);
-        uint32_t v = z ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-        v ^= v >> 11;
-        v ^= (v << 7) & 0x9d2c5680u;
-        v ^= (v << 15) & 0xefc60000u;
-        v ^= v >> 18;
-        ++idx;
-        x = xn;
-        xn = mt_next_seed_word(xn, idx + 1);
-        z = mt_next_seed_word(z, idx + 397);                                      // only used while idx + 397 <= 623
-        const uint32_t val = v & mask;
-        if (val <= max_value) row[produced++] = (uint8_t)val;
+    // the CTA's 128 rows are staged in shared memory and leave as one coalesced stream: per-thread byte
+    // stores to rows `depth` bytes apart cost one partial L2 sector write per lane and move
+    extern __shared__ __align__(16) uint8_t s_rows[];
+    const int tid = threadIdx.x;
+    const long long base = (long long)blockIdx.x * kSeedThreads;
+    const long long i = base + tid;
+    if (i < n) {
+        const uint32_t seed = seeds[i];
+        uint32_t z = seed;
+#pragma unroll
+        for (int j = 1; j <= 397; ++j) z = mt_next_seed_word(z, kSeedIndex.v[j]);   // mt[397]: 3 instructions per step
+        uint32_t x = seed, xn = mt_next_seed_word(seed, 1), idx = 0;            // mt[0], mt[1]
+        uint8_t* row = s_rows + tid * depth;
+        int produced = 0;
+        while (produced < depth && idx < 227) {
+            const uint32_t y = (x & 0x80000000u) | (xn & 0x7fffffffu);
+            uint32_t v = z ^ shr<1>(y) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+            v ^= shr<11>(v);
+            v ^= (v << 7) & 0x9d2c5680u;
+            v ^= (v << 15) & 0xefc60000u;
+            v ^= shr<18>(v);
+            ++idx;
+            x = xn;
+            xn = mt_next_seed_word(xn, idx + 1);
+            z = mt_next_seed_word(z, idx + 397);                                  // only used while idx + 397 <= 623
+            const uint32_t val = v & mask;
+            if (val <= max_value) row[produced++] = (uint8_t)val;
+        }
+        if (produced < depth) {
+            for (int k = produced; k < depth; ++k) row[k] = CUBE_NOOP;
+            if (counters) atomicAdd(&counters[3], 1ull);
+        }
     }
-    if (produced < depth) {
-        for (int k = produced; k < depth; ++k) row[k] = CUBE_NOOP;
-        if (counters) atomicAdd(&counters[3], 1ull);
-    }
+    __syncthreads();
+    const long long rows = (n - base) < (long long)kSeedThreads ? (n - base) : (long long)kSeedThreads;
+    const int nbytes = (int)rows * depth;
+    uint8_t* dst = moves + base * depth;                                         // 128 * depth: a multiple of 16
+    const int nvec = nbytes >> 4;
+    for (int v = tid; v < nvec; v += kSeedThreads)
+        reinterpret_cast<int4*>(dst)[v] = reinterpret_cast<const int4*>(s_rows)[v];
+    for (int k = (nvec << 4) + tid; k < nbytes; k += kSeedThreads) dst[k] = s_rows[k];
 }
 
 }  // namespace
@@ -66,8 +105,9 @@ int launch_seeded_moves(int size, const uint32_t* seeds, long long n, int depth,
     const uint32_t max_value = size == 3 ? 11u : 5u;
     uint32_t mask = max_value;                                                   // smallest 2^b - 1 >= max_value
     mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
-    const long long blocks = (n + 127) / 128;
-    seeded_moves_kernel<<<(unsigned)blocks, 128, 0, stream>>>(seeds, n, depth, max_value, mask, moves, counters);
+    const long long blocks = (n + kSeedThreads - 1) / kSeedThreads;
+    seeded_moves_kernel<<<(unsigned)blocks, kSeedThreads, (size_t)kSeedThreads * depth, stream>>>(seeds, n, depth, max_value,
+                                                                                                   mask, moves, counters);
     return (int)cudaGetLastError();
 }
 

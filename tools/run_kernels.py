@@ -45,6 +45,18 @@ def main():
         so = torch.empty(n, dtype=torch.uint8, device=dev)
         rw = torch.empty(n, dtype=torch.float32, device=dev)
         timed("scramble3_d32", lambda: ops.scramble(3, moves, out=st, solved=so, reward=rw), n * d)
+    if which == "seeds3":                          # K0: identically seeded move draws, 8 Mi seeds x depth 30
+        import ctypes
+        from rubiks_cube_solver_b200 import _lib
+        n, d = 8 * 2 ** 20, 30
+        seeds = torch.arange(n, dtype=torch.int32, device=dev)
+        mv = torch.empty((n, d), dtype=torch.uint8, device=dev)
+        lib = _lib.load()
+        stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        timed("seeds3", lambda: lib.cube_moves_from_seeds(3, ctypes.c_void_p(seeds.data_ptr()), n, d,
+                                                          ctypes.c_void_p(mv.data_ptr()), None, stream), n * d)
+        want = ops.moves_from_seeds(3, list(range(1000)), d)
+        assert bool((mv[:1000] == want).all())
     if which in ("scramble2", "all"):
         n, d = 16 * 2 ** 20, 20
         moves = torch.randint(0, 6, (n, d), dtype=torch.uint8, device=dev, generator=gen)
