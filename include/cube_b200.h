@@ -220,6 +220,7 @@ int cube_pipeline_scramble_host(cube_pipeline_t* p, const uint8_t* moves_host, i
  * page of mapped pinned memory that the kernels read and write directly, so a call is one or
  * two launches and one stream synchronisation, with no copy calls: ~20 us instead of ~120 us
  * through device tensors.  Blocking; all buffers are HOST buffers; any out pointer may be NULL.
+ * A handle is bound to the device current at creation and must not be used by two threads at once.
  *   stickers_host      [S]   uint8  in
  *   stickers_out_host  [S]   uint8  out
  *   onehot_u8_host     [D]   uint8  out  (the observation as 0/1 bytes, D = 147 / 480)
