@@ -22,7 +22,8 @@ namespace {
 // shift / xor / multiply chains.  Measured: 8 Mi seeds x depth 30 take 1.3 ms either way (3 390 warp
 // instructions per 32 seeds, ALU pipe 63 %, issue 59 %, `math_pipe_throttle` and `dispatch_stall` on top:
 // profiles/r01_k0_seeded_moves_ncu_summary.json) -- the 397 sequential seed-state steps and ~50 draw
-// iterations of ~35 instructions are what the generator costs; the fused scramble behind it takes 0.18 ms.
+// iterations of ~35 instructions are what the generator costs (1.22 ms after the row stores stopped
+// rebuilding their address per draw); the fused scramble behind it takes 0.18 ms.
 template <int K>
 __device__ __forceinline__ uint32_t shr(uint32_t x)
 {
@@ -63,9 +64,11 @@ seeded_moves_kernel(const uint32_t* __restrict__ seeds, long long n, int depth, 
 #pragma unroll
         for (int j = 1; j <= 397; ++j) z = mt_next_seed_word(z, kSeedIndex.v[j]);   // mt[397]: 3 instructions per step
         uint32_t x = seed, xn = mt_next_seed_word(seed, 1), idx = 0;            // mt[0], mt[1]
-        uint8_t* row = s_rows + tid * depth;
-        int produced = 0;
-        while (produced < depth && idx < 227) {
+        // the row as a 32-bit shared-window address that only ever advances: the generic pointer form made
+        // the compiler rebuild the window base (S2R) for every accepted draw
+        uint32_t p = (uint32_t)__cvta_generic_to_shared(s_rows) + (uint32_t)(tid * depth);
+        const uint32_t end = p + (uint32_t)depth;
+        while (p < end && idx < 227) {
             const uint32_t y = (x & 0x80000000u) | (xn & 0x7fffffffu);
             uint32_t v = z ^ shr<1>(y) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
             v ^= shr<11>(v);
@@ -77,10 +80,13 @@ seeded_moves_kernel(const uint32_t* __restrict__ seeds, long long n, int depth, 
             xn = mt_next_seed_word(xn, idx + 1);
             z = mt_next_seed_word(z, idx + 397);                                  // only used while idx + 397 <= 623
             const uint32_t val = v & mask;
-            if (val <= max_value) row[produced++] = (uint8_t)val;
+            if (val <= max_value) {
+                asm volatile("st.shared.u8 [%0], %1;" ::"r"(p), "r"(val) : "memory");
+                ++p;
+            }
         }
-        if (produced < depth) {
-            for (int k = produced; k < depth; ++k) row[k] = CUBE_NOOP;
+        if (p < end) {
+            for (; p < end; ++p) asm volatile("st.shared.u8 [%0], %1;" ::"r"(p), "r"((uint32_t)CUBE_NOOP) : "memory");
             if (counters) atomicAdd(&counters[3], 1ull);
         }
     }
