@@ -86,6 +86,35 @@ def main():
         control[i] = np.mean([episode(s, d, False, True)[0] for s in SEEDS[:100]])
         print("control (orientation labels 1 <-> 2) depth %2d: %.1f %%" % (d, 100.0 * control[i]), flush=True)
     out["control_solve_rate"] = control
+
+    # the reference's own MCTS (mcts.py, test.py:139-147: up to numMCTSSim = 50 simulations of one tree) with the
+    # checkpoint as its value / policy net -- BASELINE config 5's consumer
+    import importlib
+    import random
+    mcts_mod = importlib.import_module("mcts")
+    cfg = {"mcts": {"numMCTSSim": 50, "cpuct": 1.0, "virtual_loss_const": 150, "value_min": -10.0}, "test": {"cube_size": 2}}
+    cases = [(s, d) for d in (5, 8, 12) for s in range(40)]
+    m_solved, m_sims, m_acts = [], [], []
+    for seed, depth in cases:
+        state = env.reset(seed=seed, scramble_count=depth)
+        random.seed(1000 + seed)
+        tree = mcts_mod.MCTS(model, cfg)
+        result, used = None, 50
+        with torch.no_grad():
+            for k in range(50):
+                result = tree.train(state, env)
+                if result is not None:
+                    used = k + 1
+                    break
+        acts = list(result) if result is not None else []
+        m_solved.append(result is not None)
+        m_sims.append(used)
+        m_acts.append(acts + [-1] * (51 - len(acts)))
+    out["mcts_cases"], out["mcts_solved"] = np.array(cases), np.array(m_solved)
+    out["mcts_n_sims"], out["mcts_actions"] = np.array(m_sims), np.array(m_acts, dtype=np.int8)
+    for d in (5, 8, 12):
+        sel = out["mcts_cases"][:, 1] == d
+        print("reference MCTS (50 simulations) depth %2d: solves %.1f %%" % (d, 100.0 * out["mcts_solved"][sel].mean()), flush=True)
     dst = os.path.join(os.path.dirname(HERE), "tests", "golden", "pin222.npz")
     np.savez_compressed(dst, **out)
     print("wrote", dst, os.path.getsize(dst), "bytes")

@@ -127,3 +127,27 @@ def test_cuda_path_reproduces_the_reference_checkpoints_episodes(pin, mask):
     rate = solved.mean(axis=1)
     assert (rate[:4] == 1.0).all() and rate[4] >= 0.95 and rate[5] >= 0.8
     model.cpu()
+
+
+@pytest.mark.gpu
+def test_batched_mcts_with_the_reference_checkpoint(pin):
+    """BASELINE config 5's consumer end to end: the reference's own mcts.py with the checkpoint as its net
+    (oracle/gen_pin222.py: 50 simulations, 40 seeds at depths 5 / 8 / 12) against BatchedMCTS on the GPU with
+    the same weights and the same per-tree random seeds.  The scores are float32 sums of net outputs, and the
+    GPU's GEMM may round a logit differently from the CPU's, so a few trees may part ways: every returned
+    action list must solve its cube, and the solved flags must agree for at least 90 % of the trees."""
+    from rubiks_cube_solver_b200 import mcts_batch
+    g, model, _ = pin
+    cases = g["mcts_cases"]
+    roots = np.stack([O.scramble(2, np.random.RandomState(int(s)).randint(6, size=(1, int(d))))[0] for s, d in cases])
+    search = mcts_batch.BatchedMCTS(model.cuda(), 2, num_sim=50, cpuct=1.0, virtual_loss_const=150, value_min=-10.0)
+    out = search.run(torch.from_numpy(roots).cuda(), seeds=[1000 + int(s) for s, _ in cases])
+    solved = out["solved"].cpu().numpy()
+    acts, n_act = out["actions"].cpu().numpy(), out["n_actions"].cpu().numpy()
+    for i in np.flatnonzero(solved):
+        end = O.scramble(2, acts[i, :n_act[i]][None].astype(np.int64), init=roots[i:i + 1])
+        assert O.is_solved(2, end)[0]
+    assert (solved == g["mcts_solved"]).mean() >= 0.9
+    same = solved & g["mcts_solved"]
+    assert (out["n_sims"].cpu().numpy()[same] == g["mcts_n_sims"][same]).mean() >= 0.9
+    model.cpu()
