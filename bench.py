@@ -339,7 +339,8 @@ def measure_mcts(torch, dev):
     """test.py's MCTS branch (test.py:139-147: up to numMCTSSim = 50 simulations per cube, config.yaml:29)
     for 65 536 2x2x2 cubes in lock-step through BatchedMCTS (device tree store, one traversal kernel, one leaf batch and one update kernel per
     simulation), beside the reference-semantics per-cube search (oracle/mcts_ref.py) on one host core.
-    Net: DeepCube's 2x2x2 layer shapes (147-512-128-{64-6, 64-1}, pretrained/222model.pt), random init."""
+    Net: DeepCube's 2x2x2 layer shapes (147-512-128-{64-6, 64-1}) with the weights of the reference's
+    pretrained/222model.pt (BASELINE config 5's net) when the fixture tests/golden/pin222.npz is present."""
     import random
     import numpy as np
     from rubiks_cube_solver_b200 import mcts_batch, ops
@@ -366,6 +367,14 @@ def measure_mcts(torch, dev):
 
     torch.manual_seed(1)
     net = Net()
+    weights = "random init"
+    fixture = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tests", "golden", "pin222.npz")
+    if os.path.exists(fixture):                                # the weights of the reference's pretrained/222model.pt
+        g = np.load(fixture)
+        names = {"encoder_net": "enc", "policy_net": "pol", "value_net": "val"}
+        net.load_state_dict({names[k[2:].split(".")[0]] + k[2 + len(k[2:].split(".")[0]):]: torch.from_numpy(g[k])
+                             for k in g.files if k.startswith("w:")})
+        weights = "pretrained/222model.pt (epoch %d, tests/golden/pin222.npz)" % int(g["epoch"])
     gpu_net = Net().to(dev)
     gpu_net.load_state_dict(net.state_dict())
     n_trees, num_sim, depth = 65536, 50, 8
@@ -392,7 +401,7 @@ def measure_mcts(torch, dev):
             cpu_sims += used
     cpu_dt = time.perf_counter() - t0
     return {"simulations_per_s_batched_gpu": sims / dt, "simulations_per_s_reference_semantics_1_core": cpu_sims / cpu_dt,
-            "trees": n_trees, "solved": int(res["solved"].sum()), "ms": dt * 1e3,
+            "trees": n_trees, "solved": int(res["solved"].sum()), "ms": dt * 1e3, "net_weights": weights,
             "note": "one simulation = traverse + leaf expansion (6 children, net value/policy) + back-propagation "
                     "(mcts.py:36-130); 65 536 cubes scrambled 8 deep, 50 simulations each"}
 
