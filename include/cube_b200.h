@@ -182,6 +182,17 @@ int cube_mcts_update(int cube_size, const cube_mcts_tree_t* tree, const uint8_t*
                      const float* policy, float value_min, int sim_index, int8_t* actions_out,
                      int32_t* n_actions, int32_t* n_sims, void* stream);
 
+/* cube_expand with COMPACT CODES instead of the children's one-hot rows: code[row] = the column of the
+ * single 1 of that one-hot row (what argmax over the row gives), KEY = (R + 3) & ~3 bytes per state
+ * (8 / 20), zero-padded.  The batched MCTS keys its tree nodes with them (the reference keys its dict with
+ * np.array2string of the observation, mcts.py:57,105: equal observations <=> equal codes).
+ *   child_codes   [n, A, KEY] uint8  out or NULL
+ *   parent_codes  [n, KEY]    uint8  out or NULL
+ *   parent_onehot [n, R, C]   dtype  out or NULL     children / solved / reward / counters as in cube_expand */
+int cube_expand_codes(int cube_size, const uint8_t* states, int64_t n, uint8_t* children, uint8_t* child_codes,
+                      uint8_t* parent_codes, void* parent_onehot, int dtype, uint8_t* solved, float* reward,
+                      uint64_t* counters, void* stream);
+
 /* state_to_sim_state (cube_env.py:154-175 + py222 getStickers): one-hot [n, 7, 21] of
  * `dtype` -> sticker rows [n, 24].  2x2x2 only: for cube_size 3 the reference raises
  * NotImplementedError (cube_env.py:171-172) and this returns CUBE_ERR_SIZE. */

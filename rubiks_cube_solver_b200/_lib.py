@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_PKG, "libcube_b200.so")
 
 SYMBOLS = (
     "cube_abi_version", "cube_last_error", "cube_sm_count", "cube_set_reserved_sms", "cube_moves_from_seeds", "cube_scramble", "cube_step", "cube_walk",
-    "cube_solved", "cube_encode", "cube_expand", "cube_adi_targets", "cube_mcts_traverse", "cube_mcts_update", "cube_decode", "cube_validate_actions",
+    "cube_solved", "cube_encode", "cube_expand", "cube_expand_codes", "cube_adi_targets", "cube_mcts_traverse", "cube_mcts_update", "cube_decode", "cube_validate_actions",
     "cube_pipeline_create", "cube_pipeline_destroy", "cube_pipeline_scramble_host",
     "cube_env_host_create", "cube_env_host_destroy", "cube_env_host_step", "cube_env_host_scramble", "cube_env_host_encode",
 )
@@ -60,6 +60,7 @@ def load():
     lib.cube_solved.argtypes = [ci, vp, i64, vp, vp, vp, vp]
     lib.cube_encode.argtypes = [ci, vp, i64, vp, ci, vp]
     lib.cube_expand.argtypes = [ci, vp, i64, vp, vp, vp, ci, vp, vp, vp, vp]
+    lib.cube_expand_codes.argtypes = [ci, vp, i64, vp, vp, vp, vp, ci, vp, vp, vp, vp]
     lib.cube_adi_targets.argtypes = [ci, vp, vp, vp, vp, vp, ci, i64, vp, vp, vp, vp]
     lib.cube_mcts_traverse.argtypes = [ci, vp, ctypes.c_float, ci, vp]
     lib.cube_mcts_update.argtypes = [ci, vp, vp, vp, vp, vp, vp, ctypes.c_float, ci, vp, vp, vp, vp]

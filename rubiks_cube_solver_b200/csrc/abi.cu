@@ -200,6 +200,19 @@ int cube_expand(int cube_size, const uint8_t* states, int64_t n, uint8_t* childr
                                                  (cudaStream_t)stream));
 }
 
+int cube_expand_codes(int cube_size, const uint8_t* states, int64_t n, uint8_t* children, uint8_t* child_codes,
+                      uint8_t* parent_codes, void* parent_onehot, int dtype, uint8_t* solved, float* reward,
+                      uint64_t* counters, void* stream)
+{
+    CUBE_CHECK_SIZE("cube_expand_codes");
+    if (n < 0 || dtype < 0 || dtype > 2 || (n > 0 && !states)) return fail(CUBE_ERR_ARG, "cube_expand_codes");
+    if (misaligned(states) || misaligned(children) || misaligned(parent_onehot))
+        return fail(CUBE_ERR_ALIGN, "cube_expand_codes");
+    CUBE_DONE("cube_expand_codes", cube::launch_expand_codes(cube_size, states, n, children, child_codes, parent_codes,
+                                                             parent_onehot, dtype, solved, reward,
+                                                             (unsigned long long*)counters, (cudaStream_t)stream));
+}
+
 int cube_decode(int cube_size, const void* onehot, int dtype, int64_t n, uint8_t* states_out, void* stream)
 {
     CUBE_CHECK_SIZE("cube_decode");

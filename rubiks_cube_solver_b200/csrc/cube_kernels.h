@@ -27,6 +27,12 @@ int launch_expand(int size, const uint8_t* states, long long n, uint8_t* childre
                   void* parent_onehot, int dtype, uint8_t* solved, float* reward,
                   unsigned long long* counters, cudaStream_t stream);
 
+// the same expansion with compact codes (column of the 1 of every one-hot row, (R + 3) & ~3 bytes per state,
+// zero-padded) for the children and / or the parents instead of the children's one-hot rows
+int launch_expand_codes(int size, const uint8_t* states, long long n, uint8_t* children, uint8_t* child_codes,
+                        uint8_t* parent_codes, void* parent_onehot, int dtype, uint8_t* solved, float* reward,
+                        unsigned long long* counters, cudaStream_t stream);
+
 int launch_validate(int size, const uint8_t* actions, long long count, unsigned long long* counters,
                     cudaStream_t stream);
 

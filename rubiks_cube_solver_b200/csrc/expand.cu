@@ -55,11 +55,13 @@ __global__ void __launch_bounds__(kThreads, 6)
 expand_kernel(const uint8_t* __restrict__ states, long long n, uint8_t* __restrict__ children,
               uint8_t* __restrict__ child_onehot, uint8_t* __restrict__ parent_onehot,
               uint8_t* __restrict__ solved, float* __restrict__ reward,
-              unsigned long long* __restrict__ counters)
+              unsigned long long* __restrict__ counters, uint8_t* __restrict__ child_codes,
+              uint8_t* __restrict__ parent_codes)
 {
     using G = CubeGeom<SIZE>;
     constexpr int S = G::S, A = G::A, R = G::R, C = G::C;
     constexpr int ESIZE = OneHot<DTYPE>::ESIZE;
+    constexpr int KEY = (R + 3) & ~3;                     // bytes of a code row: the R column indices, zero-padded to words
     constexpr int kParents = ExpandTile<SIZE>::kParents;
     constexpr int kRows = kParents * A;
 
@@ -83,7 +85,8 @@ expand_kernel(const uint8_t* __restrict__ states, long long n, uint8_t* __restri
         s_lut[1][tid] = (SIZE == 3) ? kEdgeCol3[tid] : 0;
     }
     if (tid == 0) s_solved_count = 0;
-    const bool need_children = children || child_onehot || solved || reward || counters;
+    const bool need_children = children || child_onehot || solved || reward || counters || child_codes;
+    const bool need_parent_cols = parent_onehot || parent_codes;
 
     const long long n_tiles = (n + kParents - 1) / kParents;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -120,7 +123,7 @@ expand_kernel(const uint8_t* __restrict__ states, long long n, uint8_t* __restri
         __syncthreads();
 
         // one-hot columns: child rows, then parent rows
-        const int n_items = (need_children ? rows : 0) + (parent_onehot ? cnt : 0);
+        const int n_items = (need_children ? rows : 0) + (need_parent_cols ? cnt : 0);
         for (int it = tid; it < n_items * R; it += kThreads) {
             const int r = it / R, slot = it - r * R;
             const bool is_child = need_children && r < rows;
@@ -155,6 +158,24 @@ expand_kernel(const uint8_t* __restrict__ states, long long n, uint8_t* __restri
             int4* dst = reinterpret_cast<int4*>(children + byte0);
             for (int i = tid; i < nvec; i += kThreads) __stcs(dst + i, reinterpret_cast<const int4*>(s_child)[i]);
             for (int i = (nvec << 4) + tid; i < nbytes; i += kThreads) children[byte0 + i] = s_child[i];
+        }
+        // compact codes: the column of the single 1 of every one-hot row (what argmax over the row gives; a
+        // 2x2x2 row without a 1 reads 0 like argmax), KEY bytes per state
+        if (child_codes) {
+            uint8_t* dst = child_codes + base * A * KEY;
+            for (int i = tid; i < rows * KEY; i += kThreads) {
+                const int r = i / KEY, k = i - r * KEY;
+                const uint8_t c = k < R ? s_colc[r * R + k] : (uint8_t)0;
+                dst[i] = c == 255 ? (uint8_t)0 : c;
+            }
+        }
+        if (parent_codes) {
+            uint8_t* dst = parent_codes + base * KEY;
+            for (int i = tid; i < cnt * KEY; i += kThreads) {
+                const int r = i / KEY, k = i - r * KEY;
+                const uint8_t c = k < R ? s_colp[r * R + k] : (uint8_t)0;
+                dst[i] = c == 255 ? (uint8_t)0 : c;
+            }
         }
         if (child_onehot) {
             uint8_t* dst = child_onehot + base * A * (long long)(G::D * ESIZE);
@@ -248,9 +269,10 @@ encode_kernel(const uint8_t* __restrict__ states, long long n, uint8_t* __restri
 
 template <int SIZE, int DTYPE>
 int launch_one(const uint8_t* states, long long n, uint8_t* children, void* child_onehot, void* parent_onehot,
-               uint8_t* solved, float* reward, unsigned long long* counters, cudaStream_t stream)
+               uint8_t* solved, float* reward, unsigned long long* counters, cudaStream_t stream,
+               uint8_t* child_codes = nullptr, uint8_t* parent_codes = nullptr)
 {
-    if (!children && !child_onehot && !solved && !reward && !counters) {
+    if (!children && !child_onehot && !solved && !reward && !counters && !child_codes && !parent_codes) {
         if (!parent_onehot) return 0;
         const long long tiles = (n + kEncodeRows - 1) / kEncodeRows;
         encode_kernel<SIZE, DTYPE><<<(unsigned)tiles, kThreads, 0, stream>>>(states, n, (uint8_t*)parent_onehot);
@@ -270,7 +292,8 @@ int launch_one(const uint8_t* states, long long n, uint8_t* children, void* chil
         done = true;
     }
     kern<<<(unsigned)grid, kThreads, 0, stream>>>(states, n, children, (uint8_t*)child_onehot,
-                                                  (uint8_t*)parent_onehot, solved, reward, counters);
+                                                  (uint8_t*)parent_onehot, solved, reward, counters, child_codes,
+                                                  parent_codes);
     return (int)cudaGetLastError();
 }
 
@@ -321,6 +344,23 @@ int launch_expand(int size, const uint8_t* states, long long n, uint8_t* childre
     if (size == SZ && dtype == DT)                                                                       \
         return launch_one<SZ, DT>(states, n, children, child_onehot, parent_onehot, solved, reward,      \
                                   counters, stream);
+    CUBE_EXPAND_CASE(3, 0) CUBE_EXPAND_CASE(3, 1) CUBE_EXPAND_CASE(3, 2)
+    CUBE_EXPAND_CASE(2, 0) CUBE_EXPAND_CASE(2, 1) CUBE_EXPAND_CASE(2, 2)
+#undef CUBE_EXPAND_CASE
+    return CUBE_ERR_ARG;
+}
+
+// expansion with compact codes instead of the children's one-hot rows (the MCTS tree's keys): always the
+// generic kernel, whose column bytes ARE the codes
+int launch_expand_codes(int size, const uint8_t* states, long long n, uint8_t* children, uint8_t* child_codes,
+                        uint8_t* parent_codes, void* parent_onehot, int dtype, uint8_t* solved, float* reward,
+                        unsigned long long* counters, cudaStream_t stream)
+{
+    if (n == 0) return 0;
+#define CUBE_EXPAND_CASE(SZ, DT)                                                                         \
+    if (size == SZ && dtype == DT)                                                                       \
+        return launch_one<SZ, DT>(states, n, children, nullptr, parent_onehot, solved, reward, counters,  \
+                                  stream, child_codes, parent_codes);
     CUBE_EXPAND_CASE(3, 0) CUBE_EXPAND_CASE(3, 1) CUBE_EXPAND_CASE(3, 2)
     CUBE_EXPAND_CASE(2, 0) CUBE_EXPAND_CASE(2, 1) CUBE_EXPAND_CASE(2, 2)
 #undef CUBE_EXPAND_CASE

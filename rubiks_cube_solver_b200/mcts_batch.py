@@ -149,10 +149,11 @@ class BatchedMCTS(object):
                     break
                 _lib.check(lib.cube_mcts_traverse(self.cube_size, ctypes.byref(tree), self.cpuct, self.loss_const, stream),
                            "cube_mcts_traverse")
-                res = ops.expand(self.cube_size, T["leaf_state"], dtype=torch.uint8, want_child_onehot=True,
-                                 want_parent_onehot=True)
-                leaf_key = self._codes(res["parent_onehot"])
-                child_key = self._codes(res["child_onehot"])
+                # the node keys come out of the expansion kernel as compact codes (cube_expand_codes), the leaf's
+                # observation directly in the net's dtype: no one-hot rows of the children, no argmax passes
+                direct = self.obs_dtype in ops.ONEHOT_DTYPES
+                res = ops.expand_codes(self.cube_size, T["leaf_state"], parent_dtype=self.obs_dtype if direct else torch.uint8)
+                leaf_key, child_key = res["parent_codes"], res["child_codes"]
                 value, logits = self.model(res["parent_onehot"].to(mdev).to(self.obs_dtype))
                 value = value.float().reshape(-1).to(dev).contiguous()
                 policy = torch.nn.functional.softmax(logits.float(), dim=-1).to(dev).contiguous()

@@ -198,6 +198,35 @@ def expand(cube_size, states, dtype=torch.bfloat16, want_children=False, want_ch
                 reward=reward)
 
 
+def key_bytes(cube_size):
+    """Bytes of a compact code row (cube_expand_codes): the R column indices, zero-padded to whole words."""
+    return (STATE_DIM[cube_size][0] + 3) & ~3
+
+
+def expand_codes(cube_size, states, parent_dtype=None, want_children=False, counters=None):
+    """All A children of every state with COMPACT CODES instead of one-hot rows (C ABI cube_expand_codes):
+    code[row] = column of the 1 of that one-hot row = `onehot.argmax(-1)`, zero-padded to key_bytes.
+
+    Returns dict(child_codes [N,A,KEY] uint8, parent_codes [N,KEY] uint8, parent_onehot [N,R,C] of
+    `parent_dtype` | None, children [N,A,S] | None, solved [N,A] uint8, reward [N,A] float32)."""
+    s, a, (r, c) = _geom(cube_size)
+    states = _require_cuda(states, "states")
+    n, dev, key = states.shape[0], states.device, key_bytes(cube_size)
+    children = torch.empty((n, a, s), dtype=torch.uint8, device=dev) if want_children else None
+    child_codes = torch.empty((n, a, key), dtype=torch.uint8, device=dev)
+    parent_codes = torch.empty((n, key), dtype=torch.uint8, device=dev)
+    parent_onehot = torch.empty((n, r, c), dtype=parent_dtype, device=dev) if parent_dtype is not None else None
+    solved = torch.empty((n, a), dtype=torch.uint8, device=dev)
+    reward = torch.empty((n, a), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().cube_expand_codes(
+            cube_size, _ptr(states), n, _ptr(children), _ptr(child_codes), _ptr(parent_codes), _ptr(parent_onehot),
+            ONEHOT_DTYPES[parent_dtype] if parent_dtype is not None else _lib.DTYPE_U8, _ptr(solved), _ptr(reward),
+            _ptr(counters), _stream(dev)), "cube_expand_codes")
+    return dict(child_codes=child_codes, parent_codes=parent_codes, parent_onehot=parent_onehot, children=children,
+                solved=solved, reward=reward)
+
+
 def moves_from_seeds(cube_size, seeds, depth, device=None):
     """moves[i] = np.random.RandomState(seeds[i]).randint(A, size=depth) for every seed, drawn on the
     device (C ABI cube_moves_from_seeds): the scramble of reset(seed, depth), cube_env.py:62-65.

@@ -809,3 +809,24 @@ def test_scramble_many_tiles_per_warp(size, depth):
     want, ws, wr, _ = C.scramble(size, moves)
     assert (states.cpu().numpy() == want).all()
     assert (solved.cpu().numpy().astype(bool) == ws).all() and (reward.cpu().numpy() == wr).all()
+
+
+@pytest.mark.parametrize("size", SIZES)
+@pytest.mark.parametrize("n", (1, 15, 16, 17, 1000))
+def test_expand_codes_equal_argmax_of_the_onehot_rows(size, n):
+    """cube_expand_codes: compact codes = argmax over every one-hot row of cube_expand's output, zero-padded;
+    children, verdicts and the parent's one-hot identical to cube_expand's."""
+    rng = np.random.RandomState(n + size)
+    A = T.N_ACTIONS[size]
+    states = cu(O.scramble(size, rng.randint(A, size=(n, 9))))
+    states[0] = cu(O.scramble(size, np.zeros((1, 0), dtype=np.int64)))[0]          # solved parent: its children are one move away
+    want = ops.expand(size, states, dtype=torch.uint8, want_children=True, want_parent_onehot=True)
+    got = ops.expand_codes(size, states, parent_dtype=torch.float32, want_children=True)
+    r, key = T.STATE_DIM[size][0], ops.key_bytes(size)
+    assert got["child_codes"].shape == (n, A, key) and got["parent_codes"].shape == (n, key)
+    assert (got["child_codes"][..., :r] == want["child_onehot"].argmax(-1).to(torch.uint8)).all()
+    assert (got["parent_codes"][..., :r] == want["parent_onehot"].argmax(-1).to(torch.uint8)).all()
+    assert (got["child_codes"][..., r:] == 0).all() and (got["parent_codes"][..., r:] == 0).all()
+    assert (got["children"] == want["children"]).all() and (got["solved"] == want["solved"]).all()
+    assert (got["reward"] == want["reward"]).all()
+    assert (got["parent_onehot"] == want["parent_onehot"].float()).all()
