@@ -14,7 +14,11 @@
  *     (py333.py:3-19; py222), row-major [n, S]; actions are uint8 indices in the
  *     order of cube_env.py:24-28.
  *   - every pointer is a DEVICE pointer unless the name ends in _host; arrays
- *     are contiguous and their base must be 16-byte aligned (CUBE_ERR_ALIGN).
+ *     are contiguous.  Sticker rows, one-hot buffers and cube_scramble's move
+ *     array must start on a 16-byte boundary, float / int32 arrays on their
+ *     natural 4 bytes (CUBE_ERR_ALIGN otherwise); action / move bytes of
+ *     cube_step / cube_walk and the solved flags may start anywhere (a sliced
+ *     buffer that is not 16- / 8- / 4-byte aligned takes a byte-wise kernel).
  *   - calls are asynchronous on `stream` (a cudaStream_t, may be NULL), never
  *     allocate, never synchronise, keep no state between calls and are
  *     re-entrant.  Return value: 0, a negative CUBE_ERR_*, or a positive
@@ -40,7 +44,7 @@
 extern "C" {
 #endif
 
-#define CUBE_ABI_VERSION 1
+#define CUBE_ABI_VERSION 2   /* 2: cube_mcts_tree_t memo fields, cube_mcts_update n_active, new entry points */
 
 #define CUBE_OK 0
 #define CUBE_ERR_SIZE (-1)
@@ -89,6 +93,18 @@ int cube_moves_from_seeds(int cube_size, const uint32_t* seeds, int64_t n, int d
  * depth >= 0 (depth 0 returns solved cubes). */
 int cube_scramble(int cube_size, const uint8_t* moves, int64_t n, int depth, uint8_t* states_out,
                   uint8_t* solved, float* reward, uint64_t* counters, void* stream);
+
+/* Every prefix of every scramble, in ONE launch -- the parents of an ADI batch: get_random_samples
+ * (cube_env.py:187-194) emits a sample after EVERY move of every cube, cube by cube.
+ *   moves      [n, depth]    uint8  in
+ *   states_out [n, depth, S] uint8  out  states_out[i, k] = sticker row after moves[i, 0..k]  (cube-major:
+ *                                        the order in which the reference appends to its replay buffer)
+ *   solved     [n, depth]    uint8  out or NULL  isSolved of every prefix
+ * counters[0] += solved prefixes, [1] += n * depth.  depth <= cube_scramble_prefixes_max_depth(cube_size)
+ * (131 / 289: a tile of 32 cubes x depth rows is staged in shared memory), else CUBE_ERR_ARG. */
+int cube_scramble_prefixes(int cube_size, const uint8_t* moves, int64_t n, int depth, uint8_t* states_out,
+                           uint8_t* solved, uint64_t* counters, void* stream);
+int cube_scramble_prefixes_max_depth(int cube_size);
 
 /* One transition on resident states -- CubeEnv.step (cube_env.py:71-111):
  * states[i] <- states[i][moveDefs[actions[i]]], then solved / reward.  In place. */
@@ -164,7 +180,13 @@ typedef struct cube_mcts_tree {
     uint8_t* path_action;                 /* [B, path_cap]   out: actions of the last traversal          */
     int32_t* path_len;                    /* [B]             out                                         */
     uint8_t* leaf_state;                  /* [B, S]          out: sticker row of the leaf that was reached */
-    int32_t* flags;                       /* [1]  |= 1 path_cap exceeded, 2 rand_table exhausted, 4 n_slots exceeded */
+    int32_t* flags;                       /* [1]  |= 1 path_cap exceeded, 2 rand_table exhausted, 4 n_slots exceeded,
+                                           *            8 rand_table holds an action >= A (taken as 0)           */
+    /* memoised dict lookups (the library's own scratch; child_slot starts at 255, the rest at 0) */
+    uint8_t* child_slot;                  /* [B, M, A]       slot of the child's node once a traversal found it, 255 = unknown */
+    uint8_t* child_seen;                  /* [B, M, A]       leading node slots already compared with that child's key, no match */
+    uint8_t* miss_key;                    /* [B, KEY]        out: the key the last traversal failed to find         */
+    int32_t* miss_seen;                   /* [B]             out: node slots it was compared with                   */
 } cube_mcts_tree_t;
 
 /* MCTS.traverse (mcts.py:52-81) for every active tree: from the root to the first key that is not in
@@ -176,11 +198,12 @@ int cube_mcts_traverse(int cube_size, const cube_mcts_tree_t* tree, float cpuct,
  * policy [B, A] from the network; W = value_min, N = L = 0), back-propagate along the path
  * (W = max(W, value), L -= 150, N += 1: mcts.py:122-129) and, if a child of the new leaf is solved,
  * write path actions + that child to actions_out [B, path_cap + 1] (int8), n_actions [B],
- * n_sims [B] = sim_index + 1 and clear `active`. */
+ * n_sims [B] = sim_index + 1 and clear `active`.  n_active (int32 on the device, or NULL) += trees that are
+ * still searching after this simulation, so a caller can stop early without reading `active` back. */
 int cube_mcts_update(int cube_size, const cube_mcts_tree_t* tree, const uint8_t* leaf_key,
                      const uint8_t* child_key_new, const uint8_t* child_done_new, const float* value,
                      const float* policy, float value_min, int sim_index, int8_t* actions_out,
-                     int32_t* n_actions, int32_t* n_sims, void* stream);
+                     int32_t* n_actions, int32_t* n_sims, int32_t* n_active, void* stream);
 
 /* cube_expand with COMPACT CODES instead of the children's one-hot rows: code[row] = the column of the
  * single 1 of that one-hot row (what argmax over the row gives), KEY = (R + 3) & ~3 bytes per state

@@ -2,30 +2,39 @@
 (gym-cube/gym_cube/envs/cube_env.py:177-252) for many cubes at once.
 
 The reference emits one sample after EVERY move of every scramble (cube_env.py:190-194),
-so the parents of an ADI batch are all scramble prefixes.  Here the prefixes are produced
-step by step on the device (K2, one launch per depth level, step-major so each level is a
-contiguous slab), expanded into all children + their one-hot rows by K3, evaluated by the
-caller's network in one batch, and reduced to (target_value, target_policy, error) by kernel K4
-(C ABI cube_adi_targets) with the reference's rules: first solved child a -> (1.0, a) (cube_env.py:217-220), otherwise
-max_a(V(child_a) + (-1.0)) with the first maximum winning (cube_env.py:240-246), and
-error = |V(state) - target| * depth**(-temperature) in float64 (cube_env.py:247-251).
+so the parents of an ADI batch are all scramble prefixes, cube by cube.  Here
+
+* ONE launch writes every prefix of every scramble, already cube-major (C ABI
+  cube_scramble_prefixes) -- round 1 issued one cube_walk launch per depth level and then
+  transposed five tensors from step-major to cube-major;
+* the parents are expanded chunk by chunk into all children + their one-hot rows (K3,
+  cube_expand) IN THE DTYPE THE NET COMPUTES IN (a bf16 DeepCube reads K3's buffer as it is, no
+  `.float()` pass), and every chunk is evaluated by the caller's network right away, while its
+  one-hot rows are still in the 126 MB L2: the [P, A, D] batch (48 GB in bf16 for 4 Mi parents)
+  never exists as a whole and never round-trips through HBM;
+* kernel K4 (C ABI cube_adi_targets) reduces child values to (target_value, target_policy,
+  error) with the reference's rules: first solved child a -> (1.0, a) (cube_env.py:217-220),
+  otherwise max_a(V(child_a) + (-1.0)) with the first maximum winning (cube_env.py:240-246), and
+  error = |V(state) - target| * depth**(-temperature) in float64 (cube_env.py:247-251).
 """
 import torch
 
 from . import ops
+from ._timing import Phases as _Phases
 
 
 def scramble_prefixes(cube_size, moves):
-    """All prefix states of every scramble.
+    """All prefix states of every scramble, cube-major: [n, depth, S] uint8 with
+    out[i, k] = state of cube i after moves[i, 0..k] (cube_env.py:187-191).
 
-    moves [n, depth] uint8 (CUDA).  Returns (trail [depth, n_pad, S] uint8 step-major,
-    n_pad) where n_pad rounds n up to a multiple of 16 with no-op rows, so every level is
-    a 16-byte aligned slab.
-    """
+    One launch (cube_scramble_prefixes) up to depth 131 (3x3x3) / 289 (2x2x2); deeper scrambles
+    fall back to one cube_walk launch per level."""
     n, depth = moves.shape
     dev = moves.device
-    n_pad = (n + 15) // 16 * 16
     s = ops.N_STICKERS[cube_size]
+    if depth <= ops.prefixes_max_depth(cube_size):
+        return ops.scramble_prefixes(cube_size, moves.contiguous())[0]
+    n_pad = (n + 15) // 16 * 16                      # every level a 16-byte aligned slab
     moves_t = torch.full((depth, n_pad), 12, dtype=torch.uint8, device=dev)      # 12 = no-op row
     moves_t[:, :n] = moves.t()
     trail = torch.empty((depth, n_pad, s), dtype=torch.uint8, device=dev)
@@ -33,7 +42,7 @@ def scramble_prefixes(cube_size, moves):
     for k in range(depth):
         ops.walk(cube_size, prev, moves_t[k], out=trail[k])
         prev = trail[k]
-    return trail, n_pad
+    return trail[:, :n].transpose(0, 1).contiguous()
 
 
 def assemble_targets(cube_size, child_values, solved, parent_values, depth_of_row, temperature):
@@ -43,43 +52,71 @@ def assemble_targets(cube_size, child_values, solved, parent_values, depth_of_ro
     return ops.adi_targets(cube_size, child_values, solved, parent_values, depth_of_row, temperature)
 
 
+def param_dtype(model):
+    """The dtype the net computes in: that of its first floating-point parameter (None: no parameters)."""
+    for p in model.parameters() if hasattr(model, "parameters") else ():
+        if p.is_floating_point():
+            return p.dtype
+    return None
+
+
+def model_dtype(model, default=torch.float32):
+    """The one-hot dtype to write for `model`: its own dtype when K3 can write it (bf16 / f32), else `default`."""
+    d = param_dtype(model)
+    return d if d in ops.ONEHOT_DTYPES else default
+
+
 @torch.no_grad()
-def generate_samples(cube_size, moves, model, temperature, model_device=None, onehot_dtype=torch.float32,
-                     forward_chunk=1 << 16):
+def generate_samples(cube_size, moves, model, temperature, model_device=None, onehot_dtype=None,
+                     forward_chunk=8192, timers=None):
     """ADI samples for every prefix of every scramble in `moves` ([n, depth] uint8, CUDA).
 
-    `model(x)` must return (value [B,1], policy) like DeepCube.forward (model.py:31-45).
-    Results are cube-major (cube 0 depth 1..d, cube 1 ...), the order in which the
-    reference appends to its replay buffer.
+    `model(x)` must return (value [B,1], policy) like DeepCube.forward (model.py:31-45).  `onehot_dtype`
+    defaults to the dtype the model computes in (bf16 / f32), so the net reads K3's buffer directly.
+    `forward_chunk` = parents per expand -> forward chunk (x A children x D elements: 8192 3x3x3 parents in
+    bf16 are 94 MB of one-hot rows, consumed from L2).  Results are cube-major (cube 0 depth 1..d, cube 1
+    ...), the order in which the reference appends to its replay buffer.  `timers`: an optional dict that
+    receives the milliseconds spent per phase (prefixes / expand / net / targets), device-timed.
     """
     n, depth = moves.shape
     dev = moves.device
     a = ops.N_ACTIONS[cube_size]
     r, c = ops.STATE_DIM[cube_size]
-    trail, n_pad = scramble_prefixes(cube_size, moves)
-    parents = trail.view(depth * n_pad, -1)
-    res = ops.expand(cube_size, parents, dtype=onehot_dtype, want_parent_onehot=True)
-    p = parents.shape[0]
+    if onehot_dtype is None:
+        onehot_dtype = model_dtype(model)
     mdev = dev if model_device is None else torch.device(model_device)
+    in_dtype = param_dtype(model)                                         # cast only when the net needs it
+    phase = _Phases(timers, dev)
 
-    def values_of(x):
-        out = []
-        for i in range(0, x.shape[0], forward_chunk):
-            v, _ = model(x[i:i + forward_chunk].to(mdev).float())
-            out.append(v.reshape(-1).to(dev))
-        return torch.cat(out)
+    def value_of(x):
+        x = x.to(mdev)
+        if in_dtype is not None and x.dtype != in_dtype:
+            x = x.to(in_dtype)
+        v, _ = model(x)
+        return v.reshape(-1).float().to(dev)
 
-    child_v = values_of(res["child_onehot"].view(p * a, r, c)).view(p, a)
-    parent_v = values_of(res["parent_onehot"])
-    depth_of_row = torch.arange(1, depth + 1, device=dev).repeat_interleave(n_pad)
-    tv, tp, err = assemble_targets(cube_size, child_v, res["solved"], parent_v, depth_of_row, temperature)
-
-    # step-major (k, cube) -> cube-major (cube, k), dropping the padding cubes
-    def cube_major(t):
-        return t.view(depth, n_pad, *t.shape[1:])[:, :n].transpose(0, 1).reshape(n * depth, *t.shape[1:])
-
-    state_u8 = cube_major(ops.encode(cube_size, parents, dtype=torch.uint8))
-    return dict(state_u8=state_u8, stickers=cube_major(parents), target_value=cube_major(tv),
-                target_policy=cube_major(tp), error=cube_major(err),
-                scramble_count=cube_major(depth_of_row), final_stickers=trail[depth - 1, :n],
-                child_solved=cube_major(res["solved"]))
+    with phase("prefixes_ms"):
+        trail = scramble_prefixes(cube_size, moves)                       # [n, depth, S]
+    parents = trail.view(n * depth, -1)
+    p = parents.shape[0]
+    chunk = max(16, int(forward_chunk) // 16 * 16)                        # slices stay 16-byte aligned
+    state = torch.empty((p, r, c), dtype=onehot_dtype, device=dev)        # the samples' `state`: the parents' one-hot
+    child_solved = torch.empty((p, a), dtype=torch.uint8, device=dev)
+    child_v = torch.empty((p, a), dtype=torch.float32, device=dev)
+    parent_v = torch.empty(p, dtype=torch.float32, device=dev)
+    buf = torch.empty((min(chunk, p), a, r, c), dtype=onehot_dtype, device=dev)
+    for i in range(0, p, chunk):
+        cnt = min(chunk, p - i)
+        with phase("expand_ms"):
+            ops.expand(cube_size, parents[i:i + cnt], dtype=onehot_dtype, child_onehot=buf[:cnt],
+                       parent_onehot=state[i:i + cnt], solved=child_solved[i:i + cnt], want_reward=False)
+        with phase("net_ms"):
+            child_v[i:i + cnt] = value_of(buf[:cnt].view(cnt * a, r, c)).view(cnt, a)
+            parent_v[i:i + cnt] = value_of(state[i:i + cnt])
+    with phase("targets_ms"):
+        depth_of_row = torch.arange(1, depth + 1, device=dev, dtype=torch.int32).repeat(n)
+        tv, tp, err = assemble_targets(cube_size, child_v, child_solved, parent_v, depth_of_row, temperature)
+    phase.finish()
+    return dict(state=state, stickers=parents, target_value=tv, target_policy=tp, error=err,
+                scramble_count=depth_of_row.long(), final_stickers=trail[:, depth - 1], child_solved=child_solved,
+                child_values=child_v, parent_values=parent_v)

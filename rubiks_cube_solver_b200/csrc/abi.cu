@@ -27,6 +27,7 @@ int fail(int code, const char* what)
 }
 
 inline bool misaligned(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) != 0; }
+inline bool misaligned4(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 3u) != 0; }   // float / int32 arrays
 
 #define CUBE_CHECK_SIZE(fn) if (cube_size != 2 && cube_size != 3) return fail(CUBE_ERR_SIZE, fn)
 #define CUBE_DONE(fn, rc) do { int rc_ = (rc); return rc_ ? fail(rc_, fn) : 0; } while (0)
@@ -96,9 +97,26 @@ int cube_scramble(int cube_size, const uint8_t* moves, int64_t n, int depth, uin
 {
     CUBE_CHECK_SIZE("cube_scramble");
     if (n < 0 || depth < 0 || (n > 0 && (!states_out || (depth > 0 && !moves)))) return fail(CUBE_ERR_ARG, "cube_scramble");
-    if (misaligned(moves) || misaligned(states_out)) return fail(CUBE_ERR_ALIGN, "cube_scramble");
+    if (misaligned(moves) || misaligned(states_out) || misaligned4(reward)) return fail(CUBE_ERR_ALIGN, "cube_scramble");
     CUBE_DONE("cube_scramble", cube::launch_scramble(cube_size, moves, n, depth, states_out, solved, reward,
                                                      (unsigned long long*)counters, (cudaStream_t)stream));
+}
+
+int cube_scramble_prefixes_max_depth(int cube_size)
+{
+    CUBE_CHECK_SIZE("cube_scramble_prefixes_max_depth");
+    return cube::prefix_max_depth(cube_size);
+}
+
+int cube_scramble_prefixes(int cube_size, const uint8_t* moves, int64_t n, int depth, uint8_t* states_out,
+                           uint8_t* solved, uint64_t* counters, void* stream)
+{
+    CUBE_CHECK_SIZE("cube_scramble_prefixes");
+    if (n < 0 || depth < 0 || depth > cube::prefix_max_depth(cube_size) || (n > 0 && depth > 0 && (!moves || !states_out)))
+        return fail(CUBE_ERR_ARG, "cube_scramble_prefixes");
+    if (misaligned(moves) || misaligned(states_out)) return fail(CUBE_ERR_ALIGN, "cube_scramble_prefixes");
+    CUBE_DONE("cube_scramble_prefixes", cube::launch_prefixes(cube_size, moves, n, depth, states_out, solved,
+                                                              (unsigned long long*)counters, (cudaStream_t)stream));
 }
 
 int cube_step(int cube_size, uint8_t* states, const uint8_t* actions, int64_t n, uint8_t* solved,
@@ -106,7 +124,7 @@ int cube_step(int cube_size, uint8_t* states, const uint8_t* actions, int64_t n,
 {
     CUBE_CHECK_SIZE("cube_step");
     if (n < 0 || (n > 0 && (!states || !actions))) return fail(CUBE_ERR_ARG, "cube_step");
-    if (misaligned(states)) return fail(CUBE_ERR_ALIGN, "cube_step");
+    if (misaligned(states) || misaligned4(reward)) return fail(CUBE_ERR_ALIGN, "cube_step");
     CUBE_DONE("cube_step", cube::launch_walk(cube_size, states, actions, n, 1, states, solved, reward,
                                              (unsigned long long*)counters, (cudaStream_t)stream));
 }
@@ -117,7 +135,7 @@ int cube_walk(int cube_size, const uint8_t* states_in, const uint8_t* moves, int
     CUBE_CHECK_SIZE("cube_walk");
     if (n < 0 || depth < 0 || (n > 0 && (!states_in || !states_out || (depth > 0 && !moves))))
         return fail(CUBE_ERR_ARG, "cube_walk");
-    if (misaligned(states_in) || misaligned(states_out)) return fail(CUBE_ERR_ALIGN, "cube_walk");
+    if (misaligned(states_in) || misaligned(states_out) || misaligned4(reward)) return fail(CUBE_ERR_ALIGN, "cube_walk");
     CUBE_DONE("cube_walk", cube::launch_walk(cube_size, states_in, moves, n, depth, states_out, solved, reward,
                                              (unsigned long long*)counters, (cudaStream_t)stream));
 }
@@ -127,7 +145,7 @@ int cube_solved(int cube_size, const uint8_t* states, int64_t n, uint8_t* solved
 {
     CUBE_CHECK_SIZE("cube_solved");
     if (n < 0 || (n > 0 && !states)) return fail(CUBE_ERR_ARG, "cube_solved");
-    if (misaligned(states)) return fail(CUBE_ERR_ALIGN, "cube_solved");
+    if (misaligned(states) || misaligned4(reward)) return fail(CUBE_ERR_ALIGN, "cube_solved");
     CUBE_DONE("cube_solved", cube::launch_solved(cube_size, states, n, solved, reward,
                                                  (unsigned long long*)counters, (cudaStream_t)stream));
 }
@@ -145,22 +163,24 @@ int cube_moves_from_seeds(int cube_size, const uint32_t* seeds, int64_t n, int d
 int cube_mcts_traverse(int cube_size, const cube_mcts_tree_t* tree, float cpuct, int virtual_loss, void* stream)
 {
     CUBE_CHECK_SIZE("cube_mcts_traverse");
-    if (!tree || tree->n_trees < 0 || tree->n_slots < 1 || tree->n_slots > 255 || tree->path_cap < 1 || tree->rand_cap < 1)
+    if (!tree || tree->n_trees < 0 || tree->n_slots < 1 || tree->n_slots > 255 || tree->path_cap < 1 || tree->rand_cap < 1 ||
+        (tree->n_trees > 0 && (!tree->child_slot || !tree->child_seen || !tree->miss_key || !tree->miss_seen)))
         return fail(CUBE_ERR_ARG, "cube_mcts_traverse");
     CUBE_DONE("cube_mcts_traverse", cube::launch_mcts_traverse(cube_size, *tree, cpuct, virtual_loss, (cudaStream_t)stream));
 }
 
 int cube_mcts_update(int cube_size, const cube_mcts_tree_t* tree, const uint8_t* leaf_key, const uint8_t* child_key_new,
                      const uint8_t* child_done_new, const float* value, const float* policy, float value_min,
-                     int sim_index, int8_t* actions_out, int32_t* n_actions, int32_t* n_sims, void* stream)
+                     int sim_index, int8_t* actions_out, int32_t* n_actions, int32_t* n_sims, int32_t* n_active, void* stream)
 {
     CUBE_CHECK_SIZE("cube_mcts_update");
-    if (!tree || tree->n_trees < 0 || tree->n_slots < 1 || tree->n_slots > 255 ||
+    if (!tree || tree->n_trees < 0 || tree->n_slots < 1 || tree->n_slots > 255 || tree->path_cap < 1 || tree->rand_cap < 1 ||
         (tree->n_trees > 0 && (!leaf_key || !child_key_new || !child_done_new || !value || !policy || !actions_out ||
-                               !n_actions || !n_sims)))
+                               !n_actions || !n_sims || !tree->child_slot || !tree->child_seen || !tree->miss_key ||
+                               !tree->miss_seen)))
         return fail(CUBE_ERR_ARG, "cube_mcts_update");
     CUBE_DONE("cube_mcts_update", cube::launch_mcts_update(cube_size, *tree, leaf_key, child_key_new, child_done_new, value,
-                                                           policy, value_min, sim_index, actions_out, n_actions, n_sims,
+                                                           policy, value_min, sim_index, actions_out, n_actions, n_sims, n_active,
                                                            (cudaStream_t)stream));
 }
 

@@ -13,6 +13,12 @@ namespace cube {
 int launch_scramble(int size, const uint8_t* moves, long long n, int depth, uint8_t* states_out,
                     uint8_t* solved, float* reward, unsigned long long* counters, cudaStream_t stream);
 
+// every prefix of every scramble, cube-major: states_out[i, k, :] = row after moves[i, 0..k]; solved [n, depth] or null.
+// depth <= prefix_max_depth(size) (one tile image of 32 cubes must fit in shared memory), else CUBE_ERR_ARG
+int launch_prefixes(int size, const uint8_t* moves, long long n, int depth, uint8_t* states_out, uint8_t* solved,
+                    unsigned long long* counters, cudaStream_t stream);
+int prefix_max_depth(int size);
+
 // depth moves applied to resident sticker rows (depth = 1: the reference's step)
 int launch_walk(int size, const uint8_t* states_in, const uint8_t* moves, long long n, int depth,
                 uint8_t* states_out, uint8_t* solved, float* reward, unsigned long long* counters,
@@ -59,7 +65,7 @@ long long launch_leaf2_children(const uint8_t* states, long long n, uint8_t* chi
 int launch_mcts_traverse(int size, const cube_mcts_tree_t& t, float cpuct, int virtual_loss, cudaStream_t stream);
 int launch_mcts_update(int size, const cube_mcts_tree_t& t, const uint8_t* leaf_key, const uint8_t* child_key_new,
                        const uint8_t* child_done_new, const float* value, const float* policy, float value_min,
-                       int sim_index, int8_t* actions_out, int* n_actions, int* n_sims, cudaStream_t stream);
+                       int sim_index, int8_t* actions_out, int* n_actions, int* n_sims, int* n_active, cudaStream_t stream);
 
 int launch_decode2(const void* onehot, int dtype, long long n, uint8_t* out, cudaStream_t stream);
 

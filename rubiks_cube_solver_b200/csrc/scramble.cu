@@ -497,7 +497,10 @@ int launch_one(const uint8_t* moves, long long n, int depth, uint8_t* out, uint8
     long long done = 0;
     static const char* const force = getenv("CUBE_SCRAMBLE_CLASSIC");               // A/B switch for profiling
     static const bool four_ok = !(getenv("CUBE_PAIR_FOUR") && getenv("CUBE_PAIR_FOUR")[0] == '0');
-    if (depth >= 1 && depth <= kMaxPairDepth && !(force && force[0] == '1')) {
+    // K1p writes the verdicts of rows 2l, 2l+1 as one 16-bit / float2 word: a sliced solved / reward buffer
+    // that is not aligned like that takes the byte-wise tile kernel
+    const bool aligned = ((reinterpret_cast<uintptr_t>(solved) & 1u) | (reinterpret_cast<uintptr_t>(reward) & 7u)) == 0;
+    if (depth >= 1 && depth <= kMaxPairDepth && aligned && !(force && force[0] == '1')) {
         if (SIZE == 2 && four_ok)
             done = launch_pairs<2, 4>(moves, n, depth, out, solved, reward, counters, stream, kMinWarpsFour);
         if (done == 0) done = launch_pairs<SIZE, 2>(moves, n, depth, out, solved, reward, counters, stream, 4);

@@ -299,7 +299,12 @@ int launch_tiles(const uint8_t* in, const uint8_t* moves, long long n, int depth
     using G = CubeGeom<SIZE>;
     long long done = 0;
     static const char* const force = getenv("CUBE_WALK_CLASSIC");                   // A/B switch for profiling
-    if (depth >= 1 && depth <= kMaxPrivateDepth && out && n >= kRowsPerTile && !(force && force[0] == '1')) {
+    // K2p stages the move bytes by bulk copies (16-byte aligned source) and writes the verdicts as 32-bit /
+    // float2 words; a caller's sliced tensor (actions_all[t] of a [T, N] array, a view into a larger solved /
+    // reward buffer) need not be aligned like that: such calls take the byte-wise tile kernel below
+    const bool aligned = ((reinterpret_cast<uintptr_t>(moves) & 15u) | (reinterpret_cast<uintptr_t>(solved) & 3u) |
+                          (reinterpret_cast<uintptr_t>(reward) & 7u)) == 0;
+    if (depth >= 1 && depth <= kMaxPrivateDepth && out && n >= kRowsPerTile && aligned && !(force && force[0] == '1')) {
         int warps = (227 * 1024 - L::kPerWarp) / L::per_warp(depth);
         if (warps > kMaxWalkWarps) warps = kMaxWalkWarps;
         warps &= ~3;

@@ -45,7 +45,8 @@ class _Tree(ctypes.Structure):
                 ("rand_cap", ctypes.c_int32)] + [
         (name, ctypes.c_void_p) for name in (
             "node_key", "child_key", "child_done", "P", "W", "N", "L", "n_nodes", "active", "root_state", "root_key",
-            "rand_table", "rand_ptr", "path_node", "path_action", "path_len", "leaf_state", "flags")]
+            "rand_table", "rand_ptr", "path_node", "path_action", "path_len", "leaf_state", "flags",
+            "child_slot", "child_seen", "miss_key", "miss_seen")]
 
 
 class BatchedMCTS(object):
@@ -107,10 +108,10 @@ class BatchedMCTS(object):
         return torch.tensor(rows, dtype=torch.uint8)
 
     @torch.no_grad()
-    def run(self, roots, seeds=None, rand_table=None):
+    def run(self, roots, seeds=None, rand_table=None, timers=None):
         """roots: uint8 [B, S] sticker rows (CUDA).  seeds: per-tree seeds of Python's `random`
-        (or rand_table: [B, draws] pre-drawn actions, `rand_cap` = 8 * (num_sim + 1) by default).  Returns dict(solved bool [B],
-        actions int64 [B, num_sim + 1] (-1 padded), n_actions, n_sims, n_nodes int64 [B],
+        (or rand_table: [B, draws] pre-drawn actions < A, `rand_cap` = 8 * (num_sim + 1) by default).  Returns dict(solved bool [B],
+        actions int64 [B, max(num_sim + 1, longest list)] (-1 padded), n_actions, n_sims, n_nodes int64 [B],
         root_N int32 [B, A], root_W float32 [B, A], root_L int32 [B, A])."""
         from . import _lib
         lib = _lib.load()
@@ -125,6 +126,8 @@ class BatchedMCTS(object):
         rand_table = rand_table.to(device=dev, dtype=torch.uint8).contiguous()
         if rand_table.dim() != 2 or rand_table.shape[0] != b:
             raise ValueError("rand_table must be [B, draws per tree]")
+        if rand_table.numel() and int(rand_table.max()) >= a:
+            raise IndexError("rand_table holds action indices >= %d" % a)           # they index the node's child rows
 
         def z(shape, dtype):
             return torch.zeros(shape, dtype=dtype, device=dev)
@@ -136,31 +139,57 @@ class BatchedMCTS(object):
                  root_key=self._codes(ops.encode(self.cube_size, roots, dtype=torch.uint8)), rand_table=rand_table,
                  rand_ptr=z((b,), torch.int32), path_node=z((b, self.path_cap), torch.uint8),
                  path_action=z((b, self.path_cap), torch.uint8), path_len=z((b,), torch.int32),
-                 leaf_state=z((b, self.s), torch.uint8), flags=z((1,), torch.int32))
+                 leaf_state=z((b, self.s), torch.uint8), flags=z((1,), torch.int32),
+                 child_slot=torch.full((b, m, a), 255, dtype=torch.uint8, device=dev), child_seen=z((b, m, a), torch.uint8),
+                 miss_key=z((b, kb), torch.uint8), miss_seen=z((b,), torch.int32))
         tree = _Tree(b, m, self.path_cap, rand_table.shape[1], *[T[name].data_ptr() for name, _ in _Tree._fields_[4:]])
         actions = torch.full((b, self.path_cap + 1), -1, dtype=torch.int8, device=dev)
         n_actions = z((b,), torch.int32)
         n_sims = torch.full((b,), self.num_sim, dtype=torch.int32, device=dev)
         stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
+        from ._timing import Phases
+        phase = Phases(timers, dev)
+        # Early exit without stalling the launch queue: every update kernel counts the trees that are still
+        # searching into its own device counter; the count travels to pinned host memory behind the
+        # simulation and is looked at (never waited for) a few simulations later.
+        still = z((self.num_sim,), torch.int32)
+        still_host = torch.full((self.num_sim,), -1, dtype=torch.int32).pin_memory()
+        landed = []
+        direct = self.obs_dtype in ops.ONEHOT_DTYPES
         with torch.cuda.device(dev):
             for sim in range(self.num_sim):
-                if sim % 8 == 0 and not bool(T["active"].any()):
+                while landed and landed[0][1].query():
+                    if int(still_host[landed.pop(0)[0]]) == 0:
+                        landed = None
+                        break
+                if landed is None:
                     break
-                _lib.check(lib.cube_mcts_traverse(self.cube_size, ctypes.byref(tree), self.cpuct, self.loss_const, stream),
-                           "cube_mcts_traverse")
+                with phase("traverse_ms"):
+                    _lib.check(lib.cube_mcts_traverse(self.cube_size, ctypes.byref(tree), self.cpuct, self.loss_const, stream),
+                               "cube_mcts_traverse")
                 # the node keys come out of the expansion kernel as compact codes (cube_expand_codes), the leaf's
                 # observation directly in the net's dtype: no one-hot rows of the children, no argmax passes
-                direct = self.obs_dtype in ops.ONEHOT_DTYPES
-                res = ops.expand_codes(self.cube_size, T["leaf_state"], parent_dtype=self.obs_dtype if direct else torch.uint8)
-                leaf_key, child_key = res["parent_codes"], res["child_codes"]
-                value, logits = self.model(res["parent_onehot"].to(mdev).to(self.obs_dtype))
-                value = value.float().reshape(-1).to(dev).contiguous()
-                policy = torch.nn.functional.softmax(logits.float(), dim=-1).to(dev).contiguous()
-                _lib.check(lib.cube_mcts_update(self.cube_size, ctypes.byref(tree), leaf_key.data_ptr(), child_key.data_ptr(),
-                                                res["solved"].data_ptr(), value.data_ptr(), policy.data_ptr(), self.value_min,
-                                                sim, actions.data_ptr(), n_actions.data_ptr(), n_sims.data_ptr(), stream),
-                           "cube_mcts_update")
+                with phase("expand_ms"):
+                    res = ops.expand_codes(self.cube_size, T["leaf_state"], parent_dtype=self.obs_dtype if direct else torch.uint8,
+                                           want_reward=False)
+                    leaf_key, child_key = res["parent_codes"], res["child_codes"]
+                with phase("net_ms"):
+                    value, logits = self.model(res["parent_onehot"].to(mdev).to(self.obs_dtype))
+                with phase("glue_ms"):
+                    value = value.float().reshape(-1).to(dev).contiguous()
+                    policy = torch.nn.functional.softmax(logits.float(), dim=-1).to(dev).contiguous()
+                with phase("update_ms"):
+                    _lib.check(lib.cube_mcts_update(self.cube_size, ctypes.byref(tree), leaf_key.data_ptr(), child_key.data_ptr(),
+                                                    res["solved"].data_ptr(), value.data_ptr(), policy.data_ptr(), self.value_min,
+                                                    sim, actions.data_ptr(), n_actions.data_ptr(), n_sims.data_ptr(),
+                                                    still[sim:].data_ptr(), stream),
+                               "cube_mcts_update")
+                still_host[sim:sim + 1].copy_(still[sim:sim + 1], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(dev))
+                landed.append((sim, ev))
+        phase.finish()
         flags = int(T["flags"].item())
         if flags:
             raise RuntimeError("BatchedMCTS: capacity exceeded (flags=%d: 1 path_cap, 2 rand_table, 4 node slots)" % flags)
@@ -168,6 +197,9 @@ class BatchedMCTS(object):
         ar = torch.arange(b, device=dev)
         same = (T["node_key"] == T["root_key"][:, None, :]).all(dim=-1) & (torch.arange(m, device=dev)[None, :] < T["n_nodes"][:, None])
         root_slot = same.int().argmax(dim=1)
-        return dict(solved=n_actions > 0, actions=actions[:, :m].long(), n_actions=n_actions.long(), n_sims=n_sims.long(),
+        # a traversal may revisit nodes (U then U' is back at the root's key), so a returned path can be longer
+        # than the node count: never cut an action list (the reference returns actions_to_leaf + [i] whole)
+        width = max(m, int(n_actions.max())) if b else m
+        return dict(solved=n_actions > 0, actions=actions[:, :width].long(), n_actions=n_actions.long(), n_sims=n_sims.long(),
                     n_nodes=T["n_nodes"].long(), root_N=T["N"][ar, root_slot], root_W=T["W"][ar, root_slot],
                     root_L=T["L"][ar, root_slot])

@@ -100,6 +100,36 @@ def scramble(cube_size, moves, out=None, solved=None, reward=None, counters=None
     return out, solved, reward
 
 
+def prefixes_max_depth(cube_size):
+    """Largest depth cube_scramble_prefixes takes (131 for 3x3x3, 289 for 2x2x2)."""
+    _geom(cube_size)
+    return _lib.load().cube_scramble_prefixes_max_depth(cube_size)
+
+
+def scramble_prefixes(cube_size, moves, out=None, want_solved=False, counters=None):
+    """Every prefix of every scramble in one launch (C ABI cube_scramble_prefixes): returns
+    (states [N, depth, S] uint8 cube-major, solved [N, depth] uint8 | None) -- the parents of an ADI batch in
+    the order the reference appends its samples (cube_env.py:187-194)."""
+    s, _, _ = _geom(cube_size)
+    moves = _require_cuda(moves, "moves")
+    if moves.dim() != 2:
+        raise ValueError("moves must be [N, depth]")
+    n, depth = moves.shape
+    if depth > prefixes_max_depth(cube_size):
+        raise ValueError("scramble_prefixes supports depth <= %d for cube_size %d" % (prefixes_max_depth(cube_size), cube_size))
+    dev = moves.device
+    if out is None:
+        out = torch.empty((n, depth, s), dtype=torch.uint8, device=dev)
+    _require_cuda(out, "out")
+    if out.numel() != n * depth * s:
+        raise ValueError("out must be [N, depth, %d]" % s)
+    solved = torch.empty((n, depth), dtype=torch.uint8, device=dev) if want_solved else None
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().cube_scramble_prefixes(cube_size, _ptr(moves), n, depth, _ptr(out), _ptr(solved),
+                                                      _ptr(counters), _stream(dev)), "cube_scramble_prefixes")
+    return out, solved
+
+
 def step(cube_size, states, actions, solved=None, reward=None, counters=None):
     """One transition in place (C ABI cube_step).  Returns (states, solved, reward)."""
     s, _, _ = _geom(cube_size)
@@ -172,11 +202,14 @@ def encode(cube_size, states, dtype=torch.bfloat16, out=None):
 
 
 def expand(cube_size, states, dtype=torch.bfloat16, want_children=False, want_child_onehot=True,
-           want_parent_onehot=False, child_onehot=None, counters=None):
+           want_parent_onehot=False, child_onehot=None, counters=None, parent_onehot=None, solved=None, reward=None,
+           want_reward=True):
     """All A children of every state (C ABI cube_expand).
 
     Returns dict(children [N,A,S] | None, child_onehot [N,A,R,C] | None,
-    parent_onehot [N,R,C] | None, solved [N,A] uint8, reward [N,A] float32).
+    parent_onehot [N,R,C] | None, solved [N,A] uint8, reward [N,A] float32 | None).
+    `child_onehot`, `parent_onehot`, `solved`, `reward` may be caller-owned output buffers (16-byte aligned
+    slices of larger tensors are fine).
     """
     s, a, (r, c) = _geom(cube_size)
     states = _require_cuda(states, "states")
@@ -187,9 +220,23 @@ def expand(cube_size, states, dtype=torch.bfloat16, want_children=False, want_ch
         child_onehot = torch.empty((n, a, r, c), dtype=dtype, device=dev)
     if child_onehot is not None:
         _require_cuda(child_onehot, "child_onehot", dtype)
-    parent_onehot = torch.empty((n, r, c), dtype=dtype, device=dev) if want_parent_onehot else None
-    solved = torch.empty((n, a), dtype=torch.uint8, device=dev)
-    reward = torch.empty((n, a), dtype=torch.float32, device=dev)
+        if child_onehot.numel() != n * a * r * c:
+            raise ValueError("child_onehot must be [N, %d, %d, %d]" % (a, r, c))
+    if want_parent_onehot and parent_onehot is None:
+        parent_onehot = torch.empty((n, r, c), dtype=dtype, device=dev)
+    if parent_onehot is not None:
+        _require_cuda(parent_onehot, "parent_onehot", dtype)
+        if parent_onehot.numel() != n * r * c:
+            raise ValueError("parent_onehot must be [N, %d, %d]" % (r, c))
+    if solved is None:
+        solved = torch.empty((n, a), dtype=torch.uint8, device=dev)
+    _require_cuda(solved, "solved")
+    if reward is None and want_reward:
+        reward = torch.empty((n, a), dtype=torch.float32, device=dev)
+    if reward is not None:
+        _require_cuda(reward, "reward", torch.float32)
+    if solved.numel() != n * a or (reward is not None and reward.numel() != n * a):
+        raise ValueError("solved / reward must be [N, %d]" % a)
     with torch.cuda.device(dev):
         _lib.check(_lib.load().cube_expand(cube_size, _ptr(states), n, _ptr(children), _ptr(child_onehot),
                                            _ptr(parent_onehot), ONEHOT_DTYPES[dtype], _ptr(solved), _ptr(reward),
@@ -203,7 +250,7 @@ def key_bytes(cube_size):
     return (STATE_DIM[cube_size][0] + 3) & ~3
 
 
-def expand_codes(cube_size, states, parent_dtype=None, want_children=False, counters=None):
+def expand_codes(cube_size, states, parent_dtype=None, want_children=False, counters=None, want_reward=True):
     """All A children of every state with COMPACT CODES instead of one-hot rows (C ABI cube_expand_codes):
     code[row] = column of the 1 of that one-hot row = `onehot.argmax(-1)`, zero-padded to key_bytes.
 
@@ -217,7 +264,7 @@ def expand_codes(cube_size, states, parent_dtype=None, want_children=False, coun
     parent_codes = torch.empty((n, key), dtype=torch.uint8, device=dev)
     parent_onehot = torch.empty((n, r, c), dtype=parent_dtype, device=dev) if parent_dtype is not None else None
     solved = torch.empty((n, a), dtype=torch.uint8, device=dev)
-    reward = torch.empty((n, a), dtype=torch.float32, device=dev)
+    reward = torch.empty((n, a), dtype=torch.float32, device=dev) if want_reward else None
     with torch.cuda.device(dev):
         _lib.check(_lib.load().cube_expand_codes(
             cube_size, _ptr(states), n, _ptr(children), _ptr(child_codes), _ptr(parent_codes), _ptr(parent_onehot),

@@ -29,7 +29,7 @@ def test_header_symbols_exported(lib):
     assert declared == set(_lib.SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.cube_abi_version() == 1
+    assert lib.cube_abi_version() == 2
 
 
 def test_argument_errors_without_cuda(lib):

@@ -405,9 +405,9 @@ def test_config4_and_5_shapes_sampled():
     # config 4 (3x3x3 ADI batch) and config 5 (2x2x2 MCTS leaves) on a slice, vs the oracle
     gen = torch.Generator(device=dev()).manual_seed(99)
     moves = torch.randint(0, 12, (4096, 30), dtype=torch.uint8, device=dev(), generator=gen)
-    trail, n_pad = adi.scramble_prefixes(3, moves)
+    trail = adi.scramble_prefixes(3, moves)                           # [cube, depth, S]: cube-major, one launch
     _, want_trail, _ = O.scramble(3, moves.cpu().numpy(), per_step=True)
-    assert (trail[:, :4096].cpu().numpy() == want_trail.transpose(1, 0, 2)).all()
+    assert (trail.cpu().numpy() == want_trail).all()
     parents = trail.view(-1, 54)
     res = ops.expand(3, parents, dtype=torch.bfloat16)
     sample = np.random.RandomState(0).randint(parents.shape[0], size=2048)
@@ -830,3 +830,240 @@ def test_expand_codes_equal_argmax_of_the_onehot_rows(size, n):
     assert (got["children"] == want["children"]).all() and (got["solved"] == want["solved"]).all()
     assert (got["reward"] == want["reward"]).all()
     assert (got["parent_onehot"] == want["parent_onehot"].float()).all()
+
+
+# ------------------------------------------------------------------ round 2: paths that had no test
+def _guarded(n_bytes, dtype=torch.uint8, guard=4096, fill=0xA5):
+    """A device buffer with `guard` canary bytes on both sides of the n_bytes payload (16-byte aligned)."""
+    raw = torch.full((guard + n_bytes + 15 + guard,), fill, dtype=torch.uint8, device=dev())
+    pad = (-(raw.data_ptr() + guard)) % 16
+    lo = guard + pad
+    view = raw[lo:lo + n_bytes].view(dtype)
+    return raw, view, lo
+
+
+def _guards_intact(raw, lo, n_bytes, fill=0xA5):
+    return bool((raw[:lo] == fill).all()) and bool((raw[lo + n_bytes:] == fill).all())
+
+
+@pytest.mark.parametrize("size", SIZES)
+@pytest.mark.parametrize("depth", (1, 7, 20, 30, 32, 64, 97, 200, 321, 400))
+def test_garbage_action_bytes_are_memory_safe_scramble(size, depth):
+    """include/cube_b200.h: action bytes 13..255 are memory-safe but give unspecified states.  Rows whose
+    moves are all valid must still be exact, the guard bytes around every output must survive, and the
+    device must not fault -- on every scramble variant (flat / swizzled / four-per-lane K1p at depth
+    <= 320, the ragged tile kernel, the deep kernel)."""
+    rng = np.random.RandomState(1000 * size + depth)
+    S, A = T.N_STICKERS[size], T.N_ACTIONS[size]
+    n = 64 * 148 * 3 + 37                                              # whole K1p tiles + a ragged tail
+    moves = rng.randint(A, size=(n, depth)).astype(np.uint8)
+    bad_rows = rng.choice(n, n // 3, replace=False)
+    for r in bad_rows[: len(bad_rows) // 2]:                            # one garbage byte somewhere
+        moves[r, rng.randint(depth)] = rng.randint(13, 256)
+    for r in bad_rows[len(bad_rows) // 2:]:                             # all garbage
+        moves[r] = rng.randint(13, 256, size=depth)
+    moves[bad_rows[0]] = 255
+    good = np.ones(n, dtype=bool)
+    good[bad_rows] = False
+    raw_s, states, lo_s = _guarded(n * S)
+    raw_f, solved, lo_f = _guarded(n)
+    raw_r, reward, lo_r = _guarded(4 * n, torch.float32)
+    counters = ops.new_counters(dev())
+    ops.scramble(size, cu(moves), out=states.view(n, S), solved=solved, reward=reward, counters=counters)
+    torch.cuda.synchronize()                                           # a fault would surface here
+    assert _guards_intact(raw_s, lo_s, n * S) and _guards_intact(raw_f, lo_f, n) and _guards_intact(raw_r, lo_r, 4 * n)
+    want, ws, wr, _ = C.scramble(size, moves[good])
+    assert (states.view(n, S).cpu().numpy()[good] == want).all()
+    assert (solved.cpu().numpy()[good].astype(bool) == ws).all() and (reward.cpu().numpy()[good] == wr).all()
+    assert set(np.unique(solved.cpu().numpy())) <= {0, 1} and set(np.unique(reward.cpu().numpy())) <= {-1.0, 1.0}
+    assert int(counters[1]) == n
+    with pytest.raises(IndexError):
+        ops.validate_actions(size, cu(moves))
+
+
+@pytest.mark.parametrize("size", SIZES)
+@pytest.mark.parametrize("depth", (1, 5, 64, 65))
+def test_garbage_action_bytes_are_memory_safe_step_and_walk(size, depth):
+    """The same canary for cube_step / cube_walk (K2p at depth <= 64, the tile kernel beyond and for the tail)."""
+    rng = np.random.RandomState(77 * size + depth)
+    S, A = T.N_STICKERS[size], T.N_ACTIONS[size]
+    n = 64 * 148 * 2 + 29
+    start = O.scramble(size, rng.randint(A, size=(n, 9)))
+    moves = rng.randint(A, size=(n, depth)).astype(np.uint8)
+    bad_rows = rng.choice(n, n // 4, replace=False)
+    for r in bad_rows:
+        moves[r, rng.randint(depth)] = rng.randint(13, 256)
+    moves[bad_rows[0]] = 255
+    good = np.ones(n, dtype=bool)
+    good[bad_rows] = False
+    raw_s, out, lo_s = _guarded(n * S)
+    raw_f, solved, lo_f = _guarded(n)
+    raw_r, reward, lo_r = _guarded(4 * n, torch.float32)
+    ops.walk(size, cu(start), cu(moves), out=out.view(n, S), solved=solved, reward=reward)
+    torch.cuda.synchronize()
+    assert _guards_intact(raw_s, lo_s, n * S) and _guards_intact(raw_f, lo_f, n) and _guards_intact(raw_r, lo_r, 4 * n)
+    want = O.scramble(size, moves[good], init=start[good])
+    assert (out.view(n, S).cpu().numpy()[good] == want).all()
+    assert (solved.cpu().numpy()[good].astype(bool) == O.is_solved(size, want)).all()
+    if depth == 1:                                                      # cube_step, in place
+        raw_i, st, lo_i = _guarded(n * S)
+        st.view(n, S).copy_(cu(start))
+        ops.step(size, st.view(n, S), cu(moves[:, 0]), solved=solved, reward=reward)
+        torch.cuda.synchronize()
+        assert _guards_intact(raw_i, lo_i, n * S)
+        assert (st.view(n, S).cpu().numpy()[good] == want).all()
+
+
+@pytest.mark.parametrize("size", SIZES)
+def test_sliced_and_offset_buffers(size):
+    """`ops.step(size, states, actions_all[t])` on a [T, N] tensor with N % 16 != 0, or a sliced
+    solved= / reward= buffer, is contiguous but not 16- / 8- / 4-byte aligned.  Such calls must work (the byte-wise
+    kernels take them), not fault."""
+    rng = np.random.RandomState(size)
+    S, A = T.N_STICKERS[size], T.N_ACTIONS[size]
+    n, steps = 64 * 300 + 13, 3                                        # N % 16 == 13
+    start = O.scramble(size, rng.randint(A, size=(n, 8)))
+    actions_all = cu(rng.randint(A, size=(steps, n)).astype(np.uint8))
+    flags = torch.zeros(steps * n + 3, dtype=torch.uint8, device=dev())
+    rewards = torch.zeros(steps * n + 3, dtype=torch.float32, device=dev())
+    states, want = cu(start), start
+    for t in range(steps):
+        so = flags[1 + t * n:1 + (t + 1) * n]                          # odd byte offset
+        rw = rewards[1 + t * n:1 + (t + 1) * n]                        # 4-byte but not 8-byte aligned
+        ops.step(size, states, actions_all[t], solved=so, reward=rw)
+        want = O.apply_moves(size, want, actions_all[t].cpu().numpy())
+        assert (states.cpu().numpy() == want).all()
+        assert (so.cpu().numpy().astype(bool) == O.is_solved(size, want)).all()
+        assert (rw.cpu().numpy() == O.rewards(O.is_solved(size, want))).all()
+    moves = rng.randint(A, size=(n, 30)).astype(np.uint8)
+    so, rw = flags[1:1 + n], rewards[1:1 + n]
+    st, _, _ = ops.scramble(size, cu(moves), solved=so, reward=rw)
+    w2, ws, wr, _ = C.scramble(size, moves)
+    assert (st.cpu().numpy() == w2).all() and (so.cpu().numpy().astype(bool) == ws).all() and (rw.cpu().numpy() == wr).all()
+    # walk with a move array that starts 1 byte into an allocation
+    mv = torch.zeros(n * 4 + 1, dtype=torch.uint8, device=dev())
+    mv[1:] = cu(moves[:, :4]).reshape(-1)
+    out, so2, _ = ops.walk(size, cu(start), mv[1:].view(n, 4))
+    assert (out.cpu().numpy() == O.scramble(size, moves[:, :4], init=start)).all()
+
+
+@pytest.mark.parametrize("size", SIZES)
+def test_reset_without_seed_draws_from_and_rewinds_the_global_rng(size):
+    """reset(seed=None) (cube_env.py:60-68): the moves come from the GLOBAL legacy generator and the
+    generator is put back, so two resets in a row give the same cube and the stream is not advanced --
+    against oracle/scalar_env.py (pinned to the reference by tests/test_oracle_vs_reference.py)."""
+    from oracle.scalar_env import ScalarCubeEnv
+    env, ref = R.make_env(torch.device("cpu"), size), ScalarCubeEnv(size)
+    for seed0, k in ((5, 1), (123, 7), (2 ** 31 + 7, 30)):
+        np.random.seed(seed0)
+        before = np.random.get_state()
+        obs = env.reset(scramble_count=k)
+        mid = np.random.get_state()
+        want_obs = ref.reset(scramble_count=k)
+        assert (np.random.get_state()[1] == before[1]).all() and np.random.get_state()[2] == before[2]
+        assert (mid[1] == before[1]).all() and mid[2] == before[2]                  # rewound by the drop-in too
+        assert (env.sim_cube == ref.sim_cube).all() and (obs == want_obs).all() and obs.dtype == want_obs.dtype
+        assert (env.sim_cube == O.scramble(size, np.random.RandomState(seed0).randint(T.N_ACTIONS[size], size=k)[None])[0]).all()
+        again = env.reset(seed=None, scramble_count=k)                              # same stream position -> same cube
+        assert (again == obs).all()
+        np.random.randint(10)                                                       # advance the stream: another cube
+        other = env.reset(scramble_count=k)
+        ref.reset(scramble_count=k)
+        assert (env.sim_cube == ref.sim_cube).all() and (other == ref.cube).all()
+    with pytest.raises(UnboundLocalError):
+        env.reset(scramble_count=0)
+
+
+def test_config3_whole_on_one_gpu_64Mi():
+    """SURVEY.md section 8d config 3 as ONE device's job: 64 Mi instances x depth 30 (2 GB of moves, 3.6 GB of
+    sticker rows) -- 32-bit tile indices, > 2^31 byte offsets and the dynamic-tail scheduler at 1 Mi tiles."""
+    size, n, depth = 3, 64 * 2 ** 20, 30
+    gen = torch.Generator(device=dev()).manual_seed(1234)
+    moves = torch.randint(0, 12, (n, depth), dtype=torch.uint8, device=dev(), generator=gen)
+    back = torch.randint(0, n, (1000,), device=dev(), generator=gen)
+    moves[back, 15:] = moves[back, :15].flip(1) ^ 1                                # rows that come back to solved
+    counters = ops.new_counters(dev())
+    states, solved, reward = ops.scramble(size, moves, counters=counters)
+    idx = np.concatenate((np.arange(4096), n - 1 - np.arange(4096), np.random.RandomState(7).randint(n, size=8192),
+                          back.cpu().numpy()))
+    want, ws, wr, _ = C.scramble(size, moves[idx].cpu().numpy())
+    assert (states[idx].cpu().numpy() == want).all()
+    assert (solved[idx].cpu().numpy().astype(bool) == ws).all() and (reward[idx].cpu().numpy() == wr).all()
+    assert ws[-1000:].all()
+    sub = slice(n - 2 ** 20 - 77, n - 77)
+    _, _, _, cnt = C.scramble(size, moves[sub].cpu().numpy())
+    assert int(solved[sub].sum()) == cnt
+    assert int(counters[0]) == int(solved.sum()) >= len(set(back.tolist())) and int(counters[1]) == n
+    assert float(reward.double().sum()) == 2 * int(counters[0]) - n
+    # checksum of checksums: every row is a permutation of the solved multiset
+    ok = torch.ones(n, dtype=torch.bool, device=dev())
+    for c in range(6):
+        ok &= (states == c).sum(dim=1) == 9
+    assert bool(ok.all())
+    del ok
+    # scramble o inverse = identity for all 64 Mi rows, in two halves (the 60-move array is 4 GB)
+    for half in range(2):
+        m = moves[half * (n // 2):(half + 1) * (n // 2)]
+        undo = torch.cat((m, m.flip(1) ^ 1), dim=1).contiguous()
+        counters.zero_()
+        s2, so2, _ = ops.scramble(size, undo, counters=counters)
+        assert int(counters[0]) == n // 2 and bool(so2.all())
+        del undo, s2, so2
+    # one step on the resident rows == a depth-31 scramble
+    extra = torch.randint(0, 12, (n,), dtype=torch.uint8, device=dev(), generator=gen)
+    stepped, so3, _ = ops.step(size, states, extra)
+    longer, so4, _ = ops.scramble(size, torch.cat((moves, extra[:, None]), dim=1).contiguous())
+    assert bool((stepped == longer).all()) and bool((so3 == so4).all())
+
+
+@pytest.mark.parametrize("size", SIZES)
+@pytest.mark.parametrize("n", (1, 15, 16, 17, 1000, 70001))
+def test_expand_codes_vs_oracle(size, n):
+    """cube_expand_codes against the ORACLE (not against cube_expand): codes = the column of the 1 of every
+    one-hot row of oracle.cube_np.encode, through the reference's tables as shipped."""
+    rng = np.random.RandomState(3 * n + size)
+    A, S = T.N_ACTIONS[size], T.N_STICKERS[size]
+    r, key = T.STATE_DIM[size][0], ops.key_bytes(size)
+    parents = O.scramble(size, rng.randint(A, size=(n, 10)))
+    parents[0] = O.scramble(size, np.array([[5]]))[0]
+    got = ops.expand_codes(size, cu(parents), parent_dtype=torch.uint8, want_children=True)
+    want_c, want_s = O.expand(size, parents)
+    assert (got["children"].cpu().numpy() == want_c).all()
+    assert (got["solved"].cpu().numpy().astype(bool) == want_s).all() and got["solved"][0, 4] == 1
+    assert (got["reward"].cpu().numpy() == np.where(want_s, 1.0, -1.0)).all()
+    enc_c = O.encode(size, want_c.reshape(n * A, S)).reshape(n, A, r, -1)
+    enc_p = O.encode(size, parents)
+    assert (enc_c.sum(-1) == 1).all() and (enc_p.sum(-1) == 1).all()
+    assert (got["child_codes"].cpu().numpy()[..., :r] == enc_c.argmax(-1)).all()
+    assert (got["parent_codes"].cpu().numpy()[..., :r] == enc_p.argmax(-1)).all()
+    assert (got["child_codes"].cpu().numpy()[..., r:] == 0).all() and (got["parent_codes"].cpu().numpy()[..., r:] == 0).all()
+    assert (got["parent_onehot"].cpu().numpy() == enc_p).all()
+
+
+@pytest.mark.parametrize("size", SIZES)
+@pytest.mark.parametrize("n,depth", [(1, 1), (31, 2), (32, 30), (33, 30), (1000, 7), (148 * 8 * 32 * 2 + 5, 30), (4099, 31),
+                                     (100, 131), (70, 289), (70, 290)])
+def test_scramble_prefixes_vs_oracle(size, n, depth):
+    """cube_scramble_prefixes: every prefix of every scramble in one launch, cube-major
+    (get_random_samples' order, cube_env.py:187-194), with the done flag of every prefix -- against the
+    oracle's per-step states.  Depths beyond the single-launch limit go through adi.scramble_prefixes'
+    per-level path."""
+    rng = np.random.RandomState(n + depth + size)
+    A, S = T.N_ACTIONS[size], T.N_STICKERS[size]
+    moves = rng.randint(A, size=(n, depth)).astype(np.uint8)
+    if depth >= 4:
+        moves[::3, 2:4] = moves[::3, :2][:, ::-1] ^ 1                   # solved again after four moves
+    _, want, want_solved = O.scramble(size, moves, per_step=True)
+    if depth <= ops.prefixes_max_depth(size):
+        counters = ops.new_counters(dev())
+        got, solved = ops.scramble_prefixes(size, cu(moves), want_solved=True, counters=counters)
+        assert got.shape == (n, depth, S) and (got.cpu().numpy() == want).all()
+        assert (solved.cpu().numpy().astype(bool) == want_solved).all()
+        assert counters.tolist()[:2] == [int(want_solved.sum()), n * depth]
+        if depth >= 4:
+            assert solved[0, 3] == 1
+    else:
+        with pytest.raises(ValueError):
+            ops.scramble_prefixes(size, cu(moves))
+    assert (adi.scramble_prefixes(size, cu(moves)).cpu().numpy() == want).all()
+    assert ops.prefixes_max_depth(size) == (131 if size == 3 else 289)
