@@ -53,16 +53,50 @@ def _cpu_init(cube_size):
 
 
 def _cpu_task(args):
+    """One worker's share of a step, timed INSIDE the worker (dispatch and pickling are not the env's work)."""
     depth, n_cubes, seed = args
     import numpy as np
     env, rng = _ENV, np.random.RandomState(seed)
     solved = 0
+    t0 = time.perf_counter()
     for _ in range(n_cubes):
         env.init_state()
         for a in rng.randint(env.action_dim, size=depth):
             _, _, done, _ = env.step(a)
         solved += int(done)
-    return n_cubes * depth, solved
+    return n_cubes * depth, solved, time.perf_counter() - t0
+
+
+def _cpu_adi_task(args):
+    """get_random_samples(buf, net, depth, cubes, T) (cube_env.py:177-252) with DeepCube's layer shapes on one core."""
+    depth, n_cubes, seed = args
+    import numpy as np
+    import torch
+    torch.set_num_threads(1)
+    np.random.seed(seed)
+    torch.manual_seed(0)
+    nn = torch.nn
+
+    class Net(nn.Module):                                   # model.py:7-29, hidden [1024, 256, 128] (config.yaml)
+        def __init__(self):
+            super().__init__()
+            self.enc = nn.Sequential(nn.Flatten(), nn.Linear(480, 1024), nn.ELU(), nn.Linear(1024, 256), nn.ELU())
+            self.pol = nn.Sequential(nn.Linear(256, 128), nn.ELU(), nn.Linear(128, 12))
+            self.val = nn.Sequential(nn.Linear(256, 128), nn.ELU(), nn.Linear(128, 1))
+
+        def forward(self, x):
+            if x.dim() == 2:
+                x = x.unsqueeze(0)
+            h = self.enc(x)
+            return self.val(h), self.pol(h)
+
+    net, buf = Net(), []
+    _ENV.device = torch.device("cpu")
+    _ENV.get_random_samples(buf, net, depth, 1, 1.0)        # warm-up
+    buf = []
+    t0 = time.perf_counter()
+    _ENV.get_random_samples(buf, net, depth, n_cubes, 1.0)
+    return len(buf), 0, time.perf_counter() - t0
 
 
 class CpuReferencePool(object):
@@ -72,12 +106,14 @@ class CpuReferencePool(object):
     def __init__(self, cube_size, procs):
         self.procs = procs
         self.pool = mp.get_context("spawn").Pool(procs, initializer=_cpu_init, initargs=(cube_size,))
-        self.run(DEPTH, 4)                                  # imports + first-touch, untimed
+        self.run(DEPTH if cube_size == 3 else 20, 4)        # imports + first-touch, untimed
 
-    def run(self, depth, cubes_per_proc, seed0=1000):
-        t0 = time.perf_counter()
-        res = self.pool.map(_cpu_task, [(depth, cubes_per_proc, seed0 + i) for i in range(self.procs)], chunksize=1)
-        return time.perf_counter() - t0, sum(r[0] for r in res)
+    def run(self, depth, cubes_per_proc, seed0=1000, procs=None, task=_cpu_task):
+        """Returns (seconds, units): the slowest worker's own loop time (all workers run at once) and the
+        transitions (or ADI samples) all of them produced."""
+        procs = self.procs if procs is None else procs
+        res = self.pool.map(task, [(depth, cubes_per_proc, seed0 + i) for i in range(procs)], chunksize=1)
+        return max(r[2] for r in res), sum(r[0] for r in res)
 
     def close(self):
         self.pool.close()
@@ -100,9 +136,24 @@ def cpu_c_oracle(cube_size, depth, n):
     return n * depth / dt, cube_c.num_threads()
 
 
+def workload_config(world, n_per_gpu, scaling):
+    """The `config` object of the JSON line: identical in both arms (`--impl b200` and `--impl reference`)."""
+    return {"workload": WORKLOAD, "cube_size": CUBE_SIZE, "depth": DEPTH, "instances_per_gpu": int(n_per_gpu),
+            "instances_total": int(world * n_per_gpu), "scaling": scaling}
+
+
+def instances_per_gpu(args, world):
+    """weak (default): every rank owns 8 Mi instances (64 Mi over 8 GPUs); strong: SURVEY.md 8d config 3 whole,
+    64 Mi instances split over the ranks (rank r owns rows [r * N / R, (r + 1) * N / R))."""
+    if args.scaling == "strong":
+        return args.instances_total // world
+    return args.instances_per_gpu
+
+
 def run_reference_arm(args):
     """K timed steps; each step is a bounded sample of the workload sized so that the whole run
-    takes about `--ref-seconds` of wall clock whatever K is."""
+    takes about `--ref-seconds` of wall clock whatever K is.  A step's time is the slowest worker's own
+    loop time (all workers run concurrently), so pool dispatch is not billed to the reference's env."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -110,7 +161,7 @@ def run_reference_arm(args):
     pool = CpuReferencePool(CUBE_SIZE, procs)
     steps, warmup = max(1, args.steps), max(0, args.warmup)
     # ~28 k transitions/s/core: cubes per process per step for the time budget
-    cubes = max(8, int(args.ref_seconds * 28000.0 / DEPTH / (steps + warmup)))
+    cubes = max(64, int(args.ref_seconds * 28000.0 / DEPTH / (steps + warmup)))
     for i in range(warmup):
         pool.run(DEPTH, cubes, seed0=5000 + 1000 * i)
     t_total, tr_total = 0.0, 0
@@ -120,19 +171,54 @@ def run_reference_arm(args):
         tr_total += n_tr
     pool.close()
     value = tr_total / t_total
-    sample = "%d processes x %d cubes x depth %d per step (3x3x3 per-cube Python env), %d steps" % (
-        procs, cubes, DEPTH, steps)
+    sample = ("%d processes x %d cubes x depth %d per step (3x3x3 per-cube Python env, oracle/scalar_env.py = the "
+              "reference's cube_env.py:71-111 restated), %d steps, timed inside the workers" % (procs, cubes, DEPTH, steps))
+    world = max(1, args.gpus)
     line = {
         "impl": "reference", "metric": "cube transitions/sec", "value": value, "unit": "transitions/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * t_total / steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "CPU arm: each step is a bounded sample of the same workload "
-                   "on every host core (the reference scales by OS processes, train.py:85-92)"},
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": workload_config(world, instances_per_gpu(args, world), args.scaling),
         "cpu_baseline": {"value": value, "unit": "transitions/s", "cores": procs, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "transitions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
     return 0
+
+
+def cpu_baselines(size, depth, cubes_per_proc):
+    """The CPU numbers BASELINE.md section 3 asks for beside the GPU line, all with the reference-semantics per-cube
+    Python env (oracle/scalar_env.py), each a bounded sample: all host cores and one process on the benchmark's
+    own workload, 2x2x2 on all cores, ADI get_random_samples states/s on all cores, and the plain-C oracle."""
+    procs = host_procs()
+    out = {}
+    pool = CpuReferencePool(size, procs)
+    dt, n_tr = pool.run(depth, cubes_per_proc)
+    out["cpu_baseline"] = {
+        "value": n_tr / dt, "unit": "transitions/s", "cores": procs, "kind": "port",
+        "sample": "%d processes x %d cubes x depth %d = %d transitions of the 3x3x3 per-cube Python env "
+                  "(oracle/scalar_env.py, reference semantics cube_env.py:71-111), timed inside the workers" % (
+                      procs, cubes_per_proc, depth, n_tr)}
+    dt1, n1 = pool.run(depth, max(64, cubes_per_proc // 5), procs=1)
+    out["cpu_baseline_single_process"] = {"value": n1 / dt1, "unit": "transitions/s", "cores": 1, "kind": "port",
+                                          "sample": "1 process x %d cubes x depth %d (3x3x3)" % (n1 // depth, depth)}
+    adi_cubes = 8
+    dta, na = pool.run(depth, adi_cubes, task=_cpu_adi_task)
+    out["cpu_baseline_adi"] = {"value": na / dta, "unit": "ADI states/s", "cores": procs, "kind": "port",
+                               "sample": "%d processes x get_random_samples(buf, net, %d, %d, 1.0), 3x3x3, DeepCube "
+                                         "[1024, 256, 128] in float32 on one thread each (cube_env.py:177-252)" % (
+                                             procs, depth, adi_cubes)}
+    pool.close()
+    pool2 = CpuReferencePool(2, procs)
+    dt2, n2 = pool2.run(20, max(64, cubes_per_proc // 3))
+    pool2.close()
+    out["cpu_baseline_2x2x2"] = {"value": n2 / dt2, "unit": "transitions/s", "cores": procs, "kind": "port",
+                                 "sample": "%d processes x %d cubes x depth 20 (2x2x2 per-cube Python env)" % (
+                                     procs, n2 // 20 // procs)}
+    cv, threads = cpu_c_oracle(size, depth, 2 ** 21)
+    out["cpu_baseline_c"] = {"value": cv, "unit": "transitions/s", "cores": threads, "kind": "port",
+                             "sample": "plain-C oracle (OpenMP), 2 Mi instances x depth 30"}
+    return out
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -271,19 +357,25 @@ def measure_other_configs(torch, ops, adi, dev, peak_gbs):
     del parents
 
     # config 4 end to end on the device: 139 810 cubes x 30 scramble prefixes (cube_env.py:187-194:
-    # every prefix is a sample) -> 4 194 300 parents -> 12 children + bf16 one-hot each
-    cubes = n // 30 // 16 * 16
+    # every prefix is a sample) -> 4 194 300 parents -> 12 children + bf16 one-hot each.  ONE launch writes
+    # all prefixes cube-major (cube_scramble_prefixes), one launch expands them.
+    cubes = n // 30
     adi_moves = torch.randint(0, 12, (cubes, 30), dtype=torch.uint8, device=dev, generator=gen)
+    trail = torch.empty((cubes, 30, 54), dtype=torch.uint8, device=dev)
 
     def adi_batch():
-        trail, n_pad = adi.scramble_prefixes(3, adi_moves)
-        ops.expand(3, trail.view(-1, 54), dtype=torch.bfloat16, child_onehot=child[: 30 * n_pad])
+        ops.scramble_prefixes(3, adi_moves, out=trail)
+        ops.expand(3, trail.view(-1, 54), dtype=torch.bfloat16, child_onehot=child[: 30 * cubes])
 
     t = time_launches(torch, adi_batch, 3, warmup=1)
-    n_par = 30 * ((cubes + 15) // 16 * 16)
+    n_par = 30 * cubes
     entry("config4_3x3_adi_prefixes_plus_expand", t, n_par, "parents/s",
-          n_par * (54 + 12 * (960 + 1 + 4)) + 30 * cubes * (2 * 54 + 6))
-    del child, adi_moves
+          n_par * (54 + 12 * (960 + 1 + 4)) + cubes * 30 * (1 + 54))
+    t = time_launches(torch, lambda: ops.scramble_prefixes(3, adi_moves, out=trail), 5, warmup=2)
+    entry("scramble_prefixes_3x3_139810x30", t, n_par, "prefix states/s", cubes * 30 * (1 + 54))
+    del child, adi_moves, trail
+    torch.cuda.empty_cache()
+    out["config4_adi_iteration_4Mi"] = measure_adi_iteration(torch, adi, ops, dev, cubes, out["config4_3x3_adi_expand_4Mi_parents"]["ms"])
 
     # 2x2x2 ADI shape: 6 children + their bf16 one-hot rows per parent (kernel K3c)
     n = 4 * 2 ** 20
@@ -313,7 +405,67 @@ def measure_other_configs(torch, ops, adi, dev, peak_gbs):
     out["drop_in_get_random_samples"] = measure_drop_in_adi(torch, dev)
     out["drop_in_env_step_latency"] = measure_drop_in_step(torch, dev)
     out["mcts_2x2_batched_search"] = measure_mcts(torch, dev)
+    out["config3_3x3_whole_64Mi_on_one_gpu"] = measure_config3_whole(torch, ops, dev, peak_gbs)
     return out
+
+
+def measure_config3_whole(torch, ops, dev, peak_gbs):
+    """SURVEY.md 8d config 3 as ONE device's job: 64 Mi instances x depth 30 (what `--scaling strong --gpus 1` runs
+    as the headline): 2 GB of moves in, 3.6 GB of sticker rows + verdicts out per launch."""
+    n, d = 64 * 2 ** 20, 30
+    gen = torch.Generator(device=dev).manual_seed(1234)
+    moves = torch.randint(0, 12, (n, d), dtype=torch.uint8, device=dev, generator=gen)
+    st = torch.empty((n, 54), dtype=torch.uint8, device=dev)
+    so = torch.empty(n, dtype=torch.uint8, device=dev)
+    rw = torch.empty(n, dtype=torch.float32, device=dev)
+    t = time_launches(torch, lambda: ops.scramble(3, moves, out=st, solved=so, reward=rw), 10)
+    gbs = n * (d + 54 + 5) / t / 1e9
+    return {"value": n * d / t, "unit": "transitions/s", "ms": t * 1e3, "algorithmic_GBps": gbs, "hbm_frac": gbs / peak_gbs,
+            "instances": n}
+
+
+def measure_adi_iteration(torch, adi, ops, dev, cubes, expand_alone_ms):
+    """One ADI iteration measured AS an iteration (cube_env.py:177-252: scramble prefixes -> 12 children -> net ->
+    targets) at BASELINE config 4's size, 139 810 cubes x 30 = 4 194 300 parents, DeepCube's layer shapes
+    ([1024, 256, 128], config.yaml) in bfloat16 reading K3's bf16 buffer directly, phases device-timed."""
+    nn = torch.nn
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.enc = nn.Sequential(nn.Flatten(), nn.Linear(480, 1024), nn.ELU(), nn.Linear(1024, 256), nn.ELU())
+            self.pol = nn.Sequential(nn.Linear(256, 128), nn.ELU(), nn.Linear(128, 12))
+            self.val = nn.Sequential(nn.Linear(256, 128), nn.ELU(), nn.Linear(128, 1))
+
+        def forward(self, x):
+            if x.dim() == 2:
+                x = x.unsqueeze(0)
+            h = self.enc(x)
+            return self.val(h), self.pol(h)
+
+    torch.manual_seed(0)
+    net = Net().to(dev).to(torch.bfloat16)
+    gen = torch.Generator(device=dev).manual_seed(5)
+    moves = torch.randint(0, 12, (cubes, 30), dtype=torch.uint8, device=dev, generator=gen)
+    adi.generate_samples(3, moves[:4096], net, 1.0)                      # warm-up (cuBLAS heuristics, allocator)
+    torch.cuda.synchronize()
+    timers = {}
+    res = adi.generate_samples(3, moves, net, 1.0, timers=timers)
+    del res
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    res = adi.generate_samples(3, moves, net, 1.0)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    del res
+    torch.cuda.empty_cache()
+    non_net = timers["prefixes_ms"] + timers["expand_ms"] + timers["targets_ms"]
+    p = cubes * 30
+    return {"parents": p, "samples_per_s": p / wall, "ms": wall * 1e3, "phases_ms": timers, "non_net_ms": non_net,
+            "cube_expand_alone_ms": expand_alone_ms, "non_net_over_expand": non_net / expand_alone_ms,
+            "net": "DeepCube [1024, 256, 128] bf16, stock torch (out of scope: model.py)",
+            "forward_chunk_parents": adi.DEFAULT_FORWARD_CHUNK,
+            "note": "non-net = prefixes (one launch, cube-major) + expansion incl. the parents' one-hot rows + target assembly"}
 
 
 def measure_drop_in_step(torch, dev):
@@ -382,13 +534,25 @@ def measure_mcts(torch, dev):
     roots, _, _ = ops.scramble(2, torch.randint(0, 6, (n_trees, depth), dtype=torch.uint8, device=dev, generator=gen),
                                want_flags=False)
     table = torch.randint(0, 6, (n_trees, 8 * (num_sim + 1)), generator=torch.Generator().manual_seed(3), dtype=torch.uint8)
-    search = mcts_batch.BatchedMCTS(gpu_net, 2, num_sim=num_sim)
-    search.run(roots[:256], rand_table=table[:256])            # warm-up
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    res = search.run(roots, rand_table=table)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
+
+    def timed_search(model, obs_dtype):
+        search = mcts_batch.BatchedMCTS(model, 2, num_sim=num_sim, obs_dtype=obs_dtype)
+        search.run(roots[:256], rand_table=table[:256])        # warm-up
+        best, res = None, None
+        for _ in range(3):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            res = search.run(roots, rand_table=table)
+            torch.cuda.synchronize()
+            dt_ = time.perf_counter() - t0
+            best = dt_ if best is None else min(best, dt_)
+        return best, res
+
+    dt, res = timed_search(gpu_net, torch.float32)
+    timers = {}
+    mcts_batch.BatchedMCTS(gpu_net, 2, num_sim=num_sim).run(roots, rand_table=table, timers=timers)
+    import copy
+    dt16, res16 = timed_search(copy.deepcopy(gpu_net).to(torch.bfloat16), torch.bfloat16)
     sims = int(res["n_sims"].sum())
     env = ScalarCubeEnv(2)
     torch.set_num_threads(1)
@@ -402,6 +566,11 @@ def measure_mcts(torch, dev):
     cpu_dt = time.perf_counter() - t0
     return {"simulations_per_s_batched_gpu": sims / dt, "simulations_per_s_reference_semantics_1_core": cpu_sims / cpu_dt,
             "trees": n_trees, "solved": int(res["solved"].sum()), "ms": dt * 1e3, "net_weights": weights,
+            "phases_ms_float32_net": timers,
+            "bf16_net": {"ms": dt16 * 1e3, "solved": int(res16["solved"].sum()),
+                         "simulations_per_s": int(res16["n_sims"].sum()) / dt16,
+                         "note": "the same search with the net (and the leaves' one-hot rows) in bfloat16: the float32 "
+                                 "net's SIMT GEMMs are two thirds of the float32 search's time"},
             "note": "one simulation = traverse + leaf expansion (6 children, net value/policy) + back-propagation "
                     "(mcts.py:36-130); 65 536 cubes scrambled 8 deep, 50 simulations each"}
 
@@ -452,6 +621,113 @@ def measure_drop_in_adi(torch, dev):
                     "(cube_env.py:177-252); 200 cubes x 30 per call; includes building the Python dicts"}
 
 
+def source_sha16():
+    """Fingerprint of the scramble kernel's sources: a profile-derived figure (roofline.traffic) is only quoted
+    when it was captured from exactly these sources."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("scramble.cu", "cube_threads.cuh", "cube_common.cuh", "cube_tables.cuh", "cube_sched.cuh", "cube_bulk.cuh"):
+        with open(os.path.join(ROOT, "rubiks_cube_solver_b200", "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def measure_e2e(torch, ops, cdist, args, dev, rank, world, n, depth, size, barrier, moves, states, solved):
+    """The metric end to end through the host-buffer C ABI (pinned host arrays in, pinned host arrays out, every
+    copy inside the timed region), on all ranks at once, max over ranks -- next to the plain-copy ceiling of the
+    SAME byte counts on the SAME box measured in the SAME run (every rank copying concurrently), so the line says
+    how far the pipeline is from what the bus gives at this N.
+
+    Headline: batched `reset(seed, depth)` (cube_env.py:50-69) = cube_pipeline_reset_host: 4 bytes per cube in
+    (the moves are drawn on the device, bit-equal to np.random.RandomState(seed).randint), sticker rows + done
+    flags + rewards out.  Beside it: host-supplied moves (round 1's e2e: 30 bytes per cube in), and both without
+    the reward array (it is +-1 by `done`)."""
+    S = ops.N_STICKERS[size]
+    pipe = ops.HostScramblePipeline(size, depth, chunk_instances=args.e2e_chunk, n_stages=3, device=dev)
+    h_moves = moves.cpu().pin_memory()
+    h_seeds = (torch.arange(n, dtype=torch.int64) + rank * n).to(torch.int32).pin_memory()      # seeds 0 .. world*n-1
+    h_states = torch.empty((n, S), dtype=torch.uint8).pin_memory()
+    h_solved = torch.empty(n, dtype=torch.uint8).pin_memory()
+    h_reward = torch.empty(n, dtype=torch.float32).pin_memory()
+    steps = max(2, min(args.steps, args.e2e_steps))
+
+    def timed(fn):
+        for _ in range(2):
+            fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        torch.cuda.synchronize()
+        dt = cdist.max_over_ranks((time.perf_counter() - t0) / steps, dev)
+        barrier()
+        return dt
+
+    d_seeds = torch.empty(n, dtype=torch.int32, device=dev)
+    d_reward = torch.empty(n, dtype=torch.float32, device=dev)
+    s_out, s_in = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+    def plain_copies(h2d, reward):
+        with torch.cuda.stream(s_out):
+            h_states.copy_(states, non_blocking=True)
+            h_solved.copy_(solved, non_blocking=True)
+            if reward:
+                h_reward.copy_(d_reward, non_blocking=True)
+        with torch.cuda.stream(s_in):
+            if h2d == "moves":
+                moves.copy_(h_moves, non_blocking=True)
+            else:
+                d_seeds.copy_(h_seeds, non_blocking=True)
+        s_out.synchronize()
+        s_in.synchronize()
+
+    variants = {}
+    counts = {}
+    for name, fn, h2d, reward in (
+            ("reset_from_seeds", lambda: counts.__setitem__("seeds", pipe.reset(h_seeds, h_states, h_solved, h_reward)[3]), "seeds", True),
+            ("reset_from_seeds_no_reward", lambda: pipe.reset(h_seeds, h_states, h_solved, None, want_reward=False), "seeds", False),
+            ("host_moves", lambda: counts.__setitem__("moves", pipe.run(h_moves, h_states, h_solved, h_reward)[3]), "moves", True),
+            ("host_moves_no_reward", lambda: pipe.run(h_moves, h_states, h_solved, None, want_reward=False), "moves", False)):
+        t = timed(fn)
+        c = timed(lambda: plain_copies(h2d, reward))
+        variants[name] = {"ms_per_step": t * 1e3, "value": world * n * depth / t, "ceiling_ms": c * 1e3,
+                          "frac_of_ceiling": c / t,
+                          "h2d_bytes_per_step": n * (depth if h2d == "moves" else 4),
+                          "d2h_bytes_per_step": n * (S + 1 + (4 if reward else 0))}
+    # parity of what came back through the pipeline (host moves ran last: h_states holds its rows)
+    counters = ops.new_counters(dev)
+    moves.copy_(h_moves)
+    ref_states, ref_solved, _ = ops.scramble(size, moves, counters=counters)
+    assert bool((h_states[:4096] == ref_states[:4096].cpu()).all()) and counts["moves"] == int(counters[0])
+    seeded = ops.scramble(size, ops.moves_from_seeds(size, h_seeds[:4096].to(torch.int64) & 0xffffffff, depth, device=dev))[0]
+    pipe.reset(h_seeds[:4096].contiguous(), h_states[:4096])
+    assert bool((h_states[:4096] == seeded.cpu()).all())
+    pipe.close()
+    head = variants["reset_from_seeds"]
+    e2e = {"value": head["value"], "unit": "transitions/s", "h2d_bytes_per_step": head["h2d_bytes_per_step"],
+           "d2h_bytes_per_step": head["d2h_bytes_per_step"], "ms_per_step": head["ms_per_step"], "steps": steps,
+           "ceiling_ms": head["ceiling_ms"], "frac_of_ceiling": head["frac_of_ceiling"],
+           "ceiling": "plain pinned D2H of the outputs || H2D of the inputs, same byte counts, all %d ranks at once, max over ranks" % world,
+           "api": "cube_pipeline_reset_host (C ABI) via ops.HostScramblePipeline.reset: batched reset(seed, %d), pinned host buffers" % depth,
+           "variants": variants}
+    return e2e
+
+
+def replay_own_rows(torch, ops, dev, size, moves, states, solved, reward, rank, n_check=4096):
+    """After the timed region every rank replays rows of ITS OWN slice through the plain-C oracle (the first half
+    of the sample from the head of the slice, the rest random) and demands byte equality."""
+    import numpy as np
+    from oracle import cube_c
+    n = moves.shape[0]
+    half = min(n, n_check // 2)
+    idx = np.unique(np.concatenate((np.arange(half), np.random.RandomState(100 + rank).randint(n, size=n_check - half))))
+    idx_t = torch.from_numpy(idx).to(dev)
+    want, ws, wr, _ = cube_c.scramble(size, moves[idx_t].cpu().numpy())
+    ok = bool((states[idx_t].cpu().numpy() == want).all()) and bool((solved[idx_t].cpu().numpy().astype(bool) == ws).all()) \
+        and bool((reward[idx_t].cpu().numpy() == wr).all())
+    return ok, int(idx.size)
+
+
 def run_b200_arm(args):
     import torch
     import rubiks_cube_solver_b200 as R
@@ -467,14 +743,13 @@ def run_b200_arm(args):
     # one process per GPU: keep this rank's host threads and pinned buffers on the GPU's own NUMA node
     numa = cdist.bind_host_to_gpu_node(local) if world > 1 and not args.no_numa_bind else {"numa_node": None}
 
-    n, depth, size = args.instances_per_gpu, DEPTH, CUBE_SIZE
+    n, depth, size = instances_per_gpu(args, world), DEPTH, CUBE_SIZE
     S = ops.N_STICKERS[size]
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     moves = torch.randint(0, 12, (n, depth), dtype=torch.uint8, device=dev, generator=gen)
     states = torch.empty((n, S), dtype=torch.uint8, device=dev)
     solved = torch.empty(n, dtype=torch.uint8, device=dev)
     reward = torch.empty(n, dtype=torch.float32, device=dev)
-    counters = ops.new_counters(dev)
     # The path's only collective (north star: "NCCL used only for the final solved-count and reward
     # reductions"): every step adds into its own pre-zeroed int64[4] counter row, and ONE SUM all-reduce
     # over the rows of the timed steps closes the timed region, so every step's global solved / produced
@@ -518,7 +793,12 @@ def run_b200_arm(args):
     drain()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    align = torch.zeros(1, dtype=torch.int32, device=dev)
     barrier()
+    # The host-side barrier releases the ranks a few tens of microseconds apart, and the closing all-reduce then
+    # waits for the last one: that start skew is not work.  A device-side all-reduce in front of the start event
+    # lines the GPUs' streams up (the steps behind it are already queued when it completes).
+    cdist.reduce_counters(align)
     clocks.recording = True
     e0.record()
     for _ in range(args.steps):
@@ -536,6 +816,14 @@ def run_b200_arm(args):
     solved_total, produced_total = int(totals[0]), int(totals[1])
     assert produced_total == world * n, (produced_total, world * n)
 
+    # parity on THIS rank's slice, every rank (sampled replay through the oracle)
+    ok, n_replayed = replay_own_rows(torch, ops, dev, size, moves, states, solved, reward, rank)
+    bad = torch.tensor([0 if ok else 1, n_replayed, int(solved.sum())], dtype=torch.int64, device=dev)
+    cdist.reduce_counters(bad)
+    assert int(bad[0]) == 0, "%d rank(s) disagree with the oracle on their own rows" % int(bad[0])
+    assert int(bad[2]) == solved_total, (int(bad[2]), solved_total)
+    parity = {"rows_replayed_through_oracle": int(bad[1]), "ranks": world, "solved_flags_sum_equals_counters": True}
+
     # roofline of the dominant kernel: kernel-only launches, CUDA events on the launching stream
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
@@ -548,15 +836,23 @@ def run_b200_arm(args):
     kern_s = local_step_s
     isolated_s = time_launches(torch, lambda: ops.scramble(size, moves, out=states, solved=solved, reward=reward), 20)
     alg_bytes = n * (depth + S + 1 + 4)
-    traffic = None
+    # DRAM bytes of one launch come from an `ncu --set full` capture (profiles/): quoted only when that capture
+    # was taken from exactly the sources this library was built from, and scaled by the instance count
+    traffic, traffic_note = None, "no capture of these sources"
     prof = os.path.join(ROOT, "profiles", "scramble3_dram_bytes_per_launch.json")
     if os.path.exists(prof):
         try:
-            traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+            rec = json.load(open(prof))
+            if rec.get("source_sha16") == source_sha16():
+                traffic = rec["dram_bytes_per_launch"] * n / rec["instances_per_launch"]
+                traffic_note = rec.get("from", "")
+            else:
+                traffic_note = "profiles/scramble3_dram_bytes_per_launch.json is from other sources (stale): not quoted"
         except Exception:                                   # noqa: BLE001
             traffic = None
     roofline = {"bound": "hbm", "kernel": "scramble_pairs_kernel<3,30,2>", "achieved": alg_bytes / kern_s / 1e9,
                 "peak": peak_gbs, "unit": "GB/s", "frac": alg_bytes / kern_s / 1e9 / peak_gbs, "traffic": traffic,
+                "traffic_source": traffic_note,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                 "kernel_ms": kern_s * 1e3, "kernel_ms_isolated": isolated_s * 1e3,
                 "transitions_per_s_kernel_only": n * depth / kern_s,
@@ -564,40 +860,20 @@ def run_b200_arm(args):
                         "(PRMT), not by HBM (SURVEY.md 8d, DESIGN.md): the HBM fraction is reported as the contract "
                         "asks; see profiles/"}
 
-    # end to end through the host-buffer C-ABI pipeline (pinned host memory, copies inside the timed region)
-    pipe = ops.HostScramblePipeline(size, depth, chunk_instances=args.e2e_chunk, n_stages=3, device=dev)
-    h_moves = moves.cpu().pin_memory()
-    h_states = torch.empty((n, S), dtype=torch.uint8).pin_memory()
-    h_solved = torch.empty(n, dtype=torch.uint8).pin_memory()
-    h_reward = torch.empty(n, dtype=torch.float32).pin_memory()
-    e2e_steps = max(2, min(args.steps, args.e2e_steps))
-    for _ in range(2):
-        pipe.run(h_moves, h_states, h_solved, h_reward)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        _, _, _, e2e_count = pipe.run(h_moves, h_states, h_solved, h_reward)
-    torch.cuda.synchronize()
-    e2e_s = cdist.max_over_ranks((time.perf_counter() - t0) / e2e_steps, dev)
-    barrier()
-    counters.zero_()
-    ops.scramble(size, moves, out=states, solved=solved, reward=reward, counters=counters)
-    assert bool((h_states[:4096] == states[:4096].cpu()).all()) and e2e_count == int(counters[0])
-    e2e = {"value": total_tr / e2e_s, "unit": "transitions/s", "h2d_bytes_per_step": n * depth,
-           "d2h_bytes_per_step": n * (S + 1 + 4), "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
-           "api": "cube_pipeline_scramble_host (C ABI) via ops.HostScramblePipeline.run, pinned host buffers"}
-    pipe.close()
-    del h_moves, h_states, h_solved, h_reward
+    e2e = measure_e2e(torch, ops, cdist, args, dev, rank, world, n, depth, size, barrier, moves, states, solved)
 
     line = {
         "metric": "cube transitions/sec", "value": value, "unit": "transitions/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": step_s * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "cube_size": size, "depth": depth, "instances_per_gpu": n,
-                   "instances_total": world * n, "sm_count": R.load_library().cube_sm_count(), "l2": "inputs (252 MB/GPU) and outputs (495 MB/GPU) exceed the 126 MB L2",
-                   "collective": ("int64[4] all-reduce(SUM) per step, asynchronous" if args.reduce_every_step else "one all-reduce(SUM) of the per-step int64[4] solved/produced counter rows at the end of the timed region"),
-                   "host_numa_binding_rank0": numa},
-        "solved_total": solved_total, "reward_total": 2 * solved_total - produced_total,
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": workload_config(world, n, args.scaling),
+        "details": {"sm_count": R.load_library().cube_sm_count(),
+                    "l2": "inputs (%d MB/GPU) and outputs (%d MB/GPU) exceed the 126 MB L2" % (n * depth >> 20, n * (S + 5) >> 20),
+                    "collective": ("int64[4] all-reduce(SUM) per step, asynchronous" if args.reduce_every_step else
+                                   "one all-reduce(SUM) of the per-step int64[4] solved/produced counter rows at the end of "
+                                   "the timed region; a device-side all-reduce in front of the start event aligns the ranks"),
+                    "host_numa_binding_rank0": numa},
+        "solved_total": solved_total, "reward_total": 2 * solved_total - produced_total, "parity": parity,
         "e2e": e2e, "roofline": roofline, "gpu_launches": args.steps, "clocks": clocks.summary(),
     }
 
@@ -607,18 +883,7 @@ def run_b200_arm(args):
             torch.cuda.empty_cache()
             line["other_configs"] = measure_other_configs(torch, ops, adi, dev, peak_gbs)
         if not args.skip_cpu:
-            procs = host_procs()
-            pool = CpuReferencePool(size, procs)
-            dt, n_tr = pool.run(depth, args.cpu_cubes_per_proc)
-            pool.close()
-            line["cpu_baseline"] = {
-                "value": n_tr / dt, "unit": "transitions/s", "cores": procs, "kind": "port",
-                "sample": "%d processes x %d cubes x depth %d = %d transitions of the 3x3x3 per-cube Python env "
-                          "(oracle/scalar_env.py, reference semantics cube_env.py:71-111)" % (
-                              procs, args.cpu_cubes_per_proc, depth, n_tr)}
-            cv, threads = cpu_c_oracle(size, depth, 2 ** 21)
-            line["cpu_baseline_c"] = {"value": cv, "unit": "transitions/s", "cores": threads, "kind": "port",
-                                      "sample": "plain-C oracle (OpenMP), 2 Mi instances x depth 30"}
+            line.update(cpu_baselines(size, depth, args.cpu_cubes_per_proc))
     if rank == 0:
         emit(line)
     if world > 1:
@@ -650,10 +915,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=("b200", "reference"), default="b200")
     ap.add_argument("--instances-per-gpu", type=int, default=N_PER_GPU)
+    ap.add_argument("--scaling", choices=("weak", "strong"), default="weak",
+                    help="weak: --instances-per-gpu on every rank; strong: --instances-total split over the ranks "
+                         "(SURVEY.md 8d config 3 whole: N = 1 runs all 64 Mi instances on one GPU)")
+    ap.add_argument("--instances-total", type=int, default=64 * 2 ** 20)
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--e2e-chunk", type=int, default=1 << 19)
     ap.add_argument("--cpu-cubes-per-proc", type=int, default=15000)
-    ap.add_argument("--ref-seconds", type=float, default=45.0)
+    ap.add_argument("--ref-seconds", type=float, default=60.0)
     ap.add_argument("--reduce-every-step", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-other", action="store_true")

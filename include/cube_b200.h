@@ -58,6 +58,17 @@ extern "C" {
 #define CUBE_DTYPE_F32 1
 #define CUBE_DTYPE_U8 2
 
+/* One-hot encodings of a 3x3x3 state ([20, 24]: row = slot, corners 3 * piece + ori, edges 2 * piece + ori).
+ * REFERENCE is the reference's table as shipped (py333.py:140-198): its corner part is lossy -- row 6 of
+ * corner_pieceDefs is mirrored and 21 reachable hashes are unassigned -- and it is what a model trained
+ * with the reference expects; it is the default everywhere and bit-exact against the reference.
+ * EXACT is an opt-in bijection with the same layout: slot 6 read the right way round, every rotation of
+ * every corner assigned (piece, ori) <- np.roll(home colours, ori) like py222; edges are unchanged.  Only
+ * EXACT can be decoded (cube_decode).  2x2x2 has a single encoding (py222's, already exact): both values
+ * mean the same there. */
+#define CUBE_ENCODING_REFERENCE 0
+#define CUBE_ENCODING_EXACT 1
+
 int cube_abi_version(void);
 const char* cube_last_error(void);
 
@@ -94,6 +105,13 @@ int cube_moves_from_seeds(int cube_size, const uint32_t* seeds, int64_t n, int d
 int cube_scramble(int cube_size, const uint8_t* moves, int64_t n, int depth, uint8_t* states_out,
                   uint8_t* solved, float* reward, uint64_t* counters, void* stream);
 
+/* Scramble, then one step, fused -- `state = env.reset(seed, k); env.step(a)` (cube_env.py:50-111) for n
+ * instances in one launch: the `depth` moves and then actions[i] are applied in registers, only the final
+ * sticker row, its done flag and its reward are written (BASELINE configs[2] read literally: "scramble + step").
+ *   actions [n] uint8 in; everything else as cube_scramble.  Equals cube_scramble on [moves | actions]. */
+int cube_scramble_step(int cube_size, const uint8_t* moves, const uint8_t* actions, int64_t n, int depth,
+                       uint8_t* states_out, uint8_t* solved, float* reward, uint64_t* counters, void* stream);
+
 /* Every prefix of every scramble, in ONE launch -- the parents of an ADI batch: get_random_samples
  * (cube_env.py:187-194) emits a sample after EVERY move of every cube, cube by cube.
  *   moves      [n, depth]    uint8  in
@@ -122,8 +140,9 @@ int cube_solved(int cube_size, const uint8_t* states, int64_t n, uint8_t* solved
 
 /* sim_state_to_state (cube_env.py:132-152): one-hot network input of each row,
  * [n, 20, 24] or [n, 7, 21] elements of `dtype` (bf16 / f32 / u8), exactly one 1
- * per one-hot row; 3x3x3 corners use the reference's table as shipped. */
-int cube_encode(int cube_size, const uint8_t* states, int64_t n, void* onehot, int dtype, void* stream);
+ * per one-hot row; `encoding` = CUBE_ENCODING_REFERENCE (3x3x3 corners through the reference's table as
+ * shipped) or CUBE_ENCODING_EXACT. */
+int cube_encode(int cube_size, const uint8_t* states, int64_t n, void* onehot, int dtype, int encoding, void* stream);
 
 /* ADI / MCTS expansion -- the child loop of get_target_value (cube_env.py:212-238)
  * and of MCTS.expand (mcts.py:96-101) for n parents at once, children in action order.
@@ -135,7 +154,7 @@ int cube_encode(int cube_size, const uint8_t* states, int64_t n, void* onehot, i
  * The reference stops at the first solved child (cube_env.py:217-220); here all A
  * children are produced and `solved` lets the caller apply that override. */
 int cube_expand(int cube_size, const uint8_t* states, int64_t n, uint8_t* children, void* child_onehot,
-                void* parent_onehot, int dtype, uint8_t* solved, float* reward, uint64_t* counters,
+                void* parent_onehot, int dtype, int encoding, uint8_t* solved, float* reward, uint64_t* counters,
                 void* stream);
 
 /* ADI target assembly -- the tail of get_target_value (cube_env.py:239-252) for n parents whose
@@ -182,11 +201,12 @@ typedef struct cube_mcts_tree {
     uint8_t* leaf_state;                  /* [B, S]          out: sticker row of the leaf that was reached */
     int32_t* flags;                       /* [1]  |= 1 path_cap exceeded, 2 rand_table exhausted, 4 n_slots exceeded,
                                            *            8 rand_table holds an action >= A (taken as 0)           */
-    /* memoised dict lookups (the library's own scratch; child_slot starts at 255, the rest at 0) */
-    uint8_t* child_slot;                  /* [B, M, A]       slot of the child's node once a traversal found it, 255 = unknown */
-    uint8_t* child_seen;                  /* [B, M, A]       leading node slots already compared with that child's key, no match */
-    uint8_t* miss_key;                    /* [B, KEY]        out: the key the last traversal failed to find         */
-    int32_t* miss_seen;                   /* [B]             out: node slots it was compared with                   */
+    /* the dict lookup `key in children_and_data` (mcts.py:57), resolved eagerly by cube_mcts_update */
+    uint8_t* child_slot;                  /* [B, M, A]       slot of the child's node, 255 = the child is not in the tree
+                                           *                  (library scratch: start it at 255)                          */
+    int32_t* sim_counter;                 /* [1] or NULL     device-side simulation index: every cube_mcts_traverse adds 1 (start
+                                           *                  it at -1) and cube_mcts_update uses it INSTEAD of its sim_index
+                                           *                  argument -- lets a caller replay one captured simulation (CUDA graph) */
 } cube_mcts_tree_t;
 
 /* MCTS.traverse (mcts.py:52-81) for every active tree: from the root to the first key that is not in
@@ -198,8 +218,9 @@ int cube_mcts_traverse(int cube_size, const cube_mcts_tree_t* tree, float cpuct,
  * policy [B, A] from the network; W = value_min, N = L = 0), back-propagate along the path
  * (W = max(W, value), L -= 150, N += 1: mcts.py:122-129) and, if a child of the new leaf is solved,
  * write path actions + that child to actions_out [B, path_cap + 1] (int8), n_actions [B],
- * n_sims [B] = sim_index + 1 and clear `active`.  n_active (int32 on the device, or NULL) += trees that are
- * still searching after this simulation, so a caller can stop early without reading `active` back. */
+ * n_sims [B] = sim_index + 1 and clear `active`.  n_active (int32 [number of simulations] on the device, or
+ * NULL): n_active[sim_index] += trees that are still searching after this simulation, so a caller can stop
+ * early without reading `active` back. */
 int cube_mcts_update(int cube_size, const cube_mcts_tree_t* tree, const uint8_t* leaf_key,
                      const uint8_t* child_key_new, const uint8_t* child_done_new, const float* value,
                      const float* policy, float value_min, int sim_index, int8_t* actions_out,
@@ -213,13 +234,14 @@ int cube_mcts_update(int cube_size, const cube_mcts_tree_t* tree, const uint8_t*
  *   parent_codes  [n, KEY]    uint8  out or NULL
  *   parent_onehot [n, R, C]   dtype  out or NULL     children / solved / reward / counters as in cube_expand */
 int cube_expand_codes(int cube_size, const uint8_t* states, int64_t n, uint8_t* children, uint8_t* child_codes,
-                      uint8_t* parent_codes, void* parent_onehot, int dtype, uint8_t* solved, float* reward,
+                      uint8_t* parent_codes, void* parent_onehot, int dtype, int encoding, uint8_t* solved, float* reward,
                       uint64_t* counters, void* stream);
 
 /* state_to_sim_state (cube_env.py:154-175 + py222 getStickers): one-hot [n, 7, 21] of
- * `dtype` -> sticker rows [n, 24].  2x2x2 only: for cube_size 3 the reference raises
- * NotImplementedError (cube_env.py:171-172) and this returns CUBE_ERR_SIZE. */
-int cube_decode(int cube_size, const void* onehot, int dtype, int64_t n, uint8_t* states_out, void* stream);
+ * `dtype` -> sticker rows [n, 24].  For cube_size 3 the reference raises NotImplementedError
+ * (cube_env.py:171-172: its corner encoding cannot be inverted) and so does CUBE_ENCODING_REFERENCE here
+ * (CUBE_ERR_SIZE); with CUBE_ENCODING_EXACT one-hot [n, 20, 24] -> sticker rows [n, 54]. */
+int cube_decode(int cube_size, const void* onehot, int dtype, int encoding, int64_t n, uint8_t* states_out, void* stream);
 
 /* counters[2] += number of entries of actions[0..count) that are >= A. */
 int cube_validate_actions(int cube_size, const uint8_t* actions, int64_t count, uint64_t* counters,
@@ -247,6 +269,20 @@ int cube_pipeline_destroy(cube_pipeline_t* p);
 int cube_pipeline_scramble_host(cube_pipeline_t* p, const uint8_t* moves_host, int64_t n,
                                 uint8_t* states_out_host, uint8_t* solved_host, float* reward_host,
                                 int64_t* solved_count);
+
+/* Batched reset(seed, k) (cube_env.py:50-69) for host arrays: only 4 bytes per instance cross the bus on the
+ * way in -- the moves np.random.RandomState(seed).randint(A, size=depth) are drawn on the device
+ * (cube_moves_from_seeds) and scrambled there.  The handle's depth must be 1..128.
+ *   seeds_host [n] uint32 in; the outputs as in cube_pipeline_scramble_host (solved_host / reward_host may be
+ *   NULL: the reward is +1 where solved, -1 elsewhere, so a caller that wants it can derive it). */
+int cube_pipeline_reset_host(cube_pipeline_t* p, const uint32_t* seeds_host, int64_t n, uint8_t* states_out_host,
+                             uint8_t* solved_host, float* reward_host, int64_t* solved_count);
+
+/* Page-locked host buffer on transparent huge pages: 2 MiB-aligned, MADV_HUGEPAGE, touched, then
+ * cudaHostRegister'ed (portable).  For the host arrays of cube_pipeline_*: with one process per GPU copying
+ * at once, 2 MiB pages need 512 times fewer DMA address translations than cudaMallocHost's 4 KiB pages. */
+int cube_host_alloc(int64_t bytes, void** out);
+int cube_host_free(void* p);
 
 /* ---- single-cube host front end (the drop-in CubeEnv's per-call path) ---------------------
  * The reference's callers drive ONE cube per call (env.reset / env.step / get_obs:

@@ -185,3 +185,66 @@ def adi_targets(child_values, solved, parent_values, depth, temperature):
 def reference_moves(size, seed, depth):
     """The move sequence `reset(seed, depth)` draws (cube_env.py:62-68)."""
     return np.random.RandomState(seed).randint(T.N_ACTIONS[size], size=depth)
+
+
+# ---- opt-in EXACT 3x3x3 encoding (not in the reference: the spec of include/cube_b200.h CUBE_ENCODING_EXACT) ----
+# The shipped corner table is lossy (row 6 of corner_pieceDefs is read the wrong way round, 21 reachable
+# hashes unassigned, py333.py:140-180).  The exact encoding keeps the reference's layout and hash weights,
+# reads slot 6 like the other seven slots and assigns all 24 rotations the py222 way:
+# (piece, ori) <- np.roll(home colours of the piece, ori).  Derived here from this oracle's own constants,
+# independently of the product's table generator.
+def _exact_corner_tables():
+    defs = T.CORNER_DEFS_3.copy()
+    defs[6] = defs[6][[0, 2, 1]]                                # [29, 15, 26]
+    home = T.SOLVED[3][defs]                                    # [8, 3] colours of every piece at home
+    inds = np.full((62, 2), -1, dtype=np.int64)
+    for p in range(8):
+        for o in range(3):
+            h = int(np.roll(home[p], o) @ T.CORNER_HASH_W)
+            assert inds[h, 0] < 0, "the exact corner hash must be injective"
+            inds[h] = (p, o)
+    return defs, home, inds
+
+
+CORNER_DEFS_EXACT, CORNER_HOME_EXACT, CORNER_INDS_EXACT = _exact_corner_tables()
+
+
+def onehot_columns_exact(states):
+    """[N, 20] column of the 1 per row in the EXACT 3x3x3 encoding; -1 where a corner triple is no cubie at all."""
+    s = np.asarray(states).astype(np.int64)
+    hc = s[:, CORNER_DEFS_EXACT] @ T.CORNER_HASH_W
+    op = CORNER_INDS_EXACT[hc]
+    cols = np.empty((s.shape[0], 20), dtype=np.int64)
+    cols[:, :8] = np.where(op[:, :, 0] >= 0, op[:, :, 0] * 3 + op[:, :, 1], -1)
+    he = s[:, T.EDGE_DEFS_3] @ T.EDGE_HASH_W
+    eo = T.EDGE_INDS_3[he]
+    cols[:, 8:] = eo[:, :, 0] * 2 + eo[:, :, 1]
+    return cols
+
+
+def encode_exact(states, dtype=np.uint8):
+    cols = onehot_columns_exact(states)
+    n = cols.shape[0]
+    out = np.zeros((n, 20, 24), dtype=dtype)
+    out[np.arange(n)[:, None], np.arange(20)[None, :], np.maximum(cols, 0)] = 1
+    return out
+
+
+def decode_exact(onehot):
+    """Inverse of encode_exact: [N, 20, 24] -> sticker rows [N, 54]."""
+    onehot = np.asarray(onehot)
+    n = onehot.shape[0]
+    col = onehot.argmax(axis=2)
+    out = np.zeros((n, 54), dtype=np.uint8)
+    out[:, 4::9] = np.arange(6, dtype=np.uint8)                 # centres never move
+    rows = np.arange(n)
+    for q in range(8):
+        piece, ori = col[:, q] // 3, col[:, q] % 3
+        for k in range(3):                                      # np.roll(home, ori)[k] == home[(k - ori) % 3]
+            out[rows, CORNER_DEFS_EXACT[q, k]] = CORNER_HOME_EXACT[piece, (k - ori) % 3]
+    edge_home = T.SOLVED[3][T.EDGE_DEFS_3]                      # [12, 2]
+    for q in range(12):
+        piece, ori = col[:, 8 + q] // 2, col[:, 8 + q] % 2
+        for k in range(2):
+            out[rows, T.EDGE_DEFS_3[q, k]] = edge_home[piece, (k - ori) % 2]
+    return out

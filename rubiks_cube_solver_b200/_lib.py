@@ -10,15 +10,16 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libcube_b200.so")
 
 SYMBOLS = (
-    "cube_abi_version", "cube_last_error", "cube_sm_count", "cube_set_reserved_sms", "cube_moves_from_seeds", "cube_scramble", "cube_scramble_prefixes", "cube_scramble_prefixes_max_depth", "cube_step", "cube_walk",
+    "cube_abi_version", "cube_last_error", "cube_sm_count", "cube_set_reserved_sms", "cube_moves_from_seeds", "cube_scramble", "cube_scramble_step", "cube_scramble_prefixes", "cube_scramble_prefixes_max_depth", "cube_step", "cube_walk",
     "cube_solved", "cube_encode", "cube_expand", "cube_expand_codes", "cube_adi_targets", "cube_mcts_traverse", "cube_mcts_update", "cube_decode", "cube_validate_actions",
-    "cube_pipeline_create", "cube_pipeline_destroy", "cube_pipeline_scramble_host",
+    "cube_pipeline_create", "cube_pipeline_destroy", "cube_pipeline_scramble_host", "cube_pipeline_reset_host", "cube_host_alloc", "cube_host_free",
     "cube_env_host_create", "cube_env_host_destroy", "cube_env_host_step", "cube_env_host_scramble", "cube_env_host_encode",
 )
 
 ABI_VERSION = 2
 CUBE_ERR_SIZE, CUBE_ERR_ARG, CUBE_ERR_ALIGN, CUBE_ERR_ACTION = -1, -2, -3, -4
 DTYPE_BF16, DTYPE_F32, DTYPE_U8 = 0, 1, 2
+ENCODING_REFERENCE, ENCODING_EXACT = 0, 1
 
 _lib = None
 
@@ -56,22 +57,26 @@ def load():
     lib.cube_set_reserved_sms.argtypes = [ci]
     lib.cube_moves_from_seeds.argtypes = [ci, vp, i64, ci, vp, vp, vp]
     lib.cube_scramble.argtypes = [ci, vp, i64, ci, vp, vp, vp, vp, vp]
+    lib.cube_scramble_step.argtypes = [ci, vp, vp, i64, ci, vp, vp, vp, vp, vp]
     lib.cube_scramble_prefixes.argtypes = [ci, vp, i64, ci, vp, vp, vp, vp]
     lib.cube_scramble_prefixes_max_depth.argtypes = [ci]
     lib.cube_step.argtypes = [ci, vp, vp, i64, vp, vp, vp, vp]
     lib.cube_walk.argtypes = [ci, vp, vp, i64, ci, vp, vp, vp, vp, vp]
     lib.cube_solved.argtypes = [ci, vp, i64, vp, vp, vp, vp]
-    lib.cube_encode.argtypes = [ci, vp, i64, vp, ci, vp]
-    lib.cube_expand.argtypes = [ci, vp, i64, vp, vp, vp, ci, vp, vp, vp, vp]
-    lib.cube_expand_codes.argtypes = [ci, vp, i64, vp, vp, vp, vp, ci, vp, vp, vp, vp]
+    lib.cube_encode.argtypes = [ci, vp, i64, vp, ci, ci, vp]
+    lib.cube_expand.argtypes = [ci, vp, i64, vp, vp, vp, ci, ci, vp, vp, vp, vp]
+    lib.cube_expand_codes.argtypes = [ci, vp, i64, vp, vp, vp, vp, ci, ci, vp, vp, vp, vp]
     lib.cube_adi_targets.argtypes = [ci, vp, vp, vp, vp, vp, ci, i64, vp, vp, vp, vp]
     lib.cube_mcts_traverse.argtypes = [ci, vp, ctypes.c_float, ci, vp]
     lib.cube_mcts_update.argtypes = [ci, vp, vp, vp, vp, vp, vp, ctypes.c_float, ci, vp, vp, vp, vp, vp]
-    lib.cube_decode.argtypes = [ci, vp, ci, i64, vp, vp]
+    lib.cube_decode.argtypes = [ci, vp, ci, ci, i64, vp, vp]
     lib.cube_validate_actions.argtypes = [ci, vp, i64, vp, vp]
     lib.cube_pipeline_create.argtypes = [ci, ci, i64, ci, ctypes.POINTER(vp)]
     lib.cube_pipeline_destroy.argtypes = [vp]
     lib.cube_pipeline_scramble_host.argtypes = [vp, vp, i64, vp, vp, vp, ctypes.POINTER(i64)]
+    lib.cube_pipeline_reset_host.argtypes = [vp, vp, i64, vp, vp, vp, ctypes.POINTER(i64)]
+    lib.cube_host_alloc.argtypes = [i64, ctypes.POINTER(vp)]
+    lib.cube_host_free.argtypes = [vp]
     lib.cube_env_host_create.argtypes = [ci, ci, ctypes.POINTER(vp)]
     lib.cube_env_host_destroy.argtypes = [vp]
     lib.cube_env_host_step.argtypes = [vp, vp, ci, vp, vp, ctypes.POINTER(ci), vp]

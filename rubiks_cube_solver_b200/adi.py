@@ -23,6 +23,9 @@ from . import ops
 from ._timing import Phases as _Phases
 
 
+DEFAULT_FORWARD_CHUNK = 1 << 17      # parents per expand -> forward chunk (measured: tools/adi_iteration.py)
+
+
 def scramble_prefixes(cube_size, moves):
     """All prefix states of every scramble, cube-major: [n, depth, S] uint8 with
     out[i, k] = state of cube i after moves[i, 0..k] (cube_env.py:187-191).
@@ -68,13 +71,16 @@ def model_dtype(model, default=torch.float32):
 
 @torch.no_grad()
 def generate_samples(cube_size, moves, model, temperature, model_device=None, onehot_dtype=None,
-                     forward_chunk=8192, timers=None):
+                     forward_chunk=DEFAULT_FORWARD_CHUNK, timers=None):
     """ADI samples for every prefix of every scramble in `moves` ([n, depth] uint8, CUDA).
 
     `model(x)` must return (value [B,1], policy) like DeepCube.forward (model.py:31-45).  `onehot_dtype`
     defaults to the dtype the model computes in (bf16 / f32), so the net reads K3's buffer directly.
-    `forward_chunk` = parents per expand -> forward chunk (x A children x D elements: 8192 3x3x3 parents in
-    bf16 are 94 MB of one-hot rows, consumed from L2).  Results are cube-major (cube 0 depth 1..d, cube 1
+    `forward_chunk` = parents per expand -> forward chunk (x A children x D elements).  Measured on B200 with
+    DeepCube [1024, 256, 128] in bf16 (tools/adi_iteration.py): the net, not HBM, bounds the iteration (218 ms of
+    227 ms for 4 Mi parents), chunks small enough to stay in the 126 MB L2 (8192 parents = 94 MB) lose more to
+    launch overhead than they save, so the default is 131 072 parents (1.5 GB of bf16 one-hot rows per chunk);
+    what chunking does buy is that the [P, A, D] batch (48 GB) never exists as a whole.  Results are cube-major (cube 0 depth 1..d, cube 1
     ...), the order in which the reference appends to its replay buffer.  `timers`: an optional dict that
     receives the milliseconds spent per phase (prefixes / expand / net / targets), device-timed.
     """

@@ -102,6 +102,17 @@ int cube_scramble(int cube_size, const uint8_t* moves, int64_t n, int depth, uin
                                                      (unsigned long long*)counters, (cudaStream_t)stream));
 }
 
+int cube_scramble_step(int cube_size, const uint8_t* moves, const uint8_t* actions, int64_t n, int depth,
+                       uint8_t* states_out, uint8_t* solved, float* reward, uint64_t* counters, void* stream)
+{
+    CUBE_CHECK_SIZE("cube_scramble_step");
+    if (n < 0 || depth < 0 || (n > 0 && (!states_out || !actions || (depth > 0 && !moves))))
+        return fail(CUBE_ERR_ARG, "cube_scramble_step");
+    if (misaligned(moves) || misaligned(states_out) || misaligned4(reward)) return fail(CUBE_ERR_ALIGN, "cube_scramble_step");
+    CUBE_DONE("cube_scramble_step", cube::launch_scramble(cube_size, moves, n, depth, states_out, solved, reward,
+                                                          (unsigned long long*)counters, (cudaStream_t)stream, actions));
+}
+
 int cube_scramble_prefixes_max_depth(int cube_size)
 {
     CUBE_CHECK_SIZE("cube_scramble_prefixes_max_depth");
@@ -164,7 +175,7 @@ int cube_mcts_traverse(int cube_size, const cube_mcts_tree_t* tree, float cpuct,
 {
     CUBE_CHECK_SIZE("cube_mcts_traverse");
     if (!tree || tree->n_trees < 0 || tree->n_slots < 1 || tree->n_slots > 255 || tree->path_cap < 1 || tree->rand_cap < 1 ||
-        (tree->n_trees > 0 && (!tree->child_slot || !tree->child_seen || !tree->miss_key || !tree->miss_seen)))
+        (tree->n_trees > 0 && !tree->child_slot))
         return fail(CUBE_ERR_ARG, "cube_mcts_traverse");
     CUBE_DONE("cube_mcts_traverse", cube::launch_mcts_traverse(cube_size, *tree, cpuct, virtual_loss, (cudaStream_t)stream));
 }
@@ -176,8 +187,7 @@ int cube_mcts_update(int cube_size, const cube_mcts_tree_t* tree, const uint8_t*
     CUBE_CHECK_SIZE("cube_mcts_update");
     if (!tree || tree->n_trees < 0 || tree->n_slots < 1 || tree->n_slots > 255 || tree->path_cap < 1 || tree->rand_cap < 1 ||
         (tree->n_trees > 0 && (!leaf_key || !child_key_new || !child_done_new || !value || !policy || !actions_out ||
-                               !n_actions || !n_sims || !tree->child_slot || !tree->child_seen || !tree->miss_key ||
-                               !tree->miss_seen)))
+                               !n_actions || !n_sims || !tree->child_slot)))
         return fail(CUBE_ERR_ARG, "cube_mcts_update");
     CUBE_DONE("cube_mcts_update", cube::launch_mcts_update(cube_size, *tree, leaf_key, child_key_new, child_done_new, value,
                                                            policy, value_min, sim_index, actions_out, n_actions, n_sims, n_active,
@@ -198,46 +208,54 @@ int cube_adi_targets(int cube_size, const float* child_values, const uint8_t* ch
                                                            target_policy, error, (cudaStream_t)stream));
 }
 
-int cube_encode(int cube_size, const uint8_t* states, int64_t n, void* onehot, int dtype, void* stream)
+int cube_encode(int cube_size, const uint8_t* states, int64_t n, void* onehot, int dtype, int encoding, void* stream)
 {
     CUBE_CHECK_SIZE("cube_encode");
-    if (n < 0 || dtype < 0 || dtype > 2 || (n > 0 && (!states || !onehot))) return fail(CUBE_ERR_ARG, "cube_encode");
+    if (n < 0 || dtype < 0 || dtype > 2 || encoding < 0 || encoding > 1 || (n > 0 && (!states || !onehot)))
+        return fail(CUBE_ERR_ARG, "cube_encode");
     if (misaligned(states) || misaligned(onehot)) return fail(CUBE_ERR_ALIGN, "cube_encode");
     CUBE_DONE("cube_encode", cube::launch_expand(cube_size, states, n, nullptr, nullptr, onehot, dtype, nullptr,
-                                                 nullptr, nullptr, (cudaStream_t)stream));
+                                                 nullptr, nullptr, (cudaStream_t)stream, encoding));
 }
 
 int cube_expand(int cube_size, const uint8_t* states, int64_t n, uint8_t* children, void* child_onehot,
-                void* parent_onehot, int dtype, uint8_t* solved, float* reward, uint64_t* counters,
+                void* parent_onehot, int dtype, int encoding, uint8_t* solved, float* reward, uint64_t* counters,
                 void* stream)
 {
     CUBE_CHECK_SIZE("cube_expand");
-    if (n < 0 || dtype < 0 || dtype > 2 || (n > 0 && !states)) return fail(CUBE_ERR_ARG, "cube_expand");
+    if (n < 0 || dtype < 0 || dtype > 2 || encoding < 0 || encoding > 1 || (n > 0 && !states))
+        return fail(CUBE_ERR_ARG, "cube_expand");
     if (misaligned(states) || misaligned(children) || misaligned(child_onehot) || misaligned(parent_onehot))
         return fail(CUBE_ERR_ALIGN, "cube_expand");
     CUBE_DONE("cube_expand", cube::launch_expand(cube_size, states, n, children, child_onehot, parent_onehot, dtype,
                                                  solved, reward, (unsigned long long*)counters,
-                                                 (cudaStream_t)stream));
+                                                 (cudaStream_t)stream, encoding));
 }
 
 int cube_expand_codes(int cube_size, const uint8_t* states, int64_t n, uint8_t* children, uint8_t* child_codes,
-                      uint8_t* parent_codes, void* parent_onehot, int dtype, uint8_t* solved, float* reward,
+                      uint8_t* parent_codes, void* parent_onehot, int dtype, int encoding, uint8_t* solved, float* reward,
                       uint64_t* counters, void* stream)
 {
     CUBE_CHECK_SIZE("cube_expand_codes");
-    if (n < 0 || dtype < 0 || dtype > 2 || (n > 0 && !states)) return fail(CUBE_ERR_ARG, "cube_expand_codes");
+    if (n < 0 || dtype < 0 || dtype > 2 || encoding < 0 || encoding > 1 || (n > 0 && !states))
+        return fail(CUBE_ERR_ARG, "cube_expand_codes");
     if (misaligned(states) || misaligned(children) || misaligned(parent_onehot))
         return fail(CUBE_ERR_ALIGN, "cube_expand_codes");
     CUBE_DONE("cube_expand_codes", cube::launch_expand_codes(cube_size, states, n, children, child_codes, parent_codes,
                                                              parent_onehot, dtype, solved, reward,
-                                                             (unsigned long long*)counters, (cudaStream_t)stream));
+                                                             (unsigned long long*)counters, (cudaStream_t)stream, encoding));
 }
 
-int cube_decode(int cube_size, const void* onehot, int dtype, int64_t n, uint8_t* states_out, void* stream)
+int cube_decode(int cube_size, const void* onehot, int dtype, int encoding, int64_t n, uint8_t* states_out, void* stream)
 {
     CUBE_CHECK_SIZE("cube_decode");
-    if (cube_size == 3) return fail(CUBE_ERR_SIZE, "cube_decode (3x3x3 is NotImplemented in the reference too)");
-    if (n < 0 || dtype < 0 || dtype > 2 || (n > 0 && (!onehot || !states_out))) return fail(CUBE_ERR_ARG, "cube_decode");
+    if (n < 0 || dtype < 0 || dtype > 2 || encoding < 0 || encoding > 1 || (n > 0 && (!onehot || !states_out)))
+        return fail(CUBE_ERR_ARG, "cube_decode");
+    if (cube_size == 3 && encoding != CUBE_ENCODING_EXACT)
+        return fail(CUBE_ERR_SIZE, "cube_decode (the reference's 3x3x3 encoding is lossy: NotImplemented there too; use CUBE_ENCODING_EXACT)");
+    if (misaligned(onehot) || misaligned(states_out)) return fail(CUBE_ERR_ALIGN, "cube_decode");
+    if (cube_size == 3)
+        CUBE_DONE("cube_decode", cube::launch_decode3_exact(onehot, dtype, n, states_out, (cudaStream_t)stream));
     CUBE_DONE("cube_decode", cube::launch_decode2(onehot, dtype, n, states_out, (cudaStream_t)stream));
 }
 

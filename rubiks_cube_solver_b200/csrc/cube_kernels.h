@@ -10,8 +10,10 @@
 // [2] += out-of-range actions seen by cube_validate_actions, [3] reserved
 namespace cube {
 
+// `last` (n action bytes or null): one more face turn per instance after the `depth` moves (cube_scramble_step)
 int launch_scramble(int size, const uint8_t* moves, long long n, int depth, uint8_t* states_out,
-                    uint8_t* solved, float* reward, unsigned long long* counters, cudaStream_t stream);
+                    uint8_t* solved, float* reward, unsigned long long* counters, cudaStream_t stream,
+                    const uint8_t* last = nullptr);
 
 // every prefix of every scramble, cube-major: states_out[i, k, :] = row after moves[i, 0..k]; solved [n, depth] or null.
 // depth <= prefix_max_depth(size) (one tile image of 32 cubes must fit in shared memory), else CUBE_ERR_ARG
@@ -31,13 +33,13 @@ int launch_solved(int size, const uint8_t* states, long long n, uint8_t* solved,
 // reward may be null.
 int launch_expand(int size, const uint8_t* states, long long n, uint8_t* children, void* child_onehot,
                   void* parent_onehot, int dtype, uint8_t* solved, float* reward,
-                  unsigned long long* counters, cudaStream_t stream);
+                  unsigned long long* counters, cudaStream_t stream, int encoding = CUBE_ENCODING_REFERENCE);
 
 // the same expansion with compact codes (column of the 1 of every one-hot row, (R + 3) & ~3 bytes per state,
 // zero-padded) for the children and / or the parents instead of the children's one-hot rows
 int launch_expand_codes(int size, const uint8_t* states, long long n, uint8_t* children, uint8_t* child_codes,
                         uint8_t* parent_codes, void* parent_onehot, int dtype, uint8_t* solved, float* reward,
-                        unsigned long long* counters, cudaStream_t stream);
+                        unsigned long long* counters, cudaStream_t stream, int encoding = CUBE_ENCODING_REFERENCE);
 
 int launch_validate(int size, const uint8_t* actions, long long count, unsigned long long* counters,
                     cudaStream_t stream);
@@ -68,6 +70,8 @@ int launch_mcts_update(int size, const cube_mcts_tree_t& t, const uint8_t* leaf_
                        int sim_index, int8_t* actions_out, int* n_actions, int* n_sims, int* n_active, cudaStream_t stream);
 
 int launch_decode2(const void* onehot, int dtype, long long n, uint8_t* out, cudaStream_t stream);
+// 3x3x3 one-hot rows in the EXACT encoding -> sticker rows
+int launch_decode3_exact(const void* onehot, int dtype, long long n, uint8_t* out, cudaStream_t stream);
 
 int sm_count();
 // index of the current device for per-device launch state (cudaFuncSetAttribute is per device), 0..63

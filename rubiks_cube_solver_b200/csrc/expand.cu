@@ -56,7 +56,7 @@ expand_kernel(const uint8_t* __restrict__ states, long long n, uint8_t* __restri
               uint8_t* __restrict__ child_onehot, uint8_t* __restrict__ parent_onehot,
               uint8_t* __restrict__ solved, float* __restrict__ reward,
               unsigned long long* __restrict__ counters, uint8_t* __restrict__ child_codes,
-              uint8_t* __restrict__ parent_codes)
+              uint8_t* __restrict__ parent_codes, int exact)
 {
     using G = CubeGeom<SIZE>;
     constexpr int S = G::S, A = G::A, R = G::R, C = G::C;
@@ -79,9 +79,11 @@ expand_kernel(const uint8_t* __restrict__ states, long long n, uint8_t* __restri
         const int a = i / S, k = i - a * S;
         s_gather[i] = (SIZE == 3) ? kGather3[a * 56 + k] : kGather2[a * 24 + k];
     }
-    if (tid < R) s_def[tid] = (SIZE == 3) ? kHashDef3[tid] : kHashDef2[tid];
+    // `exact`: the opt-in exact 3x3x3 encoding (un-mirrored slot 6, every corner rotation assigned); the
+    // default is the reference's table as shipped.  2x2x2 has one encoding (py222's is a bijection).
+    if (tid < R) s_def[tid] = (SIZE == 3) ? (exact ? kHashDef3x[tid] : kHashDef3[tid]) : kHashDef2[tid];
     if (tid < 128) {
-        s_lut[0][tid] = (SIZE == 3) ? kCornerCol3[tid] : kPieceCode2[tid];
+        s_lut[0][tid] = (SIZE == 3) ? (exact ? kCornerCol3x[tid] : kCornerCol3[tid]) : kPieceCode2[tid];
         s_lut[1][tid] = (SIZE == 3) ? kEdgeCol3[tid] : 0;
     }
     if (tid == 0) s_solved_count = 0;
@@ -219,7 +221,7 @@ constexpr int kEncodeRows = 128;
 
 template <int SIZE, int DTYPE>
 __global__ void __launch_bounds__(kThreads, 6)
-encode_kernel(const uint8_t* __restrict__ states, long long n, uint8_t* __restrict__ onehot)
+encode_kernel(const uint8_t* __restrict__ states, long long n, uint8_t* __restrict__ onehot, int exact)
 {
     using G = CubeGeom<SIZE>;
     constexpr int S = G::S, R = G::R, C = G::C, ESIZE = OneHot<DTYPE>::ESIZE;
@@ -229,9 +231,9 @@ encode_kernel(const uint8_t* __restrict__ states, long long n, uint8_t* __restri
     __shared__ uint8_t s_lut[2][128];
 
     const int tid = threadIdx.x;
-    if (tid < R) s_def[tid] = (SIZE == 3) ? kHashDef3[tid] : kHashDef2[tid];
+    if (tid < R) s_def[tid] = (SIZE == 3) ? (exact ? kHashDef3x[tid] : kHashDef3[tid]) : kHashDef2[tid];
     if (tid < 128) {
-        s_lut[0][tid] = (SIZE == 3) ? kCornerCol3[tid] : kPieceCode2[tid];
+        s_lut[0][tid] = (SIZE == 3) ? (exact ? kCornerCol3x[tid] : kCornerCol3[tid]) : kPieceCode2[tid];
         s_lut[1][tid] = (SIZE == 3) ? kEdgeCol3[tid] : 0;
     }
     const long long base = (long long)blockIdx.x * kEncodeRows;
@@ -270,12 +272,12 @@ encode_kernel(const uint8_t* __restrict__ states, long long n, uint8_t* __restri
 template <int SIZE, int DTYPE>
 int launch_one(const uint8_t* states, long long n, uint8_t* children, void* child_onehot, void* parent_onehot,
                uint8_t* solved, float* reward, unsigned long long* counters, cudaStream_t stream,
-               uint8_t* child_codes = nullptr, uint8_t* parent_codes = nullptr)
+               uint8_t* child_codes = nullptr, uint8_t* parent_codes = nullptr, int exact = 0)
 {
     if (!children && !child_onehot && !solved && !reward && !counters && !child_codes && !parent_codes) {
         if (!parent_onehot) return 0;
         const long long tiles = (n + kEncodeRows - 1) / kEncodeRows;
-        encode_kernel<SIZE, DTYPE><<<(unsigned)tiles, kThreads, 0, stream>>>(states, n, (uint8_t*)parent_onehot);
+        encode_kernel<SIZE, DTYPE><<<(unsigned)tiles, kThreads, 0, stream>>>(states, n, (uint8_t*)parent_onehot, exact);
         return (int)cudaGetLastError();
     }
     auto kern = expand_kernel<SIZE, DTYPE>;
@@ -293,7 +295,7 @@ int launch_one(const uint8_t* states, long long n, uint8_t* children, void* chil
     }
     kern<<<(unsigned)grid, kThreads, 0, stream>>>(states, n, children, (uint8_t*)child_onehot,
                                                   (uint8_t*)parent_onehot, solved, reward, counters, child_codes,
-                                                  parent_codes);
+                                                  parent_codes, exact);
     return (int)cudaGetLastError();
 }
 
@@ -303,9 +305,10 @@ namespace cube {
 
 int launch_expand(int size, const uint8_t* states, long long n, uint8_t* children, void* child_onehot,
                   void* parent_onehot, int dtype, uint8_t* solved, float* reward,
-                  unsigned long long* counters, cudaStream_t stream)
+                  unsigned long long* counters, cudaStream_t stream, int encoding)
 {
     if (n == 0) return 0;
+    const int exact = (size == 3 && encoding == CUBE_ENCODING_EXACT) ? 1 : 0;
     if (size == 2 && child_onehot && dtype != 1) {
         // 2x2x2 ADI shape: image kernel K3c for whole tiles of parents, generic kernel for the remainder
         // (f32: the generic kernel already streams at the HBM peak, 1.03 measured; K3c with 8 parents per
@@ -343,7 +346,7 @@ int launch_expand(int size, const uint8_t* states, long long n, uint8_t* childre
 #define CUBE_EXPAND_CASE(SZ, DT)                                                                         \
     if (size == SZ && dtype == DT)                                                                       \
         return launch_one<SZ, DT>(states, n, children, child_onehot, parent_onehot, solved, reward,      \
-                                  counters, stream);
+                                  counters, stream, nullptr, nullptr, exact);
     CUBE_EXPAND_CASE(3, 0) CUBE_EXPAND_CASE(3, 1) CUBE_EXPAND_CASE(3, 2)
     CUBE_EXPAND_CASE(2, 0) CUBE_EXPAND_CASE(2, 1) CUBE_EXPAND_CASE(2, 2)
 #undef CUBE_EXPAND_CASE
@@ -354,13 +357,14 @@ int launch_expand(int size, const uint8_t* states, long long n, uint8_t* childre
 // generic kernel, whose column bytes ARE the codes
 int launch_expand_codes(int size, const uint8_t* states, long long n, uint8_t* children, uint8_t* child_codes,
                         uint8_t* parent_codes, void* parent_onehot, int dtype, uint8_t* solved, float* reward,
-                        unsigned long long* counters, cudaStream_t stream)
+                        unsigned long long* counters, cudaStream_t stream, int encoding)
 {
     if (n == 0) return 0;
+    const int exact = (size == 3 && encoding == CUBE_ENCODING_EXACT) ? 1 : 0;
 #define CUBE_EXPAND_CASE(SZ, DT)                                                                         \
     if (size == SZ && dtype == DT)                                                                       \
         return launch_one<SZ, DT>(states, n, children, nullptr, parent_onehot, solved, reward, counters,  \
-                                  stream, child_codes, parent_codes);
+                                  stream, child_codes, parent_codes, exact);
     CUBE_EXPAND_CASE(3, 0) CUBE_EXPAND_CASE(3, 1) CUBE_EXPAND_CASE(3, 2)
     CUBE_EXPAND_CASE(2, 0) CUBE_EXPAND_CASE(2, 1) CUBE_EXPAND_CASE(2, 2)
 #undef CUBE_EXPAND_CASE

@@ -345,6 +345,46 @@ def hash_defs_3():
     return words
 
 
+# ---- opt-in EXACT 3x3x3 encoding ---------------------------------------
+# The shipped corner table is lossy: row 6 of corner_pieceDefs is mirrored (read anticlockwise where the
+# other seven slots are read clockwise) and corner_pieceInds was patched by hand, so reachable states fall
+# into unassigned hashes.  The exact encoding keeps the reference's layout ([20, 24], corners: column =
+# 3 * piece + ori, edges: 2 * piece + ori, same hash weights) but reads slot 6 the right way round and
+# assigns every rotation of every corner the py222 way, (piece, ori) <- np.roll(home colours, ori):
+# a bijection between cube states and one-hot observations, which the shipped one is not.
+CORNER_DEFS_EXACT = [list(r) for r in CORNER_SLOTS_3]                  # slot 6 = [29, 15, 26]
+CORNER_COL_3X = [0] * 128       # hash -> 3*piece+ori, all 24 rotations assigned
+CORNER_HOME_3X = [0] * 24       # column -> the three colours the slot's stickers show, one per byte
+for _p in range(8):
+    _c = [s_ // 9 for s_ in CORNER_DEFS_EXACT[_p]]
+    for _o in range(3):
+        _r = _c[-_o:] + _c[:-_o] if _o else _c                          # np.roll(c, o)
+        assert CORNER_COL_3X[_r[0] + 2 * _r[1] + 10 * _r[2]] == 0 or (_p, _o) == (0, 0)
+        CORNER_COL_3X[_r[0] + 2 * _r[1] + 10 * _r[2]] = 3 * _p + _o
+        CORNER_HOME_3X[3 * _p + _o] = _r[0] | _r[1] << 8 | _r[2] << 16
+EDGE_HOME_3 = [0] * 24          # column -> the two colours (the shipped edge table is already a bijection)
+for _p, (_s0, _s1) in enumerate(EDGE_DEFS_REF):
+    _a, _b = _s0 // 9, _s1 // 9
+    EDGE_HOME_3[2 * _p] = _a | _b << 8
+    EDGE_HOME_3[2 * _p + 1] = _b | _a << 8
+# sticker -> (slot, position inside the slot) for decoding: slot | k << 5; centres: 0x80 | colour
+STICKER_SLOT_3X = [0] * 54
+for _f in range(6):
+    STICKER_SLOT_3X[9 * _f + 4] = 0x80 | _f
+for _q, _d in enumerate(CORNER_DEFS_EXACT):
+    for _k, _s in enumerate(_d):
+        STICKER_SLOT_3X[_s] = _q | _k << 5
+for _q, _d in enumerate(EDGE_DEFS_REF):
+    for _k, _s in enumerate(_d):
+        STICKER_SLOT_3X[_s] = (8 + _q) | _k << 5
+
+
+def hash_defs_3x():
+    words = [_bytes([d[0], d[1], d[2], 0]) for d in CORNER_DEFS_EXACT]
+    words += [_bytes([d[0], d[1], d[1], 1]) for d in EDGE_DEFS_REF]
+    return words
+
+
 def hash_defs_2():
     return [_bytes([d[0], d[1], d[2], 0]) for d in PIECE_DEFS_2]
 
@@ -540,6 +580,12 @@ def render():
     o.append(_c_array("uint8_t", "kCornerCol3", CORNER_COL_3, per_line=32, fmt="%d"))
     o.append(_c_array("uint8_t", "kEdgeCol3", EDGE_COL_3, per_line=32, fmt="%d"))
     o.append(_c_array("uint8_t", "kPieceCode2", PIECE_CODE_2, per_line=32, fmt="%d"))
+    o.append("// opt-in exact 3x3x3 encoding: un-mirrored slot 6, every corner rotation assigned (gen_tables.py)\n")
+    o.append(_c_array("uint32_t", "kHashDef3x", hash_defs_3x()))
+    o.append(_c_array("uint8_t", "kCornerCol3x", CORNER_COL_3X, per_line=32, fmt="%d"))
+    o.append(_c_array("uint32_t", "kCornerHome3x", CORNER_HOME_3X))
+    o.append(_c_array("uint32_t", "kEdgeHome3", EDGE_HOME_3))
+    o.append(_c_array("uint8_t", "kStickerSlot3x", STICKER_SLOT_3X, per_line=27, fmt="%d"))
     o.append("// 2x2x2 decode (py222 getStickers): sticker positions of each slot, home colours of each cubelet\n")
     o.append(_c_array("uint8_t", "kPieceDefs2", [v for r in PIECE_DEFS_2 for v in r] + [14, 18, 23], per_line=24, fmt="%d"))
     o.append(_c_array("uint8_t", "kHomeColour2", [v // 4 for r in PIECE_DEFS_2 for v in r] + [3, 4, 5], per_line=24, fmt="%d"))

@@ -5,6 +5,10 @@
 // engines run in opposite directions at the same time).  All device memory is owned by
 // the handle; the per-call entry point allocates nothing.
 #include <cuda_runtime.h>
+#include <sys/mman.h>
+#include <cstring>
+#include <map>
+#include <mutex>
 #include <new>
 
 #include "../../include/cube_b200.h"
@@ -16,6 +20,7 @@ struct cube_pipeline {
     long long chunk;                 // instances per chunk (multiple of 256)
     cudaStream_t stream[4];
     uint8_t* d_moves[4];
+    uint32_t* d_seeds[4];            // cube_pipeline_reset_host: the chunk's seeds (4 bytes per instance instead of `depth`)
     uint8_t* d_states[4];
     uint8_t* d_solved[4];
     float* d_reward[4];
@@ -30,6 +35,7 @@ void destroy(cube_pipeline* p)
     if (!p) return;
     for (int s = 0; s < p->n_stages; ++s) {
         if (p->d_moves[s]) cudaFree(p->d_moves[s]);
+        if (p->d_seeds[s]) cudaFree(p->d_seeds[s]);
         if (p->d_states[s]) cudaFree(p->d_states[s]);
         if (p->d_solved[s]) cudaFree(p->d_solved[s]);
         if (p->d_reward[s]) cudaFree(p->d_reward[s]);
@@ -59,6 +65,7 @@ int cube_pipeline_create(int cube_size, int depth, int64_t chunk_instances, int 
     for (int s = 0; s < n_stages && e == cudaSuccess; ++s) {
         e = cudaStreamCreateWithFlags(&p->stream[s], cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaMalloc(&p->d_moves[s], (size_t)p->chunk * (depth > 0 ? depth : 1));
+        if (e == cudaSuccess) e = cudaMalloc(&p->d_seeds[s], (size_t)p->chunk * sizeof(uint32_t));
         if (e == cudaSuccess) e = cudaMalloc(&p->d_states[s], (size_t)p->chunk * S);
         if (e == cudaSuccess) e = cudaMalloc(&p->d_solved[s], (size_t)p->chunk);
         if (e == cudaSuccess) e = cudaMalloc(&p->d_reward[s], (size_t)p->chunk * sizeof(float));
@@ -79,13 +86,14 @@ int cube_pipeline_destroy(cube_pipeline* p)
     return 0;
 }
 
-// moves_host [n, depth]; states_out_host [n, S]; solved_host [n] / reward_host [n] may be NULL.
-// Blocks until the host buffers are filled.  Host buffers should be page-locked for the
-// copies to overlap; pageable memory works but serialises.
-int cube_pipeline_scramble_host(cube_pipeline* p, const uint8_t* moves_host, int64_t n, uint8_t* states_out_host,
-                                uint8_t* solved_host, float* reward_host, int64_t* solved_count)
+}  // extern "C"
+
+namespace {
+
+// the chunk loop shared by the two front ends: `seeds_host` != nullptr draws the moves on the device (K0)
+int run_host(cube_pipeline* p, const uint8_t* moves_host, const uint32_t* seeds_host, int64_t n, uint8_t* states_out_host,
+             uint8_t* solved_host, float* reward_host, int64_t* solved_count)
 {
-    if (!p || n < 0 || (n > 0 && (!states_out_host || (p->depth > 0 && !moves_host)))) return CUBE_ERR_ARG;
     const size_t S = p->cube_size == 3 ? 54 : 24;
     cudaError_t e = cudaMemsetAsync(p->d_counters, 0, sizeof(unsigned long long) * 4 * p->n_stages, p->stream[0]);
     if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream[0]);
@@ -95,12 +103,20 @@ int cube_pipeline_scramble_host(cube_pipeline* p, const uint8_t* moves_host, int
         const int s = (int)(c % p->n_stages);
         const long long cnt = (n - off) < p->chunk ? (n - off) : p->chunk;
         cudaStream_t st = p->stream[s];
-        if (p->depth > 0)
+        if (seeds_host) {
+            e = cudaMemcpyAsync(p->d_seeds[s], seeds_host + off, (size_t)cnt * sizeof(uint32_t), cudaMemcpyHostToDevice, st);
+            if (e != cudaSuccess) break;
+            rc = cube::launch_seeded_moves(p->cube_size, p->d_seeds[s], cnt, p->depth, p->d_moves[s],
+                                           p->d_counters + 4 * s, st);
+            if (rc) break;
+        } else if (p->depth > 0) {
             e = cudaMemcpyAsync(p->d_moves[s], moves_host + off * p->depth, (size_t)cnt * p->depth,
                                 cudaMemcpyHostToDevice, st);
-        if (e != cudaSuccess) break;
-        rc = cube::launch_scramble(p->cube_size, p->d_moves[s], cnt, p->depth, p->d_states[s], p->d_solved[s],
-                                   p->d_reward[s], p->d_counters + 4 * s, st);
+            if (e != cudaSuccess) break;
+        }
+        rc = cube::launch_scramble(p->cube_size, p->d_moves[s], cnt, p->depth, p->d_states[s],
+                                   solved_host ? p->d_solved[s] : nullptr, reward_host ? p->d_reward[s] : nullptr,
+                                   p->d_counters + 4 * s, st);
         if (rc) break;
         e = cudaMemcpyAsync(states_out_host + off * S, p->d_states[s], (size_t)cnt * S, cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess && solved_host)
@@ -115,14 +131,87 @@ int cube_pipeline_scramble_host(cube_pipeline* p, const uint8_t* moves_host, int
     }
     if (rc) return rc;
     if (e != cudaSuccess) return (int)e;
-    if (solved_count) {
-        e = cudaMemcpy(p->h_counters, p->d_counters, sizeof(unsigned long long) * 4 * p->n_stages,
-                       cudaMemcpyDeviceToHost);
-        if (e != cudaSuccess) return (int)e;
-        long long total = 0;
-        for (int s = 0; s < p->n_stages; ++s) total += (long long)p->h_counters[4 * s];
-        *solved_count = total;
+    e = cudaMemcpy(p->h_counters, p->d_counters, sizeof(unsigned long long) * 4 * p->n_stages, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return (int)e;
+    long long total = 0, starved = 0;
+    for (int s = 0; s < p->n_stages; ++s) {
+        total += (long long)p->h_counters[4 * s];
+        starved += (long long)p->h_counters[4 * s + 3];
     }
+    if (solved_count) *solved_count = total;
+    return starved ? CUBE_ERR_ARG : 0;           // a seeded row ran out of raw draws (practically impossible, see K0)
+}
+
+}  // namespace
+
+extern "C" {
+
+// moves_host [n, depth]; states_out_host [n, S]; solved_host [n] / reward_host [n] may be NULL.
+// Blocks until the host buffers are filled.  Host buffers should be page-locked for the
+// copies to overlap; pageable memory works but serialises.
+int cube_pipeline_scramble_host(cube_pipeline* p, const uint8_t* moves_host, int64_t n, uint8_t* states_out_host,
+                                uint8_t* solved_host, float* reward_host, int64_t* solved_count)
+{
+    if (!p || n < 0 || (n > 0 && (!states_out_host || (p->depth > 0 && !moves_host)))) return CUBE_ERR_ARG;
+    return run_host(p, moves_host, nullptr, n, states_out_host, solved_host, reward_host, solved_count);
+}
+
+// Batched reset(seed, k) (cube_env.py:50-69) for host arrays: 4 bytes per instance go to the device, the moves
+// np.random.RandomState(seed).randint(A, size=depth) are drawn there (K0) and scrambled (K1p).
+int cube_pipeline_reset_host(cube_pipeline* p, const uint32_t* seeds_host, int64_t n, uint8_t* states_out_host,
+                             uint8_t* solved_host, float* reward_host, int64_t* solved_count)
+{
+    if (!p || n < 0 || p->depth < 1 || p->depth > 128 || (n > 0 && (!states_out_host || !seeds_host))) return CUBE_ERR_ARG;
+    return run_host(p, nullptr, seeds_host, n, states_out_host, solved_host, reward_host, solved_count);
+}
+
+}  // extern "C"
+
+// ---- page-locked host buffers on huge pages ---------------------------------------------------------
+// cudaMallocHost / pin_memory give 4 KiB pages.  With one process per GPU all copying at once, the DMA
+// engines' address translations (IOMMU / ATS in a virtual machine) are one more shared resource; a buffer
+// that sits on 2 MiB transparent huge pages needs 512 times fewer of them.  The buffer is 2 MiB-aligned,
+// advised MADV_HUGEPAGE, touched (so the pages exist before they are locked) and then registered.
+namespace {
+std::mutex g_host_mu;
+std::map<void*, std::pair<void*, size_t>> g_host_maps;      // aligned pointer -> (mapping base, mapping length)
+constexpr size_t kHuge = 2u << 20;
+}  // namespace
+
+extern "C" {
+
+int cube_host_alloc(int64_t bytes, void** out)
+{
+    if (!out || bytes <= 0) return CUBE_ERR_ARG;
+    const size_t len = ((size_t)bytes + kHuge - 1) / kHuge * kHuge;
+    void* base = mmap(nullptr, len + kHuge, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (base == MAP_FAILED) return (int)cudaErrorMemoryAllocation;
+    void* p = reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(base) + kHuge - 1) / kHuge * kHuge);
+    (void)madvise(p, len, MADV_HUGEPAGE);                    // best effort: THP may be disabled on the host
+    memset(p, 0, len);
+    const cudaError_t e = cudaHostRegister(p, len, cudaHostRegisterPortable);
+    if (e != cudaSuccess) {
+        munmap(base, len + kHuge);
+        return (int)e;
+    }
+    std::lock_guard<std::mutex> lock(g_host_mu);
+    g_host_maps[p] = std::make_pair(base, len + kHuge);
+    *out = p;
+    return 0;
+}
+
+int cube_host_free(void* p)
+{
+    std::pair<void*, size_t> m;
+    {
+        std::lock_guard<std::mutex> lock(g_host_mu);
+        auto it = g_host_maps.find(p);
+        if (it == g_host_maps.end()) return CUBE_ERR_ARG;
+        m = it->second;
+        g_host_maps.erase(it);
+    }
+    cudaHostUnregister(p);
+    munmap(m.first, m.second);
     return 0;
 }
 

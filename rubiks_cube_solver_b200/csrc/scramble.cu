@@ -72,7 +72,7 @@ template <int SIZE, bool FULL>
 __global__ void __launch_bounds__(kTile, CUBE_SCRAMBLE_MIN_BLOCKS)
 scramble_tile_kernel(const uint8_t* __restrict__ moves, long long n, long long tile0, int depth,
                      uint8_t* __restrict__ out, uint8_t* __restrict__ solved, float* __restrict__ reward,
-                     unsigned long long* __restrict__ counters)
+                     unsigned long long* __restrict__ counters, const uint8_t* __restrict__ last)
 {
     using G = CubeGeom<SIZE>;
     using L = ScrambleSmem<SIZE>;
@@ -116,6 +116,10 @@ scramble_tile_kernel(const uint8_t* __restrict__ moves, long long n, long long t
         CubieState st;
         cubie_init(st);
         scramble_run_staged<SIZE>(st, row, depth, s_moves, s_tbl);
+        if (last) {                                       // cube_scramble_step: one more face turn per instance
+            st.c0 = cubie_fold_twist(st.c0); st.c1 = cubie_fold_twist(st.c1);
+            cubie_move<SIZE>(st, s_tbl, (uint32_t)__ldg(last + base + row) & 0xfu);
+        }
         ok = scramble_finish<SIZE>(st, row, s_clut, s_elut, s_out);
         s_flags[row] = ok ? 1 : 0;
     }
@@ -203,7 +207,8 @@ template <int SIZE, int DEPTH, int NS>
 __global__ void __launch_bounds__(PairCfg<SIZE, NS>::kMaxWarps * 32, 1)
 scramble_pairs_kernel(const uint8_t* __restrict__ moves, int n_tiles, int depth_rt, uint8_t* __restrict__ out,
                       uint8_t* __restrict__ solved, float* __restrict__ reward, unsigned long long* __restrict__ counters,
-                      sched::Slot* slot, int tail_div, const __grid_constant__ CUtensorMap move_map)
+                      sched::Slot* slot, int tail_div, const __grid_constant__ CUtensorMap move_map,
+                      const uint8_t* __restrict__ last)
 {
     using L = PairSmem<SIZE, NS>;
     constexpr int kPairTile = L::kPairTile;
@@ -264,6 +269,21 @@ scramble_pairs_kernel(const uint8_t* __restrict__ moves, int n_tiles, int depth_
         const int buf = it & 1;
         const int next = tiles.pop(lane);
         if (next < n_tiles) stage(next, buf ^ 1);                     // prefetch the next tile's moves
+        // cube_scramble_step: the trailing action of every instance (rows 2l, 2l+1 are neighbours: one 16-bit load;
+        // 2x2x2 rows l + 32k: 32 consecutive bytes per load), fetched before the walk so its latency is hidden
+        uint32_t last_w[NS];
+        if (last) {
+            if (SIZE == 3) {
+#pragma unroll
+                for (int h = 0; h < NS; h += 2) {
+                    const uint32_t v = *reinterpret_cast<const uint16_t*>(last + (long long)tile * kPairTile + 32 * h + 2 * lane);
+                    last_w[h] = v & 0xffu; last_w[h + 1] = v >> 8;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < NS; ++k) last_w[k] = last[(long long)tile * kPairTile + 32 * k + lane];
+            }
+        }
         bulk::mbar_wait(&s_bar[buf], (uint32_t)(it >> 1) & 1u);
 
         CubieState st[NS];
@@ -271,6 +291,14 @@ scramble_pairs_kernel(const uint8_t* __restrict__ moves, int n_tiles, int depth_
         for (int k = 0; k < NS; ++k) cubie_init(st[k]);
         if constexpr (kPriv) scramble_pairs_run_swizzled<SIZE, NS>(st, s_moves + buf * mstride, lane, depth, tbl, lanereg, roff);
         else scramble_pairs_run<SIZE, (DEPTH > 0 ? DEPTH : 0), NS>(st, rows, depth, s_moves + buf * mstride, tbl, lanereg, roff);
+        if (last) {                                                   // one more face turn: the pair row (action, no move)
+#pragma unroll
+            for (int k = 0; k < NS; ++k) {
+                st[k].c0 = cubie_fold_twist(st[k].c0); st[k].c1 = cubie_fold_twist(st[k].c1);
+                const uint32_t y = (last_w[k] | 0x0c0c0c00u) * (uint32_t)(CUBE_PAIR_BASE + 256) + tbl.bias();
+                pair_apply<SIZE>(st[k], tbl, cube_prmt(y, lanereg, 0x5514u), roff);
+            }
+        }
         if (lane == 0) bulk::wait_read_all();                         // the previous store has released the out tile
         __syncwarp();
         bool ok[NS];
@@ -316,7 +344,7 @@ template <int SIZE>
 __global__ void __launch_bounds__(kTile, 4)
 scramble_deep_kernel(const uint8_t* __restrict__ moves, long long n, int depth, uint8_t* __restrict__ out,
                      uint8_t* __restrict__ solved, float* __restrict__ reward,
-                     unsigned long long* __restrict__ counters)
+                     unsigned long long* __restrict__ counters, const uint8_t* __restrict__ last)
 {
     using G = CubeGeom<SIZE>;
     using L = ScrambleSmem<SIZE>;
@@ -342,6 +370,10 @@ scramble_deep_kernel(const uint8_t* __restrict__ moves, long long n, int depth, 
                 cubie_move<SIZE>(st, s_tbl, (uint32_t)__ldg(row + k) & 0xfu);
                 if ((k & 3) == 3) { st.c0 = cubie_fold_twist(st.c0); st.c1 = cubie_fold_twist(st.c1); }
             }
+            if (last) {
+                st.c0 = cubie_fold_twist(st.c0); st.c1 = cubie_fold_twist(st.c1);
+                cubie_move<SIZE>(st, s_tbl, (uint32_t)__ldg(last + base + tid) & 0xfu);
+            }
             ok = scramble_finish<SIZE>(st, tid, s_clut, s_elut, s_out);
             if (solved) solved[base + tid] = ok ? 1 : 0;
             if (reward) reward[base + tid] = ok ? 1.0f : -1.0f;
@@ -361,7 +393,7 @@ scramble_deep_kernel(const uint8_t* __restrict__ moves, long long n, int depth, 
 
 template <int SIZE>
 int launch_classic(const uint8_t* moves, long long n, int depth, uint8_t* out, uint8_t* solved, float* reward,
-                   unsigned long long* counters, cudaStream_t stream)
+                   unsigned long long* counters, cudaStream_t stream, const uint8_t* last)
 {
     const bool staged = depth <= kMaxStagedDepth;
     const int smem = ScrambleSmem<SIZE>::bytes(depth, staged);
@@ -381,9 +413,9 @@ int launch_classic(const uint8_t* moves, long long n, int depth, uint8_t* out, u
         }
         const long long full_tiles = n / kTile;
         if (full_tiles > 0)
-            kern_full<<<(unsigned)full_tiles, kTile, smem, stream>>>(moves, n, 0, depth, out, solved, reward, counters);
+            kern_full<<<(unsigned)full_tiles, kTile, smem, stream>>>(moves, n, 0, depth, out, solved, reward, counters, last);
         if (full_tiles < n_tiles)
-            kern_tail<<<1, kTile, smem, stream>>>(moves, n, full_tiles, depth, out, solved, reward, counters);
+            kern_tail<<<1, kTile, smem, stream>>>(moves, n, full_tiles, depth, out, solved, reward, counters, last);
     } else {
         auto kern = scramble_deep_kernel<SIZE>;
         int per_sm = 0;
@@ -391,7 +423,7 @@ int launch_classic(const uint8_t* moves, long long n, int depth, uint8_t* out, u
             per_sm = 1;
         long long grid = (long long)cube::sm_count() * per_sm;
         if (grid > n_tiles) grid = n_tiles;
-        kern<<<(unsigned)grid, kTile, smem, stream>>>(moves, n, depth, out, solved, reward, counters);
+        kern<<<(unsigned)grid, kTile, smem, stream>>>(moves, n, depth, out, solved, reward, counters, last);
     }
     return (int)cudaGetLastError();
 }
@@ -430,7 +462,7 @@ bool encode_move_map(CUtensorMap* map, const uint8_t* moves, long long n_tiles, 
 // (a multiple of 32 * NS; 0 = not applicable: fewer than `min_warps` warps fit, too few rows), or -cudaError.
 template <int SIZE, int NS>
 long long launch_pairs(const uint8_t* moves, long long n, int depth, uint8_t* out, uint8_t* solved, float* reward,
-                       unsigned long long* counters, cudaStream_t stream, int min_warps)
+                       unsigned long long* counters, cudaStream_t stream, int min_warps, const uint8_t* last)
 {
     using L = PairSmem<SIZE, NS>;
     constexpr int kPairTile = L::kPairTile;
@@ -483,7 +515,7 @@ long long launch_pairs(const uint8_t* moves, long long n, int depth, uint8_t* ou
     cfg_l.attrs = attr;
     cfg_l.numAttrs = pdl ? 1 : 0;
     cudaError_t e = cudaLaunchKernelEx(&cfg_l, kern, moves, (int)n_tiles, depth, out, solved, reward, counters, slot,
-                                       sched::tail_div(), move_map);
+                                       sched::tail_div(), move_map, last);
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) return -(long long)e;
     return n_tiles * kPairTile;
@@ -491,7 +523,7 @@ long long launch_pairs(const uint8_t* moves, long long n, int depth, uint8_t* ou
 
 template <int SIZE>
 int launch_one(const uint8_t* moves, long long n, int depth, uint8_t* out, uint8_t* solved, float* reward,
-               unsigned long long* counters, cudaStream_t stream)
+               unsigned long long* counters, cudaStream_t stream, const uint8_t* last)
 {
     using G = CubeGeom<SIZE>;
     long long done = 0;
@@ -499,16 +531,17 @@ int launch_one(const uint8_t* moves, long long n, int depth, uint8_t* out, uint8
     static const bool four_ok = !(getenv("CUBE_PAIR_FOUR") && getenv("CUBE_PAIR_FOUR")[0] == '0');
     // K1p writes the verdicts of rows 2l, 2l+1 as one 16-bit / float2 word: a sliced solved / reward buffer
     // that is not aligned like that takes the byte-wise tile kernel
-    const bool aligned = ((reinterpret_cast<uintptr_t>(solved) & 1u) | (reinterpret_cast<uintptr_t>(reward) & 7u)) == 0;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(solved) & 1u) | (reinterpret_cast<uintptr_t>(reward) & 7u) |
+                          (reinterpret_cast<uintptr_t>(last) & 1u)) == 0;
     if (depth >= 1 && depth <= kMaxPairDepth && aligned && !(force && force[0] == '1')) {
         if (SIZE == 2 && four_ok)
-            done = launch_pairs<2, 4>(moves, n, depth, out, solved, reward, counters, stream, kMinWarpsFour);
-        if (done == 0) done = launch_pairs<SIZE, 2>(moves, n, depth, out, solved, reward, counters, stream, 4);
+            done = launch_pairs<2, 4>(moves, n, depth, out, solved, reward, counters, stream, kMinWarpsFour, last);
+        if (done == 0) done = launch_pairs<SIZE, 2>(moves, n, depth, out, solved, reward, counters, stream, 4, last);
         if (done < 0) return (int)-done;
     }
     if (done == n) return 0;
     return launch_classic<SIZE>(moves + done * depth, n - done, depth, out + done * G::S, solved ? solved + done : nullptr,
-                                reward ? reward + done : nullptr, counters, stream);
+                                reward ? reward + done : nullptr, counters, stream, last ? last + done : nullptr);
 }
 
 }  // namespace
@@ -516,11 +549,11 @@ int launch_one(const uint8_t* moves, long long n, int depth, uint8_t* out, uint8
 namespace cube {
 
 int launch_scramble(int size, const uint8_t* moves, long long n, int depth, uint8_t* states_out,
-                    uint8_t* solved, float* reward, unsigned long long* counters, cudaStream_t stream)
+                    uint8_t* solved, float* reward, unsigned long long* counters, cudaStream_t stream, const uint8_t* last)
 {
     if (n == 0) return 0;
-    if (size == 3) return launch_one<3>(moves, n, depth, states_out, solved, reward, counters, stream);
-    return launch_one<2>(moves, n, depth, states_out, solved, reward, counters, stream);
+    if (size == 3) return launch_one<3>(moves, n, depth, states_out, solved, reward, counters, stream, last);
+    return launch_one<2>(moves, n, depth, states_out, solved, reward, counters, stream, last);
 }
 
 }  // namespace cube

@@ -46,7 +46,7 @@ class _Tree(ctypes.Structure):
         (name, ctypes.c_void_p) for name in (
             "node_key", "child_key", "child_done", "P", "W", "N", "L", "n_nodes", "active", "root_state", "root_key",
             "rand_table", "rand_ptr", "path_node", "path_action", "path_len", "leaf_state", "flags",
-            "child_slot", "child_seen", "miss_key", "miss_seen")]
+            "child_slot", "sim_counter")]
 
 
 class BatchedMCTS(object):
@@ -76,12 +76,13 @@ class BatchedMCTS(object):
     """
 
     def __init__(self, model, cube_size, num_sim=50, cpuct=1.0, virtual_loss_const=150, value_min=-10.0,
-                 obs_dtype=torch.float32, model_device=None, path_cap=None):
+                 obs_dtype=torch.float32, model_device=None, path_cap=None, graph=False):
         if not 1 <= int(num_sim) <= 254:
             raise ValueError("num_sim must be in 1..254 (node slots are addressed with one byte)")
         self.model, self.cube_size, self.num_sim = model, cube_size, int(num_sim)
         self.cpuct, self.loss_const, self.value_min = float(cpuct), int(virtual_loss_const), float(value_min)
         self.obs_dtype, self.model_device = obs_dtype, model_device
+        self.graph = bool(graph)      # replay simulations 2.. as ONE captured CUDA graph (the model must be capturable)
         self.s, self.a = ops.N_STICKERS[cube_size], ops.N_ACTIONS[cube_size]
         self.r, self.c = ops.STATE_DIM[cube_size]
         self.key_bytes = 20 if cube_size == 3 else 8
@@ -140,59 +141,73 @@ class BatchedMCTS(object):
                  rand_ptr=z((b,), torch.int32), path_node=z((b, self.path_cap), torch.uint8),
                  path_action=z((b, self.path_cap), torch.uint8), path_len=z((b,), torch.int32),
                  leaf_state=z((b, self.s), torch.uint8), flags=z((1,), torch.int32),
-                 child_slot=torch.full((b, m, a), 255, dtype=torch.uint8, device=dev), child_seen=z((b, m, a), torch.uint8),
-                 miss_key=z((b, kb), torch.uint8), miss_seen=z((b,), torch.int32))
+                 child_slot=torch.full((b, m, a), 255, dtype=torch.uint8, device=dev),
+                 sim_counter=torch.full((1,), -1, dtype=torch.int32, device=dev))
         tree = _Tree(b, m, self.path_cap, rand_table.shape[1], *[T[name].data_ptr() for name, _ in _Tree._fields_[4:]])
         actions = torch.full((b, self.path_cap + 1), -1, dtype=torch.int8, device=dev)
         n_actions = z((b,), torch.int32)
         n_sims = torch.full((b,), self.num_sim, dtype=torch.int32, device=dev)
-        stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-
         from ._timing import Phases
         phase = Phases(timers, dev)
         # Early exit without stalling the launch queue: every update kernel counts the trees that are still
-        # searching into its own device counter; the count travels to pinned host memory behind the
-        # simulation and is looked at (never waited for) a few simulations later.
+        # searching into still[sim]; the counts travel to pinned host memory behind every simulation and are
+        # looked at (never waited for) a few simulations later.
         still = z((self.num_sim,), torch.int32)
         still_host = torch.full((self.num_sim,), -1, dtype=torch.int32).pin_memory()
-        landed = []
         direct = self.obs_dtype in ops.ONEHOT_DTYPES
+
+        def simulate():
+            """One simulation of every tree on the current stream; the simulation index lives on the device."""
+            st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            with phase("traverse_ms"):
+                _lib.check(lib.cube_mcts_traverse(self.cube_size, ctypes.byref(tree), self.cpuct, self.loss_const, st),
+                           "cube_mcts_traverse")
+            # the node keys come out of the expansion kernel as compact codes (cube_expand_codes), the leaf's
+            # observation directly in the net's dtype: no one-hot rows of the children, no argmax passes
+            with phase("expand_ms"):
+                res = ops.expand_codes(self.cube_size, T["leaf_state"], parent_dtype=self.obs_dtype if direct else torch.uint8,
+                                       want_reward=False)
+            with phase("net_ms"):
+                value, logits = self.model(res["parent_onehot"].to(mdev).to(self.obs_dtype))
+            with phase("glue_ms"):
+                value = value.float().reshape(-1).to(dev).contiguous()
+                policy = torch.nn.functional.softmax(logits.float(), dim=-1).to(dev).contiguous()
+            with phase("update_ms"):
+                _lib.check(lib.cube_mcts_update(self.cube_size, ctypes.byref(tree), res["parent_codes"].data_ptr(),
+                                                res["child_codes"].data_ptr(), res["solved"].data_ptr(), value.data_ptr(),
+                                                policy.data_ptr(), self.value_min, 0, actions.data_ptr(), n_actions.data_ptr(),
+                                                n_sims.data_ptr(), still.data_ptr(), st),
+                           "cube_mcts_update")
+            still_host.copy_(still, non_blocking=True)
+            return res, value, policy                                    # kept alive by the caller (graph replays reuse them)
+
         with torch.cuda.device(dev):
-            for sim in range(self.num_sim):
+            graph, keep, landed, sim = None, None, [], 0
+            while sim < self.num_sim:
+                done = False
                 while landed and landed[0][1].query():
-                    if int(still_host[landed.pop(0)[0]]) == 0:
-                        landed = None
-                        break
-                if landed is None:
+                    if int(landed.pop(0)[2]) == 0:
+                        done = True
+                if done:
                     break
-                with phase("traverse_ms"):
-                    _lib.check(lib.cube_mcts_traverse(self.cube_size, ctypes.byref(tree), self.cpuct, self.loss_const, stream),
-                               "cube_mcts_traverse")
-                # the node keys come out of the expansion kernel as compact codes (cube_expand_codes), the leaf's
-                # observation directly in the net's dtype: no one-hot rows of the children, no argmax passes
-                with phase("expand_ms"):
-                    res = ops.expand_codes(self.cube_size, T["leaf_state"], parent_dtype=self.obs_dtype if direct else torch.uint8,
-                                           want_reward=False)
-                    leaf_key, child_key = res["parent_codes"], res["child_codes"]
-                with phase("net_ms"):
-                    value, logits = self.model(res["parent_onehot"].to(mdev).to(self.obs_dtype))
-                with phase("glue_ms"):
-                    value = value.float().reshape(-1).to(dev).contiguous()
-                    policy = torch.nn.functional.softmax(logits.float(), dim=-1).to(dev).contiguous()
-                with phase("update_ms"):
-                    _lib.check(lib.cube_mcts_update(self.cube_size, ctypes.byref(tree), leaf_key.data_ptr(), child_key.data_ptr(),
-                                                    res["solved"].data_ptr(), value.data_ptr(), policy.data_ptr(), self.value_min,
-                                                    sim, actions.data_ptr(), n_actions.data_ptr(), n_sims.data_ptr(),
-                                                    still[sim:].data_ptr(), stream),
-                               "cube_mcts_update")
-                still_host[sim:sim + 1].copy_(still[sim:sim + 1], non_blocking=True)
+                if self.graph and sim == 1 and timers is None:
+                    # the first simulation ran eagerly (library warm-up); the rest replay one captured simulation
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph):
+                        keep = simulate()
+                if graph is not None:
+                    graph.replay()
+                else:
+                    keep = simulate()
                 ev = torch.cuda.Event()
                 ev.record(torch.cuda.current_stream(dev))
-                landed.append((sim, ev))
+                landed.append((sim, ev, still_host[sim:sim + 1]))
+                sim += 1
         phase.finish()
         flags = int(T["flags"].item())
         if flags:
-            raise RuntimeError("BatchedMCTS: capacity exceeded (flags=%d: 1 path_cap, 2 rand_table, 4 node slots)" % flags)
+            raise RuntimeError("BatchedMCTS: capacity exceeded (flags=%d: 1 path_cap, 2 rand_table, 4 node slots, "
+                               "8 rand_table action out of range)" % flags)
         # the root's statistics, for inspection / tests
         ar = torch.arange(b, device=dev)
         same = (T["node_key"] == T["root_key"][:, None, :]).all(dim=-1) & (torch.arange(m, device=dev)[None, :] < T["n_nodes"][:, None])

@@ -17,6 +17,17 @@ N_STICKERS = {2: 24, 3: 54}
 N_ACTIONS = {2: 6, 3: 12}
 STATE_DIM = {2: (7, 21), 3: (20, 24)}                      # utils.py:162-186 get_env_config
 ONEHOT_DTYPES = {torch.bfloat16: _lib.DTYPE_BF16, torch.float32: _lib.DTYPE_F32, torch.uint8: _lib.DTYPE_U8}
+ENCODINGS = {"reference": _lib.ENCODING_REFERENCE, "exact": _lib.ENCODING_EXACT}
+
+
+def _encoding(name):
+    """"reference": the reference's one-hot tables as shipped (3x3x3 corners lossy, py333.py:140-180) -- the
+    default, bit-exact against the reference.  "exact": the opt-in bijective 3x3x3 encoding (include/cube_b200.h),
+    the only one `decode` can invert.  2x2x2 has a single encoding."""
+    try:
+        return ENCODINGS[name]
+    except KeyError:
+        raise ValueError("encoding must be 'reference' or 'exact', got %r" % (name,))
 
 
 def _geom(cube_size):
@@ -97,6 +108,29 @@ def scramble(cube_size, moves, out=None, solved=None, reward=None, counters=None
     with torch.cuda.device(dev):
         _lib.check(_lib.load().cube_scramble(cube_size, _ptr(moves), n, depth, _ptr(out), _ptr(solved), _ptr(reward),
                                              _ptr(counters), _stream(dev)), "cube_scramble")
+    return out, solved, reward
+
+
+def scramble_step(cube_size, moves, actions, out=None, solved=None, reward=None, counters=None):
+    """Scramble then one step, fused (C ABI cube_scramble_step): `reset` followed by `step(actions[i])` in one
+    launch.  Returns (states, solved, reward) of the stepped cubes."""
+    s, _, _ = _geom(cube_size)
+    moves = _require_cuda(moves, "moves")
+    actions = _require_cuda(actions, "actions")
+    if moves.dim() != 2 or actions.numel() != moves.shape[0]:
+        raise ValueError("moves must be [N, depth] and actions [N]")
+    n, depth = moves.shape
+    dev = moves.device
+    if out is None:
+        out = torch.empty((n, s), dtype=torch.uint8, device=dev)
+    _require_cuda(out, "out")
+    if solved is None:
+        solved = torch.empty(n, dtype=torch.uint8, device=dev)
+    if reward is None:
+        reward = torch.empty(n, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().cube_scramble_step(cube_size, _ptr(moves), _ptr(actions), n, depth, _ptr(out), _ptr(solved),
+                                                  _ptr(reward), _ptr(counters), _stream(dev)), "cube_scramble_step")
     return out, solved, reward
 
 
@@ -186,7 +220,7 @@ def is_solved(cube_size, states, counters=None):
     return solved, reward
 
 
-def encode(cube_size, states, dtype=torch.bfloat16, out=None):
+def encode(cube_size, states, dtype=torch.bfloat16, out=None, encoding="reference"):
     """One-hot network input [N, R, C] (C ABI cube_encode)."""
     s, _, (r, c) = _geom(cube_size)
     states = _require_cuda(states, "states")
@@ -196,14 +230,14 @@ def encode(cube_size, states, dtype=torch.bfloat16, out=None):
         out = torch.empty((n, r, c), dtype=dtype, device=dev)
     _require_cuda(out, "out", dtype)
     with torch.cuda.device(dev):
-        _lib.check(_lib.load().cube_encode(cube_size, _ptr(states), n, _ptr(out), ONEHOT_DTYPES[dtype], _stream(dev)),
-                   "cube_encode")
+        _lib.check(_lib.load().cube_encode(cube_size, _ptr(states), n, _ptr(out), ONEHOT_DTYPES[dtype], _encoding(encoding),
+                                           _stream(dev)), "cube_encode")
     return out
 
 
 def expand(cube_size, states, dtype=torch.bfloat16, want_children=False, want_child_onehot=True,
            want_parent_onehot=False, child_onehot=None, counters=None, parent_onehot=None, solved=None, reward=None,
-           want_reward=True):
+           want_reward=True, encoding="reference"):
     """All A children of every state (C ABI cube_expand).
 
     Returns dict(children [N,A,S] | None, child_onehot [N,A,R,C] | None,
@@ -239,8 +273,8 @@ def expand(cube_size, states, dtype=torch.bfloat16, want_children=False, want_ch
         raise ValueError("solved / reward must be [N, %d]" % a)
     with torch.cuda.device(dev):
         _lib.check(_lib.load().cube_expand(cube_size, _ptr(states), n, _ptr(children), _ptr(child_onehot),
-                                           _ptr(parent_onehot), ONEHOT_DTYPES[dtype], _ptr(solved), _ptr(reward),
-                                           _ptr(counters), _stream(dev)), "cube_expand")
+                                           _ptr(parent_onehot), ONEHOT_DTYPES[dtype], _encoding(encoding), _ptr(solved),
+                                           _ptr(reward), _ptr(counters), _stream(dev)), "cube_expand")
     return dict(children=children, child_onehot=child_onehot, parent_onehot=parent_onehot, solved=solved,
                 reward=reward)
 
@@ -250,7 +284,8 @@ def key_bytes(cube_size):
     return (STATE_DIM[cube_size][0] + 3) & ~3
 
 
-def expand_codes(cube_size, states, parent_dtype=None, want_children=False, counters=None, want_reward=True):
+def expand_codes(cube_size, states, parent_dtype=None, want_children=False, counters=None, want_reward=True,
+                 encoding="reference"):
     """All A children of every state with COMPACT CODES instead of one-hot rows (C ABI cube_expand_codes):
     code[row] = column of the 1 of that one-hot row = `onehot.argmax(-1)`, zero-padded to key_bytes.
 
@@ -268,8 +303,8 @@ def expand_codes(cube_size, states, parent_dtype=None, want_children=False, coun
     with torch.cuda.device(dev):
         _lib.check(_lib.load().cube_expand_codes(
             cube_size, _ptr(states), n, _ptr(children), _ptr(child_codes), _ptr(parent_codes), _ptr(parent_onehot),
-            ONEHOT_DTYPES[parent_dtype] if parent_dtype is not None else _lib.DTYPE_U8, _ptr(solved), _ptr(reward),
-            _ptr(counters), _stream(dev)), "cube_expand_codes")
+            ONEHOT_DTYPES[parent_dtype] if parent_dtype is not None else _lib.DTYPE_U8, _encoding(encoding), _ptr(solved),
+            _ptr(reward), _ptr(counters), _stream(dev)), "cube_expand_codes")
     return dict(child_codes=child_codes, parent_codes=parent_codes, parent_onehot=parent_onehot, children=children,
                 solved=solved, reward=reward)
 
@@ -331,19 +366,23 @@ def adi_targets(cube_size, child_values, child_solved, parent_values, scramble_c
     return tv, tp.long(), err
 
 
-def decode(cube_size, onehot):
-    """One-hot [N, 7, 21] -> sticker rows [N, 24]; 2x2x2 only (C ABI cube_decode)."""
-    _geom(cube_size)
-    if cube_size == 3:
-        raise NotImplementedError("3x3x3 decode is not implemented in the reference (cube_env.py:171-172)")
+def decode(cube_size, onehot, encoding="reference"):
+    """One-hot -> sticker rows (C ABI cube_decode): [N, 7, 21] -> [N, 24] for 2x2x2; for 3x3x3 only the opt-in
+    exact encoding has an inverse ([N, 20, 24] -> [N, 54]) -- with the reference's lossy table this raises
+    NotImplementedError exactly like cube_env.py:171-172."""
+    s, _, (r, c) = _geom(cube_size)
+    enc = _encoding(encoding)
+    if cube_size == 3 and enc != _lib.ENCODING_EXACT:
+        raise NotImplementedError("3x3x3 decode is not implemented in the reference (cube_env.py:171-172): its corner "
+                                  "encoding is lossy; encode and decode with encoding='exact'")
     if not onehot.is_cuda or onehot.dtype not in ONEHOT_DTYPES or not onehot.is_contiguous():
         raise TypeError("onehot must be a contiguous CUDA tensor of dtype bf16, f32 or u8")
     n = onehot.shape[0]
-    if onehot.numel() != n * 147:
-        raise ValueError("onehot must be [N, 7, 21]")
-    out = torch.empty((n, 24), dtype=torch.uint8, device=onehot.device)
+    if onehot.numel() != n * r * c:
+        raise ValueError("onehot must be [N, %d, %d]" % (r, c))
+    out = torch.empty((n, s), dtype=torch.uint8, device=onehot.device)
     with torch.cuda.device(onehot.device):
-        _lib.check(_lib.load().cube_decode(cube_size, _ptr(onehot), ONEHOT_DTYPES[onehot.dtype], n, _ptr(out),
+        _lib.check(_lib.load().cube_decode(cube_size, _ptr(onehot), ONEHOT_DTYPES[onehot.dtype], enc, n, _ptr(out),
                                            _stream(onehot.device)), "cube_decode")
     return out
 
@@ -441,26 +480,51 @@ class HostScramblePipeline(object):
                                                         ctypes.byref(handle)), "cube_pipeline_create")
         self._h = handle
 
-    def run(self, moves_host, states_out=None, solved=None, reward=None):
+    def _outputs(self, n, states_out, solved, reward, want_solved, want_reward):
+        if states_out is None:
+            states_out = torch.empty((n, self.s), dtype=torch.uint8).pin_memory()
+        if solved is None and want_solved:
+            solved = torch.empty(n, dtype=torch.uint8).pin_memory()
+        if reward is None and want_reward:
+            reward = torch.empty(n, dtype=torch.float32).pin_memory()
+        return states_out, solved, reward
+
+    @staticmethod
+    def _hp(t):
+        return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+    def run(self, moves_host, states_out=None, solved=None, reward=None, want_solved=True, want_reward=True):
         """moves_host: CPU uint8 tensor [N, depth] (pinned for full overlap).  Returns CPU tensors
-        (states, solved, reward) and the solved count; blocks until they are filled."""
+        (states, solved, reward) and the solved count; blocks until they are filled.  `want_reward=False`
+        skips the reward array (4 of 59 bytes per instance on the way back: it is +-1 by `solved`)."""
         if moves_host.is_cuda or moves_host.dtype != torch.uint8 or not moves_host.is_contiguous():
             raise TypeError("moves_host must be a contiguous CPU uint8 tensor")
         n = moves_host.shape[0]
         if moves_host.shape != (n, self.depth):
             raise ValueError("moves_host must be [N, %d]" % self.depth)
-        if states_out is None:
-            states_out = torch.empty((n, self.s), dtype=torch.uint8).pin_memory()
-        if solved is None:
-            solved = torch.empty(n, dtype=torch.uint8).pin_memory()
-        if reward is None:
-            reward = torch.empty(n, dtype=torch.float32).pin_memory()
+        states_out, solved, reward = self._outputs(n, states_out, solved, reward, want_solved, want_reward)
         count = ctypes.c_int64(0)
         with torch.cuda.device(self.device):
             _lib.check(_lib.load().cube_pipeline_scramble_host(
-                self._h, ctypes.c_void_p(moves_host.data_ptr()), n, ctypes.c_void_p(states_out.data_ptr()),
-                ctypes.c_void_p(solved.data_ptr()), ctypes.c_void_p(reward.data_ptr()), ctypes.byref(count)),
-                "cube_pipeline_scramble_host")
+                self._h, ctypes.c_void_p(moves_host.data_ptr()), n, self._hp(states_out), self._hp(solved),
+                self._hp(reward), ctypes.byref(count)), "cube_pipeline_scramble_host")
+        return states_out, solved, reward, int(count.value)
+
+    def reset(self, seeds_host, states_out=None, solved=None, reward=None, want_solved=True, want_reward=True):
+        """Batched `reset(seed, depth)` (cube_env.py:50-69) for host arrays (C ABI cube_pipeline_reset_host):
+        seeds_host is a CPU int32 / uint32-valued tensor [N] (the 32 bits of each seed); only 4 bytes per cube
+        go to the device, the moves are drawn there.  Same returns as `run`."""
+        if seeds_host.is_cuda or seeds_host.dtype != torch.int32 or not seeds_host.is_contiguous():
+            raise TypeError("seeds_host must be a contiguous CPU int32 tensor (the seeds' 32 bits)")
+        if not 1 <= self.depth <= 128:
+            raise ValueError("seeded resets need 1 <= depth <= 128")
+        n = seeds_host.numel()
+        states_out, solved, reward = self._outputs(n, states_out, solved, reward, want_solved, want_reward)
+        count = ctypes.c_int64(0)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().cube_pipeline_reset_host(
+                self._h, ctypes.c_void_p(seeds_host.data_ptr()), n, self._hp(states_out), self._hp(solved),
+                self._hp(reward), ctypes.byref(count)), "cube_pipeline_reset_host")
         return states_out, solved, reward, int(count.value)
 
     def close(self):
@@ -473,3 +537,40 @@ class HostScramblePipeline(object):
             self.close()
         except Exception:  # noqa: BLE001 - interpreter shutdown
             pass
+
+
+class _HostBlock(object):
+    def __init__(self, ptr):
+        self.ptr = ptr
+
+    def __del__(self):
+        try:
+            _lib.load().cube_host_free(self.ptr)
+        except Exception:  # noqa: BLE001 - interpreter shutdown
+            pass
+
+
+def host_buffer(shape, dtype=torch.uint8):
+    """A page-locked CPU tensor on 2 MiB transparent huge pages (C ABI cube_host_alloc) for the host arrays of
+    `HostScramblePipeline`; freed when the tensor is garbage-collected."""
+    shape = tuple(int(x) for x in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+    n = 1
+    for x in shape:
+        n *= x
+    nbytes = max(1, n * torch.empty(0, dtype=dtype).element_size())
+    ptr = ctypes.c_void_p()
+    _lib.check(_lib.load().cube_host_alloc(nbytes, ctypes.byref(ptr)), "cube_host_alloc")
+    block = _HostBlock(ptr)
+    raw = (ctypes.c_uint8 * nbytes).from_address(ptr.value)
+    t = torch.frombuffer(raw, dtype=torch.uint8, count=nbytes)
+    t = t.view(dtype)[:n].view(shape)
+    _host_blocks.append(block)
+    return t
+
+
+_host_blocks = []          # views of a buffer share its storage: the mappings live until release_host_buffers()
+
+
+def release_host_buffers():
+    """Free every buffer handed out by `host_buffer` (call when none of them is in use any more)."""
+    del _host_blocks[:]

@@ -1067,3 +1067,192 @@ def test_scramble_prefixes_vs_oracle(size, n, depth):
             ops.scramble_prefixes(size, cu(moves))
     assert (adi.scramble_prefixes(size, cu(moves)).cpu().numpy() == want).all()
     assert ops.prefixes_max_depth(size) == (131 if size == 3 else 289)
+
+
+@pytest.mark.parametrize("size", SIZES)
+@pytest.mark.parametrize("obs_dtype", (torch.float32, torch.bfloat16))
+def test_batched_mcts_graph_replay_equals_eager_and_golden(size, obs_dtype):
+    """BatchedMCTS(graph=True) replays simulations 2.. as one captured CUDA graph (the simulation index lives on
+    the device): same searches as the eager loop and as the reference's own mcts.py (golden vectors).  The exact
+    net's outputs are exact in bf16 too (one-hot inputs, weights that are multiples of 1/8)."""
+    from rubiks_cube_solver_b200 import mcts_batch
+    from oracle.gen_golden import ExactSearchNet, MCTS_CFG
+    g = golden("mcts_%d.npz" % size)
+    cases = g["cases"]
+    roots = np.stack([O.scramble(size, O.reference_moves(size, int(sd), int(d))[None])[0] for sd, d in cases])
+    net = ExactSearchNet(T.STATE_DIM[size], T.N_ACTIONS[size]).to(dev())
+    cfg = MCTS_CFG["mcts"]
+    outs = []
+    for graph in (False, True):
+        search = mcts_batch.BatchedMCTS(net, size, num_sim=cfg["numMCTSSim"], cpuct=cfg["cpuct"], obs_dtype=obs_dtype,
+                                        virtual_loss_const=cfg["virtual_loss_const"], value_min=cfg["value_min"], graph=graph)
+        outs.append(search.run(cu(roots), seeds=[1000 + int(sd) for sd, _ in cases]))
+    for out in outs:
+        assert (out["n_sims"].cpu().numpy() == g["n_sims"]).all() and (out["n_actions"].cpu().numpy() == g["n_actions"]).all()
+        assert (out["actions"].cpu().numpy()[:, :g["actions"].shape[1]] == g["actions"]).all()
+        assert (out["n_nodes"].cpu().numpy() == g["n_nodes"]).all()
+        assert (out["root_N"].cpu().numpy() == g["root_N"]).all() and (out["root_L"].cpu().numpy() == g["root_L"]).all()
+        assert (out["root_W"].cpu().numpy().astype(np.float64) == g["root_W"]).all()
+
+
+@pytest.mark.parametrize("size", SIZES)
+@pytest.mark.parametrize("num_sim", (1, 2, 3, 4, 30))
+def test_batched_mcts_short_searches_full_action_lists(size, num_sim):
+    """a traversal may bounce (U then U' is back at the root's key), so a returned path can be longer
+    than num_sim + 1; the action list must come back whole (n_actions <= actions.shape[1]) and equal to the
+    per-cube search of oracle/mcts_ref.py.  Many shallow cubes, tiny simulation budgets."""
+    import random
+    from rubiks_cube_solver_b200 import mcts_batch
+    from oracle import mcts_ref
+    from oracle.gen_golden import ExactSearchNet
+    from oracle.scalar_env import ScalarCubeEnv
+    n = 300 if num_sim < 30 else 60
+    rng = np.random.RandomState(31 * num_sim + size)
+    A = T.N_ACTIONS[size]
+    depths = rng.randint(1, 5, size=n)
+    roots = np.stack([O.scramble(size, rng.randint(A, size=(1, int(d))))[0] for d in depths])
+    gpu_net = ExactSearchNet(T.STATE_DIM[size], A).to(dev())
+    cpu_net = ExactSearchNet(T.STATE_DIM[size], A)
+    out = mcts_batch.BatchedMCTS(gpu_net, size, num_sim=num_sim, graph=(num_sim == 30)).run(cu(roots), seeds=list(range(n)))
+    assert int(out["n_actions"].max()) <= out["actions"].shape[1]
+    env = ScalarCubeEnv(size)
+    for i in range(n):
+        env.sim_cube = roots[i].astype(np.int64)
+        env.cube = env._observe(env.sim_cube)
+        with torch.no_grad():
+            acts, used, tree = mcts_ref.solve(cpu_net.predict, env, env.cube, num_sim, random.Random(i))
+        k = int(out["n_actions"][i])
+        assert out["actions"][i, :k].tolist() == (acts or []), i
+        assert (out["actions"][i, k:] == -1).all()
+        assert int(out["n_sims"][i]) == used and int(out["n_nodes"][i]) == len(tree.nodes), i
+        if acts:                                                         # the returned list solves the cube
+            s = roots[i][None]
+            for a in acts:
+                s = O.apply_moves(size, s, np.array([a]))
+            assert O.is_solved(size, s)[0]
+
+
+def test_batched_mcts_rejects_bad_random_actions():
+    from rubiks_cube_solver_b200 import mcts_batch
+    from oracle.gen_golden import ExactSearchNet
+    net = ExactSearchNet(T.STATE_DIM[2], 6).to(dev())
+    roots = cu(O.scramble(2, np.array([[0, 2, 4]])))
+    table = torch.full((1, 64), 6, dtype=torch.uint8)
+    with pytest.raises(IndexError):
+        mcts_batch.BatchedMCTS(net, 2, num_sim=4).run(roots, rand_table=table)
+
+
+def test_host_reset_pipeline_from_seeds_and_hugepage_buffers():
+    """cube_pipeline_reset_host: batched reset(seed, k) for host arrays (4 bytes per cube on the way in, moves
+    drawn on the device) against np.random.RandomState(seed).randint + the oracle; outputs land in huge-page
+    buffers from cube_host_alloc; solved / reward arrays are optional."""
+    for size, depth in ((3, 30), (2, 10)):
+        n = 200000 + 77
+        seeds = torch.arange(n, dtype=torch.int64) * 7 + 3
+        seeds[5] = 2 ** 32 - 1
+        packed = torch.where(seeds >= 2 ** 31, seeds - 2 ** 32, seeds).to(torch.int32).contiguous()
+        pipe = ops.HostScramblePipeline(size, depth, chunk_instances=1 << 16, n_stages=3)
+        states_buf = ops.host_buffer((n, T.N_STICKERS[size]))
+        states, solved, reward, count = pipe.reset(packed, states_out=states_buf)
+        assert states.data_ptr() == states_buf.data_ptr() and states.data_ptr() % (2 << 20) == 0
+        moves = np.stack([np.random.RandomState(int(s)).randint(T.N_ACTIONS[size], size=depth) for s in seeds[:3000]])
+        want, ws, wr, _ = C.scramble(size, moves.astype(np.uint8))
+        assert (states[:3000].numpy() == want).all() and (solved[:3000].numpy().astype(bool) == ws).all()
+        assert (reward[:3000].numpy() == wr).all()
+        dev_moves = ops.moves_from_seeds(size, seeds, depth)
+        dev_states, dev_solved, _ = ops.scramble(size, dev_moves)
+        assert (states.numpy() == dev_states.cpu().numpy()).all() and count == int(dev_solved.sum())
+        s2, so2, rw2, c2 = pipe.reset(packed[:1000].contiguous(), want_solved=False, want_reward=False)
+        assert so2 is None and rw2 is None and (s2.numpy() == want[:1000]).all() and c2 == int(ws[:1000].sum())
+        s3, so3, rw3, _ = pipe.run(torch.from_numpy(moves.astype(np.uint8)), want_reward=False)
+        assert rw3 is None and (s3.numpy() == want).all() and (so3.numpy().astype(bool) == ws).all()
+        pipe.close()
+        with pytest.raises(ValueError):
+            ops.HostScramblePipeline(size, 129, chunk_instances=1 << 12).reset(packed[:10].contiguous())
+    ops.release_host_buffers()
+
+
+def test_exact_3x3_encoding_roundtrip_and_reference_mode_unchanged():
+    """the opt-in exact 3x3x3 encoding (encoding="exact": un-mirrored corner slot 6, every
+    corner rotation assigned) is a bijection -- decode(encode(s)) == s on a million random states, in every
+    dtype -- and equals the NumPy spec (oracle.cube_np.encode_exact); the default stays the reference's lossy
+    table bit for bit (py333.py:140-180) and stays un-decodable (cube_env.py:171-172)."""
+    n = 10 ** 6
+    gen = torch.Generator(device=dev()).manual_seed(8)
+    states, _, _ = ops.scramble(3, torch.randint(0, 12, (n, 40), dtype=torch.uint8, device=dev(), generator=gen),
+                                want_flags=False)
+    states[0] = ops.solved_states(3, 1, dev())[0]
+    sample = states[:50000].cpu().numpy()
+    for dt in (torch.uint8, torch.bfloat16, torch.float32):
+        enc = ops.encode(3, states, dtype=dt, encoding="exact")
+        assert bool((ops.decode(3, enc, encoding="exact") == states).all()), dt
+        got, clean = onehot_to_u8(enc[:50000])
+        assert clean and (got == O.encode_exact(sample)).all(), dt
+        del enc
+    # one 1 per row; pieces form a permutation; twists sum to 0 mod 3, flips to 0 mod 2
+    cols = ops.encode(3, states, dtype=torch.uint8, encoding="exact").argmax(-1)
+    assert bool((cols[:, :8].div(3, rounding_mode="floor").sort(dim=1).values == torch.arange(8, device=dev())).all())
+    assert bool((cols[:, 8:].div(2, rounding_mode="floor").sort(dim=1).values == torch.arange(12, device=dev())).all())
+    assert bool(((cols[:, :8] % 3).sum(1) % 3 == 0).all()) and bool(((cols[:, 8:] % 2).sum(1) % 2 == 0).all())
+    # the reference mode is what it was: the shipped table, different from the exact one, not decodable
+    ref, _ = onehot_to_u8(ops.encode(3, states[:50000].contiguous(), dtype=torch.uint8))
+    assert (ref == O.encode(3, sample)).all() and not (ref == O.encode_exact(sample)).all()
+    assert (ref[:, 8:] == O.encode_exact(sample)[:, 8:]).all()                    # edges are the same in both
+    with pytest.raises(NotImplementedError):
+        ops.decode(3, ops.encode(3, states[:16].contiguous(), dtype=torch.uint8))
+    with pytest.raises(ValueError):
+        ops.encode(3, states[:16].contiguous(), encoding="lossless")
+    # expansion in the exact encoding: children's one-hot rows and compact codes
+    par = states[:4099].contiguous()
+    res = ops.expand(3, par, dtype=torch.bfloat16, want_children=True, want_parent_onehot=True, encoding="exact")
+    wc, ws = O.expand(3, par.cpu().numpy())
+    assert (res["children"].cpu().numpy() == wc).all() and (res["solved"].cpu().numpy().astype(bool) == ws).all()
+    got, clean = onehot_to_u8(res["child_onehot"])
+    assert clean and (got.reshape(-1, 20, 24) == O.encode_exact(wc.reshape(-1, 54))).all()
+    assert bool((ops.decode(3, res["child_onehot"].view(-1, 20, 24), encoding="exact").view(-1, 12, 54) == res["children"]).all())
+    codes = ops.expand_codes(3, par, encoding="exact")
+    assert (codes["child_codes"].cpu().numpy() == O.onehot_columns_exact(wc.reshape(-1, 54)).reshape(-1, 12, 20)).all()
+    assert (codes["parent_codes"].cpu().numpy() == O.onehot_columns_exact(par.cpu().numpy())).all()
+    # 2x2x2 has one encoding: both names give py222's
+    s2, _, _ = ops.scramble(2, torch.randint(0, 6, (5000, 14), dtype=torch.uint8, device=dev(), generator=gen), want_flags=False)
+    assert bool((ops.encode(2, s2, dtype=torch.uint8, encoding="exact") == ops.encode(2, s2, dtype=torch.uint8)).all())
+    assert bool((ops.decode(2, ops.encode(2, s2, dtype=torch.uint8), encoding="exact") == s2).all())
+    # ragged sizes of the decode kernel
+    for m in (1, 63, 64, 65, 1000):
+        e = ops.encode(3, states[:m].contiguous(), dtype=torch.bfloat16, encoding="exact")
+        assert bool((ops.decode(3, e, encoding="exact") == states[:m]).all())
+
+
+@pytest.mark.parametrize("size", SIZES)
+@pytest.mark.parametrize("n,depth", [(1, 1), (63, 30), (64 * 148 * 3 + 37, 30), (5000, 20), (4099, 31), (3000, 32), (777, 0),
+                                     (2000, 200), (1500, 321), (130, 400)])
+def test_scramble_step_fused_equals_scramble_then_step(size, n, depth):
+    """cube_scramble_step: `reset` then `step(a)` in one launch (configs[2] read literally) == the oracle's
+    scramble of [moves | action] == cube_scramble followed by cube_step, on every scramble variant (K1p flat /
+    swizzled / four-per-lane, the tile kernel's ragged tail, the deep kernel); rows whose action undoes the
+    last move of a 2-move identity come back solved."""
+    rng = np.random.RandomState(5 * n + depth + size)
+    A = T.N_ACTIONS[size]
+    moves = rng.randint(A, size=(n, depth)).astype(np.uint8)
+    act = rng.randint(A, size=n).astype(np.uint8)
+    if depth >= 2 and depth % 2 == 1:                                   # an odd palindrome-inverse, closed by the action
+        h = depth // 2
+        k = min(n, 50)
+        moves[:k, h + 1:] = moves[:k, :h][:, ::-1] ^ 1
+        act[:k] = moves[:k, h] ^ 1
+    counters = ops.new_counters(dev())
+    states, solved, reward = ops.scramble_step(size, cu(moves), cu(act), counters=counters)
+    want, ws, wr, cnt = C.scramble(size, np.concatenate((moves, act[:, None]), axis=1))
+    assert (states.cpu().numpy() == want).all()
+    assert (solved.cpu().numpy().astype(bool) == ws).all() and (reward.cpu().numpy() == wr).all()
+    assert counters.tolist()[:2] == [cnt, n]
+    if depth >= 2 and depth % 2 == 1:
+        assert ws[:min(n, 50)].all()
+    two, _, _ = ops.scramble(size, cu(moves))
+    stepped, s2, _ = ops.step(size, two, cu(act))
+    assert bool((stepped == states).all()) and bool((s2 == solved).all())
+    # an action array at an odd address takes the byte-wise kernels
+    off = torch.zeros(n + 1, dtype=torch.uint8, device=dev())
+    off[1:] = cu(act)
+    st2, _, _ = ops.scramble_step(size, cu(moves), off[1:])
+    assert bool((st2 == states).all())

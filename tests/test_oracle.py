@@ -257,3 +257,24 @@ def test_mcts_oracle_matches_reference_golden(size):
         assert [int(v) for v in root[3]] == g["root_N"][i].tolist()
         assert [float(v) for v in root[2]] == g["root_W"][i].tolist()
         assert [int(v) for v in root[4]] == g["root_L"][i].tolist()
+
+
+def test_exact_3x3_encoding_spec_is_a_bijection():
+    """oracle.cube_np.encode_exact / decode_exact (the spec of the opt-in CUBE_ENCODING_EXACT): every corner triple
+    of a reachable state is assigned, pieces form a permutation, twists / flips obey the cube's parities,
+    decode inverts encode, and the reference encoding provably is NOT injective on the same states."""
+    from oracle import cube_np as O
+    rng = np.random.RandomState(3)
+    s = O.scramble(3, rng.randint(12, size=(30000, 45)))
+    cols = O.onehot_columns_exact(s)
+    assert (cols >= 0).all()
+    assert (np.sort(cols[:, :8] // 3, axis=1) == np.arange(8)).all() and (np.sort(cols[:, 8:] // 2, axis=1) == np.arange(12)).all()
+    assert ((cols[:, :8] % 3).sum(1) % 3 == 0).all() and ((cols[:, 8:] % 2).sum(1) % 2 == 0).all()
+    enc = O.encode_exact(s)
+    assert (enc.sum(axis=2) == 1).all() and (O.decode_exact(enc) == s).all()
+    assert (O.onehot_columns_exact(O.solved_states(3, 1))[0] == np.concatenate((3 * np.arange(8), 2 * np.arange(12)))).all()
+    ref = O.encode(3, s)
+    assert (ref[:, 8:] == enc[:, 8:]).all()
+    # the shipped table maps different corner configurations to the same observation
+    corner_cfg = np.unique(s[:, O.CORNER_DEFS_EXACT.ravel()], axis=0).shape[0]
+    assert np.unique(ref[:, :8].argmax(2), axis=0).shape[0] < corner_cfg == np.unique(cols[:, :8], axis=0).shape[0]

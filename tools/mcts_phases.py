@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--trees", type=int, default=65536)
     ap.add_argument("--sims", type=int, default=50)
     ap.add_argument("--depth", type=int, default=8)
+    ap.add_argument("--variants", action="store_true", help="also time graph replay and a bf16 net")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     import bench
@@ -64,6 +65,29 @@ def main():
         wall = (time.perf_counter() - t0) * 1e3
         print(json.dumps({"trees": args.trees, "sims": args.sims, "wall_ms": wall, "solved": int(res["solved"].sum()),
                           "sims_run": int(res["n_sims"].sum()), "phases_ms": timers}), flush=True)
+    if args.variants:
+        variants(net, roots, table, args.sims)
+
+
+def variants(net, roots, table, sims):
+    """Wall time of the whole search: eager / CUDA-graph replay, float32 / bfloat16 net."""
+    import copy
+    out = {}
+    for name, dtype, graph in (("f32_eager", torch.float32, False), ("f32_graph", torch.float32, True),
+                               ("bf16_eager", torch.bfloat16, False), ("bf16_graph", torch.bfloat16, True)):
+        m = copy.deepcopy(net).to(dtype)
+        search = mcts_batch.BatchedMCTS(m, 2, num_sim=sims, obs_dtype=dtype, graph=graph)
+        search.run(roots[:256], rand_table=table[:256])
+        torch.cuda.synchronize()
+        best = None
+        for _ in range(3):
+            t0 = time.perf_counter()
+            res = search.run(roots, rand_table=table)
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) * 1e3
+            best = dt if best is None else min(best, dt)
+        out[name] = {"ms": best, "solved": int(res["solved"].sum()), "sims_run": int(res["n_sims"].sum())}
+    print(json.dumps(out), flush=True)
 
 
 if __name__ == "__main__":
