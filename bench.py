@@ -109,11 +109,14 @@ class CpuReferencePool(object):
         self.run(DEPTH if cube_size == 3 else 20, 4)        # imports + first-touch, untimed
 
     def run(self, depth, cubes_per_proc, seed0=1000, procs=None, task=_cpu_task):
-        """Returns (seconds, units): the slowest worker's own loop time (all workers run at once) and the
-        transitions (or ADI samples) all of them produced."""
+        """All workers run their share at once, each timing its own loop.  Returns (seconds, units) with
+        units / seconds = the SUM of the workers' own rates (what the cores deliver together while all are busy;
+        robust against one worker starting a few milliseconds late) and units = what they produced together."""
         procs = self.procs if procs is None else procs
         res = self.pool.map(task, [(depth, cubes_per_proc, seed0 + i) for i in range(procs)], chunksize=1)
-        return max(r[2] for r in res), sum(r[0] for r in res)
+        units = sum(r[0] for r in res)
+        rate = sum(r[0] / r[2] for r in res)
+        return units / rate, units
 
     def close(self):
         self.pool.close()

@@ -68,6 +68,29 @@ CUBE_HD bool scramble_finish(CubieState& st, int tid, const uint32_t* s_clut, co
 }
 
 
+// ---- K1x: every prefix of one scramble (cube_scramble_prefixes) ---------------------------------
+// `my` = the cube's depth move bytes; row0 = index of its first row in the tile image s_img (rows are the
+// tile's output block: cube-major, depth rows per cube).  Returns the number of solved prefixes; flags (or
+// null) receives the done flag of every prefix.  The running state stays lazy (twist fields folded every 4
+// moves like the fused scramble); each level is finished on a copy.
+template <int SIZE>
+CUBE_HD unsigned prefix_walk(const uint8_t* my, int depth, int row0, const uint32_t* s_tbl, const uint32_t* s_clut,
+                             const uint32_t* s_elut, uint8_t* s_img, uint8_t* flags)
+{
+    CubieState st;
+    cubie_init(st);
+    unsigned n_solved = 0;
+    for (int k = 0; k < depth; ++k) {
+        cubie_move<SIZE>(st, s_tbl, (uint32_t)my[k] & 0xfu);
+        if ((k & 3) == 3) { st.c0 = cubie_fold_twist(st.c0); st.c1 = cubie_fold_twist(st.c1); }
+        CubieState now = st;
+        const bool ok = scramble_finish<SIZE>(now, row0 + k, s_clut, s_elut, s_img);
+        n_solved += ok ? 1u : 0u;
+        if (flags) flags[k] = ok ? 1 : 0;
+    }
+    return n_solved;
+}
+
 // ---- K1p: fused scramble, two moves per table row --------------------------------------------
 // The pair table lives in shared memory with 256 bytes per row, every vector replicated once per
 // lane slot: 3x3x3 rows are two 16-byte vectors (P, Q) x 8 slots; 2x2x2 rows are (selectors, T0) as
@@ -336,6 +359,79 @@ CUBE_HD void scramble_pairs_run(CubieState (&st)[NS], const int (&rows)[NS], int
             for (int k = 0; k < NS; ++k) pair_apply<SIZE>(st[k], tbl, cube_prmt(y[k], lanereg, 0x5534u), roff);
         }
     }
+}
+
+// A SLICE of a deep scramble (depth > 320, scramble_sliced_kernel): `count` moves per instance starting at byte
+// offset off[k] of s_moves, applied to a state that is carried over from the previous slice.  Same schedule as
+// the generic path above: a fold first (the previous slice may have left a field at 30), then groups of five
+// words with a fold after each; the <= 4 words left over and the tail add <= 20 on top of <= 10.
+template <int SIZE, int NS, class TBL>
+CUBE_HD void scramble_pairs_run_at(CubieState (&st)[NS], const uint32_t (&off)[NS], int count, const uint8_t* s_moves,
+                                   const TBL& tbl, uint32_t lanereg, uint32_t roff)
+{
+    const uint32_t* mw = reinterpret_cast<const uint32_t*>(s_moves);
+    const int nfull = count >> 2, tail = count & 3;
+    const uint32_t bias = tbl.bias();
+    constexpr uint32_t K = (uint32_t)(CUBE_PAIR_BASE + 256);
+    uint32_t wi[NS], sh[NS], lo[NS];
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+        wi[k] = off[k] >> 2; sh[k] = (off[k] & 3u) << 3;
+        lo[k] = mw[wi[k]];
+    }
+    auto fold = [&]() {
+#pragma unroll
+        for (int k = 0; k < NS; ++k) {
+            st[k].c0 = cubie_fold_twist(st[k].c0);
+            st[k].c1 = cubie_fold_twist(st[k].c1);
+        }
+    };
+    auto word = [&](int j) {
+        uint32_t y[NS];
+#pragma unroll
+        for (int k = 0; k < NS; ++k) {
+            const uint32_t hi = mw[wi[k] + j + 1];
+            y[k] = cube_funnel_r(lo[k], hi, sh[k]) * K + bias;
+            lo[k] = hi;
+        }
+#pragma unroll
+        for (int k = 0; k < NS; ++k) pair_apply<SIZE>(st[k], tbl, cube_prmt(y[k], lanereg, 0x5514u), roff);
+#pragma unroll
+        for (int k = 0; k < NS; ++k) pair_apply<SIZE>(st[k], tbl, cube_prmt(y[k], lanereg, 0x5534u), roff);
+    };
+    fold();
+    int j = 0;
+    for (; j + 5 <= nfull; j += 5) {
+        word(j); word(j + 1); word(j + 2); word(j + 3); word(j + 4);
+        fold();
+    }
+    for (; j < nfull; ++j) word(j);
+    if (tail) {                                          // last 1..3 moves, padded with the no-move index
+        const uint32_t keep = (1u << (8 * tail)) - 1u;
+        uint32_t y[NS];
+#pragma unroll
+        for (int k = 0; k < NS; ++k) {
+            const uint32_t w = (cube_funnel_r(lo[k], mw[wi[k] + nfull + 1], sh[k]) & keep) | (0x0c0c0c0cu & ~keep);
+            y[k] = w * K + bias;
+        }
+#pragma unroll
+        for (int k = 0; k < NS; ++k) pair_apply<SIZE>(st[k], tbl, cube_prmt(y[k], lanereg, 0x5514u), roff);
+        if (tail == 3) {
+#pragma unroll
+            for (int k = 0; k < NS; ++k) pair_apply<SIZE>(st[k], tbl, cube_prmt(y[k], lanereg, 0x5534u), roff);
+        }
+    }
+}
+
+// cube_scramble_step: one more face turn after the walk -- the pair row (action, no move).  The fold first:
+// the walk may leave a twist field at 30, and a turn adds up to 2.
+template <int SIZE, class TBL>
+CUBE_HD void scramble_pairs_last(CubieState& st, uint32_t action, const TBL& tbl, uint32_t lanereg, uint32_t roff)
+{
+    st.c0 = cubie_fold_twist(st.c0);
+    st.c1 = cubie_fold_twist(st.c1);
+    const uint32_t y = (action | 0x0c0c0c00u) * (uint32_t)(CUBE_PAIR_BASE + 256) + tbl.bias();
+    pair_apply<SIZE>(st, tbl, cube_prmt(y, lanereg, 0x5514u), roff);
 }
 
 // Swizzled move tile.  In the flat tile image a lane's move words are `rows * depth` bytes apart: when

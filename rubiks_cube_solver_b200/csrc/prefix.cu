@@ -74,19 +74,9 @@ prefix_kernel(const uint8_t* __restrict__ moves, long long n, int depth, uint8_t
         }
         if (lane == 0) bulk::wait_read_all();                           // the previous tile's store has read the image
         __syncwarp();
-        if (lane < cnt) {
-            CubieState st;
-            cubie_init(st);
-            const uint8_t* my = s_mv + lane * depth;
-            for (int k = 0; k < depth; ++k) {
-                cubie_move<SIZE>(st, s_tbl, (uint32_t)my[k] & 0xfu);
-                if ((k & 3) == 3) { st.c0 = cubie_fold_twist(st.c0); st.c1 = cubie_fold_twist(st.c1); }
-                CubieState now = st;                                    // reduced copy: the running state stays lazy
-                const bool ok = scramble_finish<SIZE>(now, lane * depth + k, s_clut, s_elut, s_img);
-                n_solved += ok ? 1u : 0u;
-                if (solved) solved[(cube0 + lane) * depth + k] = ok ? 1 : 0;
-            }
-        }
+        if (lane < cnt)
+            n_solved += prefix_walk<SIZE>(s_mv + lane * depth, depth, lane * depth, s_tbl, s_clut, s_elut, s_img,
+                                          solved ? solved + (cube0 + lane) * depth : nullptr);
         bulk::fence_smem_writes();
         __syncwarp();
         uint8_t* dst_g = out + cube0 * row_bytes;

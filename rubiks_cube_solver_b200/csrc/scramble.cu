@@ -291,13 +291,9 @@ scramble_pairs_kernel(const uint8_t* __restrict__ moves, int n_tiles, int depth_
         for (int k = 0; k < NS; ++k) cubie_init(st[k]);
         if constexpr (kPriv) scramble_pairs_run_swizzled<SIZE, NS>(st, s_moves + buf * mstride, lane, depth, tbl, lanereg, roff);
         else scramble_pairs_run<SIZE, (DEPTH > 0 ? DEPTH : 0), NS>(st, rows, depth, s_moves + buf * mstride, tbl, lanereg, roff);
-        if (last) {                                                   // one more face turn: the pair row (action, no move)
+        if (last) {                                                   // cube_scramble_step: one more face turn
 #pragma unroll
-            for (int k = 0; k < NS; ++k) {
-                st[k].c0 = cubie_fold_twist(st[k].c0); st[k].c1 = cubie_fold_twist(st[k].c1);
-                const uint32_t y = (last_w[k] | 0x0c0c0c00u) * (uint32_t)(CUBE_PAIR_BASE + 256) + tbl.bias();
-                pair_apply<SIZE>(st[k], tbl, cube_prmt(y, lanereg, 0x5514u), roff);
-            }
+            for (int k = 0; k < NS; ++k) scramble_pairs_last<SIZE>(st[k], last_w[k], tbl, lanereg, roff);
         }
         if (lane == 0) bulk::wait_read_all();                         // the previous store has released the out tile
         __syncwarp();
@@ -337,6 +333,160 @@ scramble_pairs_kernel(const uint8_t* __restrict__ moves, int n_tiles, int depth_
     if (lane == 0) bulk::wait_read_all();                             // shared memory must outlive the copies' reads
     __syncthreads();
     sched::release(slot);
+}
+
+// ---- K1p, sliced: sequences deeper than kMaxPairDepth (test.py scrambles 1 000 deep, test.py:44) -------------
+// A tile's move bytes no longer fit in a warp's buffers, so they arrive in SLICES of kSlice moves per row while
+// the cubie state stays in registers from slice to slice.  A slice of a tile is 64 pieces of the row-major move
+// array, `depth` bytes apart: every lane fetches the pieces of its two rows with two small bulk copies from the
+// 16-byte boundary below each piece (the piece then starts (row * depth) & 15 bytes into its slot: the same
+// shift in every slice, because kSlice is a multiple of 16) and announces their bytes on the buffer's mbarrier
+// (32 arrivals).  Double-buffered across slices AND tiles.  64 small copies per 64 x 240 transitions are far
+// below the copy engine's rate of one small copy per ~20 cycles per SM.  Replaces the 3x cliff at depth 321
+// (the single-move kernel reading its moves byte by byte from global memory: 0.5e12 tr/s).
+constexpr int kSlice = 240;                       // moves per row and slice: a multiple of 16 (and of 4)
+constexpr int kSliceStride = kSlice + 32;         // bytes per row slot: shift <= 15, rounded up to 16
+
+template <int SIZE>
+struct SlicedSmem {
+    using G = CubeGeom<SIZE>;
+    static constexpr int kOutBytes = 64 * G::S;
+    static constexpr int kMovesAt = 16 + kOutBytes;                   // after the two mbarriers and the out tile
+    static constexpr int kPerWarpBytes = kMovesAt + 2 * 64 * kSliceStride;
+    static constexpr int kFixed = PairSmem<SIZE, 2>::kPerWarp;        // pair table + colour LUTs, as in K1p
+    __host__ __device__ static constexpr int bytes(int warps) { return kFixed + warps * kPerWarpBytes; }
+};
+
+template <int SIZE>
+__global__ void __launch_bounds__(8 * 32, 1)
+scramble_sliced_kernel(const uint8_t* __restrict__ moves, int n_tiles, int depth, uint8_t* __restrict__ out,
+                       uint8_t* __restrict__ solved, float* __restrict__ reward, unsigned long long* __restrict__ counters,
+                       const uint8_t* __restrict__ last)
+{
+    using L = SlicedSmem<SIZE>;
+    using P = PairSmem<SIZE, 2>;
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, warps = (int)(blockDim.x >> 5);
+    const uint32_t window = bulk::smem_addr(smem_raw);
+    uint8_t* smem = smem_raw + ((256u - (window & 255u)) & 255u);     // the pair table on a 256-byte boundary
+    uint8_t* s_ptbl = smem + P::kTable;
+    const PairTableShared tbl{(bulk::smem_addr(s_ptbl) >> 8) * 0x01000100u};
+    uint32_t* s_clut = reinterpret_cast<uint32_t*>(smem + P::kCornerLut);
+    uint32_t* s_elut = reinterpret_cast<uint32_t*>(smem + P::kEdgeLut);
+    uint8_t* mine = smem + L::kFixed + warp * L::kPerWarpBytes;
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(mine);              // [2]: 32 arrivals each
+    uint8_t* s_out = mine + 16;
+    uint8_t* s_moves = mine + L::kMovesAt;                            // [2][64][kSliceStride]
+
+    pair_table_fill<SIZE>(s_ptbl, tid, blockDim.x);
+    if (tid < 32) s_clut[tid] = (SIZE == 3) ? kCornerColour3[tid] : kCornerColour2[tid];
+    if (tid >= 64 && tid < 96) s_elut[tid - 64] = (SIZE == 3) ? kEdgeColour3[tid - 64] : 0u;
+    if (lane == 0) { bulk::mbar_init(&s_bar[0], 32); bulk::mbar_init(&s_bar[1], 32); }
+    __syncthreads();
+
+    const int n_slices = (depth + kSlice - 1) / kSlice;
+    int rows[2];
+    rows[0] = (SIZE == 3) ? 2 * lane : lane;
+    rows[1] = (SIZE == 3) ? 2 * lane + 1 : lane + 32;
+    uint32_t shift[2], off[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        shift[k] = (uint32_t)(((long long)rows[k] * depth) & 15);
+        off[k] = (uint32_t)(rows[k] * kSliceStride) + shift[k];
+    }
+    // the lane's two pieces of slice `s` of tile `t` into buffer `b`
+    auto stage = [&](int t, int s, int b) {
+        const int len = depth - s * kSlice < kSlice ? depth - s * kSlice : kSlice;
+        uint32_t bytes[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) bytes[k] = (shift[k] + (uint32_t)len + 15u) & ~15u;
+        bulk::mbar_expect_tx(&s_bar[b], bytes[0] + bytes[1]);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const long long g = ((long long)t * 64 + rows[k]) * depth + (long long)s * kSlice;
+            bulk::load(s_moves + (b * 64 + rows[k]) * kSliceStride, moves + (g & ~15LL), bytes[k], &s_bar[b]);
+        }
+    };
+    const uint32_t lanereg = pair_lanereg<SIZE>(lane), roff = pair_roff2(lane);
+    const ColourLutShared lut{bulk::smem_addr(s_clut), bulk::smem_addr(s_elut)};
+    unsigned n_solved = 0;
+    const int stride = (int)gridDim.x * warps;
+    int tile = (int)blockIdx.x * warps + warp;
+    if (tile < n_tiles) stage(tile, 0, 0);
+    for (unsigned it = 0; tile < n_tiles; tile += stride) {
+        CubieState st[2];
+        cubie_init(st[0]);
+        cubie_init(st[1]);
+        for (int s = 0; s < n_slices; ++s, ++it) {
+            const int buf = (int)(it & 1u);
+            __syncwarp();                                             // every lane is done with the other buffer
+            if (s + 1 < n_slices) stage(tile, s + 1, buf ^ 1);
+            else if (tile + stride < n_tiles) stage(tile + stride, 0, buf ^ 1);
+            bulk::mbar_wait(&s_bar[buf], (it >> 1) & 1u);
+            const int len = depth - s * kSlice < kSlice ? depth - s * kSlice : kSlice;
+            uint32_t o[2] = {off[0] + (uint32_t)(buf * 64 * kSliceStride), off[1] + (uint32_t)(buf * 64 * kSliceStride)};
+            scramble_pairs_run_at<SIZE, 2>(st, o, len, s_moves, tbl, lanereg, roff);
+        }
+        if (last) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+                scramble_pairs_last<SIZE>(st[k], (uint32_t)__ldg(last + (long long)tile * 64 + rows[k]), tbl, lanereg, roff);
+        }
+        if (lane == 0) bulk::wait_read_all();                         // the previous store has released the out tile
+        __syncwarp();
+        bool ok[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            ok[k] = scramble_pairs_finish<SIZE>(st[k], rows[k], lut, s_out);
+            n_solved += ok[k] ? 1u : 0u;
+        }
+        bulk::fence_smem_writes();
+        __syncwarp();
+        if (lane == 0) {
+            bulk::store(out + (long long)tile * L::kOutBytes, s_out, (uint32_t)L::kOutBytes);
+            bulk::commit();
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {                                 // a deep scramble is not verdict-bound: plain stores
+            if (solved) solved[(long long)tile * 64 + rows[k]] = ok[k] ? 1 : 0;
+            if (reward) reward[(long long)tile * 64 + rows[k]] = ok[k] ? 1.0f : -1.0f;
+        }
+    }
+    n_solved = __reduce_add_sync(0xffffffffu, n_solved);
+    if (lane == 0 && n_solved && counters) atomicAdd(&counters[0], (unsigned long long)n_solved);
+    if (blockIdx.x == 0 && tid == 0 && counters) atomicAdd(&counters[1], (unsigned long long)n_tiles * 64);
+    if (lane == 0) bulk::wait_read_all();
+}
+
+// Whole tiles of a deep batch through the sliced kernel; the LAST whole tile is left to the caller (a piece's
+// copy may run up to 15 bytes past its row: never past the move array when a tile follows).  Returns the number
+// of instances handled (0: not applicable) or -cudaError.
+template <int SIZE>
+long long launch_sliced(const uint8_t* moves, long long n, int depth, uint8_t* out, uint8_t* solved, float* reward,
+                        unsigned long long* counters, cudaStream_t stream, const uint8_t* last)
+{
+    using L = SlicedSmem<SIZE>;
+    long long n_tiles = n / 64 - 1;
+    if (n_tiles < 1) return 0;
+    if (n_tiles > 0x3fffffff) n_tiles = 0x3fffffff;
+    int warps = (227 * 1024 - 256 - L::kFixed) / L::kPerWarpBytes;
+    if (warps > 8) warps = 8;
+    if (warps < 1) return 0;
+    const int smem = L::bytes(warps) + 256 < 66048 + 256 ? 66048 + 256 : L::bytes(warps) + 256;
+    auto kern = scramble_sliced_kernel<SIZE>;
+    static std::atomic<int> configured_dev[64];
+    std::atomic<int>& cfg = configured_dev[cube::device_slot()];
+    if (smem > cfg.load(std::memory_order_relaxed)) {
+        const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return -(long long)e;
+        cfg.store(smem, std::memory_order_relaxed);
+    }
+    long long grid = (n_tiles + warps - 1) / warps;
+    if (grid > cube::persistent_ctas()) grid = cube::persistent_ctas();
+    kern<<<(unsigned)grid, warps * 32, smem, stream>>>(moves, (int)n_tiles, depth, out, solved, reward, counters, last);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return -(long long)e;
+    return n_tiles * 64;
 }
 
 // deep sequences (depth > kMaxStagedDepth): persistent CTAs, moves read straight from global
@@ -537,6 +687,11 @@ int launch_one(const uint8_t* moves, long long n, int depth, uint8_t* out, uint8
         if (SIZE == 2 && four_ok)
             done = launch_pairs<2, 4>(moves, n, depth, out, solved, reward, counters, stream, kMinWarpsFour, last);
         if (done == 0) done = launch_pairs<SIZE, 2>(moves, n, depth, out, solved, reward, counters, stream, 4, last);
+        if (done < 0) return (int)-done;
+    }
+    static const bool sliced_ok = !(getenv("CUBE_PAIR_SLICED") && getenv("CUBE_PAIR_SLICED")[0] == '0');
+    if (depth > kMaxPairDepth && aligned && sliced_ok && !(force && force[0] == '1')) {
+        done = launch_sliced<SIZE>(moves, n, depth, out, solved, reward, counters, stream, last);
         if (done < 0) return (int)-done;
     }
     if (done == n) return 0;

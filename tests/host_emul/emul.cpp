@@ -35,8 +35,73 @@ void scramble_t(const uint8_t* moves, long long n, int depth, uint8_t* out, uint
 
 // K1p: persistent pair-table kernel, one tile of 32 * NS rows at a time with the kernel's lane -> row map
 // (rows beyond the last whole tile are left untouched: the library hands them to the tile-per-CTA kernel)
+// K1p sliced (depth > 320): the kernel's staging arithmetic -- per row and slice a copy from the 16-byte
+// boundary below the piece into a 272-byte slot, the piece starting (row * depth) & 15 bytes in -- and the
+// slice runner that carries the state over.  `moves` must be readable 16 bytes past its end (the kernel never
+// stages the last tile for that reason; the emulation stages all of them).
+template <int SIZE>
+void scramble_sliced_t(const uint8_t* moves, long long n, int depth, uint8_t* out, uint8_t* solved, const uint8_t* last)
+{
+    using G = CubeGeom<SIZE>;
+    constexpr int kSlice = 240, kStride = 272;
+    const uint32_t* clut = SIZE == 3 ? kCornerColour3 : kCornerColour2;
+    std::vector<uint8_t> tbl(65792 + 256, 0xa5);
+    uint8_t* s_ptbl_mem = tbl.data() + ((16 - (reinterpret_cast<uintptr_t>(tbl.data()) & 15)) & 15);
+    for (int t = 0; t < 96; ++t) pair_table_fill<SIZE>(s_ptbl_mem, t, 96);
+    const PairTableHost s_ptbl{s_ptbl_mem};
+    std::vector<uint8_t> buf(64 * kStride + 16), s_out(64 * G::S);
+    uint8_t* s_moves = buf.data() + ((16 - (reinterpret_cast<uintptr_t>(buf.data()) & 15)) & 15);
+    const int n_slices = (depth + kSlice - 1) / kSlice;
+    for (long long tile = 0; tile * 64 + 64 <= n; ++tile) {
+        std::vector<CubieState> st(64);
+        for (auto& c : st) cubie_init(c);
+        for (int s = 0; s < n_slices; ++s) {
+            const int len = depth - s * kSlice < kSlice ? depth - s * kSlice : kSlice;
+            std::memset(s_moves, 0xee, 64 * kStride);
+            for (int row = 0; row < 64; ++row) {
+                const long long g = (tile * 64 + row) * depth + (long long)s * kSlice;
+                const uint32_t shift = (uint32_t)(((long long)row * depth) & 15);
+                std::memcpy(s_moves + row * kStride, moves + (g & ~15LL), (shift + len + 15) & ~15u);
+            }
+            for (int lane = 0; lane < 32; ++lane) {
+                int rows[2] = {SIZE == 3 ? 2 * lane : lane, SIZE == 3 ? 2 * lane + 1 : lane + 32};
+                CubieState two[2] = {st[rows[0]], st[rows[1]]};
+                uint32_t off[2];
+                for (int k = 0; k < 2; ++k) off[k] = (uint32_t)(rows[k] * kStride) + (uint32_t)(((long long)rows[k] * depth) & 15);
+                scramble_pairs_run_at<SIZE, 2>(two, off, len, s_moves, s_ptbl, pair_lanereg<SIZE>(lane), pair_roff2(lane));
+                st[rows[0]] = two[0]; st[rows[1]] = two[1];
+            }
+        }
+        for (int lane = 0; lane < 32; ++lane)
+            for (int k = 0; k < 2; ++k) {
+                const int row = SIZE == 3 ? 2 * lane + k : lane + 32 * k;
+                if (last) scramble_pairs_last<SIZE>(st[row], last[tile * 64 + row], s_ptbl, pair_lanereg<SIZE>(lane), pair_roff2(lane));
+                solved[tile * 64 + row] = scramble_pairs_finish<SIZE>(st[row], row, ColourLutHost{clut, kEdgeColour3}, s_out.data());
+            }
+        std::memcpy(out + tile * 64 * G::S, s_out.data(), (size_t)64 * G::S);
+    }
+}
+
+// K1x: all prefixes of every scramble, a tile of 32 cubes at a time with the kernel's tile image
+template <int SIZE>
+void prefixes_t(const uint8_t* moves, long long n, int depth, uint8_t* out, uint8_t* solved)
+{
+    using G = CubeGeom<SIZE>;
+    const uint32_t* tbl = SIZE == 3 ? kMoveWords3 : kMoveWords2;
+    const uint32_t* clut = SIZE == 3 ? kCornerColour3 : kCornerColour2;
+    std::vector<uint8_t> img((size_t)32 * depth * G::S + 16);
+    for (long long cube0 = 0; cube0 < n; cube0 += 32) {
+        const int cnt = (int)((n - cube0) < 32 ? (n - cube0) : 32);
+        for (int lane = 0; lane < cnt; ++lane)
+            prefix_walk<SIZE>(moves + (cube0 + lane) * depth, depth, lane * depth, tbl, clut, kEdgeColour3, img.data(),
+                              solved + (cube0 + lane) * depth);
+        std::memcpy(out + cube0 * depth * G::S, img.data(), (size_t)cnt * depth * G::S);
+    }
+}
+
 template <int SIZE, int NS>
-void scramble_pairs_t(const uint8_t* moves, long long n, int depth, uint8_t* out, uint8_t* solved, bool fixed, bool priv)
+void scramble_pairs_t(const uint8_t* moves, long long n, int depth, uint8_t* out, uint8_t* solved, bool fixed, bool priv,
+                      const uint8_t* last = nullptr)
 {
     using G = CubeGeom<SIZE>;
     constexpr int T = 32 * NS;
@@ -72,6 +137,8 @@ void scramble_pairs_t(const uint8_t* moves, long long n, int depth, uint8_t* out
             else if (fixed && depth == 20) scramble_pairs_run<SIZE, 20, NS>(st, rows, depth, s_moves.data(), s_ptbl, lr, pair_roff2(lane));
             else if (fixed && depth == 43) scramble_pairs_run<SIZE, 43, NS>(st, rows, depth, s_moves.data(), s_ptbl, lr, pair_roff2(lane));
             else scramble_pairs_run<SIZE, 0, NS>(st, rows, depth, s_moves.data(), s_ptbl, lr, pair_roff2(lane));
+            if (last)
+                for (int k = 0; k < NS; ++k) scramble_pairs_last<SIZE>(st[k], last[base + rows[k]], s_ptbl, lr, pair_roff2(lane));
             for (int k = 0; k < NS; ++k)
                 ok[k] |= (uint32_t)scramble_pairs_finish<SIZE>(st[k], rows[k], ColourLutHost{clut, kEdgeColour3}, s_out.data()) << lane;
         }
@@ -221,6 +288,25 @@ void emul_scramble_pairs(int size, const uint8_t* moves, long long n, int depth,
     if (size == 3) scramble_pairs_t<3, 2>(moves, n, depth, out, solved, fix, swz);
     else if (fixed & 4) scramble_pairs_t<2, 4>(moves, n, depth, out, solved, fix, swz);
     else scramble_pairs_t<2, 2>(moves, n, depth, out, solved, fix, swz);
+}
+// cube_scramble_step through the pair kernel: the walk, then one more face turn from `last` (whole tiles only)
+void emul_scramble_step_pairs(int size, const uint8_t* moves, const uint8_t* last, long long n, int depth, uint8_t* out,
+                              uint8_t* solved, int fixed)
+{
+    const bool fix = (fixed & 3) == 1, swz = (fixed & 3) == 2;
+    if (size == 3) scramble_pairs_t<3, 2>(moves, n, depth, out, solved, fix, swz, last);
+    else if (fixed & 4) scramble_pairs_t<2, 4>(moves, n, depth, out, solved, fix, swz, last);
+    else scramble_pairs_t<2, 2>(moves, n, depth, out, solved, fix, swz, last);
+}
+// K1p sliced (deep scrambles; `last` may be null); `moves` readable 16 bytes past its end
+void emul_scramble_sliced(int size, const uint8_t* moves, const uint8_t* last, long long n, int depth, uint8_t* out, uint8_t* solved)
+{
+    if (size == 3) scramble_sliced_t<3>(moves, n, depth, out, solved, last); else scramble_sliced_t<2>(moves, n, depth, out, solved, last);
+}
+// cube_scramble_prefixes: out [n, depth, S] cube-major, solved [n, depth]
+void emul_prefixes(int size, const uint8_t* moves, long long n, int depth, uint8_t* out, uint8_t* solved)
+{
+    if (size == 3) prefixes_t<3>(moves, n, depth, out, solved); else prefixes_t<2>(moves, n, depth, out, solved);
 }
 void emul_walk(int size, const uint8_t* in, const uint8_t* moves, long long n, int depth, uint8_t* out,
                uint8_t* solved)

@@ -43,9 +43,16 @@ def test_argument_errors_without_cuda(lib):
     assert lib.cube_scramble(3, aligned, 1, 1, None, None, None, None, None) == _lib.CUBE_ERR_ARG
     assert lib.cube_scramble(3, odd, 1, 1, aligned, None, None, None, None) == _lib.CUBE_ERR_ALIGN
     assert lib.cube_step(5, aligned, aligned, 1, None, None, None, None) == _lib.CUBE_ERR_SIZE
-    assert lib.cube_encode(3, aligned, 1, aligned, 7, None) == _lib.CUBE_ERR_ARG
-    assert lib.cube_expand(2, odd, 1, None, None, None, 0, None, None, None, None) == _lib.CUBE_ERR_ALIGN
-    assert lib.cube_decode(3, aligned, 2, 1, aligned, None) == _lib.CUBE_ERR_SIZE
+    assert lib.cube_encode(3, aligned, 1, aligned, 7, 0, None) == _lib.CUBE_ERR_ARG
+    assert lib.cube_encode(3, aligned, 1, aligned, 0, 2, None) == _lib.CUBE_ERR_ARG           # unknown encoding
+    assert lib.cube_expand(2, odd, 1, None, None, None, 0, 0, None, None, None, None) == _lib.CUBE_ERR_ALIGN
+    assert lib.cube_decode(3, aligned, 2, _lib.ENCODING_REFERENCE, 1, aligned, None) == _lib.CUBE_ERR_SIZE   # lossy: no inverse
+    assert lib.cube_decode(3, odd, 2, _lib.ENCODING_EXACT, 1, aligned, None) == _lib.CUBE_ERR_ALIGN
+    assert lib.cube_scramble_step(3, aligned, None, 1, 1, aligned, None, None, None, None) == _lib.CUBE_ERR_ARG
+    assert lib.cube_scramble_prefixes(3, aligned, 1, 132, aligned, None, None, None) == _lib.CUBE_ERR_ARG
+    assert lib.cube_scramble_prefixes_max_depth(3) == 131 and lib.cube_scramble_prefixes_max_depth(2) == 289
+    assert lib.cube_pipeline_reset_host(None, None, 1, None, None, None, None) == _lib.CUBE_ERR_ARG
+    assert lib.cube_host_alloc(0, None) == _lib.CUBE_ERR_ARG and lib.cube_host_free(aligned) == _lib.CUBE_ERR_ARG
     with pytest.raises(NotImplementedError):
         _lib.check(_lib.CUBE_ERR_SIZE, "x")
     with pytest.raises(IndexError):
@@ -182,3 +189,29 @@ def test_numa_binding_helper_is_best_effort():
     assert cdist._parse_cpulist("") == set()
     info = cdist.bind_host_to_gpu_node(0)
     assert isinstance(info, dict) and info.get("numa_node") is None or isinstance(info.get("numa_node"), int)
+
+
+def test_bench_scaling_modes_and_reference_arm_line():
+    """bench.py host logic without a GPU: weak / strong instance counts (rank r of R owns
+    N / R rows), one `config` object shared by both arms, and the reference arm's JSON line (a tiny sample)."""
+    import json
+    import subprocess
+    import sys
+    import bench
+
+    class Args:
+        scaling, instances_total, instances_per_gpu = "strong", 64 * 2 ** 20, 8 * 2 ** 20
+
+    assert [bench.instances_per_gpu(Args, w) for w in (1, 2, 4, 8)] == [64 * 2 ** 20 // w for w in (1, 2, 4, 8)]
+    Args.scaling = "weak"
+    assert [bench.instances_per_gpu(Args, w) for w in (1, 8)] == [8 * 2 ** 20] * 2
+    cfg = bench.workload_config(8, 8 * 2 ** 20, "weak")
+    assert cfg["instances_total"] == 64 * 2 ** 20 and cfg["depth"] == 30 and cfg["cube_size"] == 3
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "8", "--steps", "2",
+                          "--warmup", "1", "--ref-seconds", "0.5"], capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["config"] == cfg and line["n_gpus"] == 8 and line["steps"] == 2
+    assert line["value"] > 0 and line["e2e"]["value"] == line["value"] and line["cpu_baseline"]["kind"] == "port"
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["unit"] == "transitions/s" and line["higher_is_better"] is True

@@ -1256,3 +1256,36 @@ def test_scramble_step_fused_equals_scramble_then_step(size, n, depth):
     off[1:] = cu(act)
     st2, _, _ = ops.scramble_step(size, cu(moves), off[1:])
     assert bool((st2 == states).all())
+
+
+@pytest.mark.parametrize("size", SIZES)
+@pytest.mark.parametrize("depth", (321, 480, 481, 723, 1000))
+def test_deep_scrambles_sliced_kernel(size, depth):
+    """Depth > 320 (test.py:44 scrambles 1 000 deep): K1p's sliced variant -- move bytes staged 240 per row at a
+    time from the 16-byte boundary below each piece, state carried in registers -- with several tiles per warp
+    (both buffers, barrier phases across tiles), the last whole tile and the ragged tail through the deep kernel,
+    rows that come back to solved, twist pile-ups, and the fused trailing action."""
+    rng = np.random.RandomState(depth + 13 * size)
+    A = T.N_ACTIONS[size]
+    n = 64 * 148 * 4 * 2 + 64 + 29
+    moves = rng.randint(A, size=(n, depth)).astype(np.uint8)
+    h = depth // 2
+    back = rng.choice(n, 400, replace=False)
+    moves[back, h:2 * h] = moves[back, :h][:, ::-1] ^ 1
+    if depth % 2:
+        moves[back, -1] = 12
+    if size == 3:
+        moves[:64] = np.tile(np.array([2, 4], dtype=np.uint8), (64, depth // 2 + 1))[:, :depth]
+    counters = ops.new_counters(dev())
+    states, solved, reward = ops.scramble(size, cu(moves), counters=counters)
+    clean = np.where(moves == 12, 0, moves)
+    want, ws, wr, _ = C.scramble(size, clean)
+    if depth % 2:
+        want[back], ws[back], wr[back], _ = C.scramble(size, moves[back, :-1])
+    assert (states.cpu().numpy() == want).all()
+    assert (solved.cpu().numpy().astype(bool) == ws).all() and (reward.cpu().numpy() == wr).all()
+    assert counters.tolist()[:2] == [int(ws.sum()), n] and ws[back].all()
+    act = rng.randint(A, size=n).astype(np.uint8)
+    st2, so2, _ = ops.scramble_step(size, cu(moves), cu(act))
+    assert (st2.cpu().numpy() == O.apply_moves(size, want, act)).all()
+    assert (so2.cpu().numpy().astype(bool) == O.is_solved(size, O.apply_moves(size, want, act))).all()

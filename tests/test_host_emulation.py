@@ -26,6 +26,9 @@ def emul():
     vp, ll = ctypes.c_void_p, ctypes.c_longlong
     lib.emul_scramble.argtypes = [ctypes.c_int, vp, ll, ctypes.c_int, vp, vp]
     lib.emul_scramble_pairs.argtypes = [ctypes.c_int, vp, ll, ctypes.c_int, vp, vp, ctypes.c_int]
+    lib.emul_scramble_step_pairs.argtypes = [ctypes.c_int, vp, vp, ll, ctypes.c_int, vp, vp, ctypes.c_int]
+    lib.emul_scramble_sliced.argtypes = [ctypes.c_int, vp, vp, ll, ctypes.c_int, vp, vp]
+    lib.emul_prefixes.argtypes = [ctypes.c_int, vp, ll, ctypes.c_int, vp, vp]
     lib.emul_walk_private.argtypes = [ctypes.c_int, vp, vp, ll, ctypes.c_int, vp, vp]
     lib.emul_walk.argtypes = [ctypes.c_int, vp, vp, ll, ctypes.c_int, vp, vp]
     lib.emul_expand.argtypes = [ctypes.c_int, ctypes.c_int, vp, ll, vp, vp, vp, vp]
@@ -243,3 +246,82 @@ def test_lazy_twist_field_never_overflows(size):
                 field = fold(field)
                 assert max(field) <= 8
     assert worst <= 24
+
+
+@pytest.mark.parametrize("size", (2, 3))
+@pytest.mark.parametrize("depth", (1, 2, 3, 4, 5, 8, 29, 30, 31, 64, 131))
+def test_prefixes_emulation(emul, size, depth):
+    """K1x (cube_scramble_prefixes): the per-lane walk of prefix.cu -- lazy twist folds every four moves, every
+    level finished on a copy into the tile image at row lane * depth + k (rows of both parities) -- against the
+    oracle's per-step states and done flags; a ragged last tile."""
+    rng = np.random.RandomState(depth + 50 * size)
+    n = 32 * 3 + 7
+    A = T.N_ACTIONS[size]
+    moves = rng.randint(A, size=(n, depth)).astype(np.uint8)
+    if depth >= 4:
+        moves[::2, 2:4] = moves[::2, :2][:, ::-1] ^ 1
+    out = np.empty((n, depth, T.N_STICKERS[size]), dtype=np.uint8)
+    solved = np.empty((n, depth), dtype=np.uint8)
+    emul.emul_prefixes(size, _p(moves), n, depth, _p(out), _p(solved))
+    _, want, flags = O.scramble(size, moves, per_step=True)
+    assert (out == want).all() and (solved.astype(bool) == flags).all()
+    if depth >= 4:
+        assert solved[0, 3] == 1
+
+
+@pytest.mark.parametrize("size", (2, 3))
+@pytest.mark.parametrize("depth,fixed", [(d, 0) for d in (1, 2, 7, 29, 31, 100, 319)] + [(30, 1), (20, 1), (32, 2), (96, 2), (320, 2)]
+                         + [(20, 5), (30, 5), (9, 4)])
+def test_scramble_step_pairs_emulation(emul, size, depth, fixed):
+    """cube_scramble_step through K1p: the walk of `depth` moves leaves twist fields as large as 30; the trailing
+    action (fold, then the pair row (action, no move)) must still give the depth + 1 scramble of the oracle."""
+    if (fixed & 4) and size == 3:
+        pytest.skip("four instances per lane is a 2x2x2 variant")
+    if (fixed & 3) == 2 and depth % (8 if size == 3 else 16):
+        pytest.skip("swizzled tiles need depth % 8 (3x3x3) / % 16 (2x2x2) == 0")
+    rng = np.random.RandomState(3 * depth + size + fixed)
+    tile = 128 if fixed & 4 else 64
+    n = tile * 3
+    A = T.N_ACTIONS[size]
+    moves = rng.randint(A, size=(n, depth)).astype(np.uint8)
+    if size == 3 and depth >= 2:
+        moves[:32] = np.tile(np.array([2, 4], dtype=np.uint8), (32, depth // 2 + 1))[:, :depth]   # F R F R ...: twists pile up
+    last = rng.randint(A, size=n).astype(np.uint8)
+    last[::5] = 12                                                      # the no-move index as the action
+    out = np.empty((n, T.N_STICKERS[size]), dtype=np.uint8)
+    solved = np.empty(n, dtype=np.uint8)
+    emul.emul_scramble_step_pairs(size, _p(moves), _p(last), n, depth, _p(out), _p(solved), fixed)
+    want = O.scramble(size, moves)
+    stepped = want.copy()
+    real = last < A
+    stepped[real] = O.apply_moves(size, want[real], last[real])
+    assert (out == stepped).all()
+    assert (solved.astype(bool) == O.is_solved(size, stepped)).all()
+
+
+@pytest.mark.parametrize("size", (2, 3))
+@pytest.mark.parametrize("depth,with_last", [(321, 0), (400, 0), (479, 1), (480, 0), (481, 0), (723, 0), (1000, 1), (241, 0), (17, 0)])
+def test_scramble_sliced_emulation(emul, size, depth, with_last):
+    """K1p sliced (deep scrambles): pieces staged from the 16-byte boundary below them into 272-byte slots, the
+    shift (row * depth) & 15 the same in every slice, the cubie state carried from slice to slice with a fold
+    at every slice start (worst case: F R F R ... piles the twists up) -- against the oracle."""
+    rng = np.random.RandomState(depth + size)
+    n = 64 * 2
+    A = T.N_ACTIONS[size]
+    moves = np.zeros(n * depth + 16, dtype=np.uint8)                    # readable 16 bytes past the end
+    m2 = moves[:n * depth].reshape(n, depth)
+    m2[:] = rng.randint(A, size=(n, depth))
+    m2[:8] = np.tile(np.array([2, 4], dtype=np.uint8), (8, depth // 2 + 1))[:, :depth]
+    h = depth // 2
+    m2[8:24, h:2 * h] = m2[8:24, :h][:, ::-1] ^ 1                       # back to solved (then one more move if odd)
+    last = rng.randint(A, size=n).astype(np.uint8) if with_last else None
+    out = np.empty((n, T.N_STICKERS[size]), dtype=np.uint8)
+    solved = np.empty(n, dtype=np.uint8)
+    emul.emul_scramble_sliced(size, _p(moves), _p(last), n, depth, _p(out), _p(solved))
+    want = O.scramble(size, m2)
+    if with_last:
+        want = O.apply_moves(size, want, last)
+    assert (out == want).all()
+    assert (solved.astype(bool) == O.is_solved(size, want)).all()
+    if depth % 2 == 0 and not with_last:
+        assert solved[8:24].all()

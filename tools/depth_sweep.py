@@ -14,7 +14,9 @@ for size, a, n in ((3, 12, 4 << 20), (2, 6, 8 << 20)):
     if only and size not in only:
         continue
     s = ops.N_STICKERS[size]
-    for depth in (1, 2, 7, 8, 10, 16, 19, 20, 21, 24, 29, 30, 31, 32, 40, 48, 64, 96, 97, 128, 160, 200, 256, 320, 321):
+    for depth in (1, 2, 7, 8, 10, 16, 19, 20, 21, 24, 29, 30, 31, 32, 40, 48, 64, 96, 97, 128, 160, 200, 256, 320, 321, 480, 1000):
+        if depth > 320:
+            n = min(n, 1 << 20)
         moves = torch.randint(0, a, (n, depth), dtype=torch.uint8, device=dev)
         st = torch.empty((n, s), dtype=torch.uint8, device=dev)
         so = torch.empty(n, dtype=torch.uint8, device=dev)

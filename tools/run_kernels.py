@@ -99,6 +99,43 @@ def main():
         child = torch.empty((n, 6, 7, 21), dtype=torch.bfloat16, device=dev)
         timed("expand2", lambda: ops.expand(2, parents, dtype=torch.bfloat16, child_onehot=child), n)
         print("   expand2 algorithmic bytes/parent %d" % (24 + 6 * (294 + 5)))
+    if which in ("prefixes3", "small"):            # K1x: every prefix of 139 810 scrambles x depth 30 (config 4's parents)
+        n, d = 139810, 30
+        moves = torch.randint(0, 12, (n, d), dtype=torch.uint8, device=dev, generator=gen)
+        out = torch.empty((n, d, 54), dtype=torch.uint8, device=dev)
+        timed("prefixes3", lambda: ops.scramble_prefixes(3, moves, out=out), n * d)
+        print("   prefixes3 algorithmic bytes/cube %d" % (d + d * 54))
+    if which in ("adi_targets", "small"):          # K4: target assembly for 4 Mi parents
+        p = 4 * 2 ** 20
+        cv = torch.randn((p, 12), device=dev, generator=gen)
+        so = (torch.rand((p, 12), device=dev, generator=gen) < 0.01).to(torch.uint8)
+        pv = torch.randn(p, device=dev, generator=gen)
+        k = torch.randint(1, 31, (p,), device=dev, generator=gen).to(torch.int32)
+        timed("adi_targets", lambda: ops.adi_targets(3, cv, so, pv, k, 1.0), p)
+        print("   adi_targets algorithmic bytes/parent %d (incl. the wrapper's int64 policy copy)" % (48 + 12 + 4 + 4 + 4 + 4 + 8))
+    if which in ("decode2", "small"):              # 2x2x2 one-hot -> stickers, 4 Mi rows of bf16
+        n = 4 * 2 ** 20
+        st, _, _ = ops.scramble(2, torch.randint(0, 6, (n, 14), dtype=torch.uint8, device=dev, generator=gen), want_flags=False)
+        oh = ops.encode(2, st, dtype=torch.bfloat16)
+        timed("decode2", lambda: ops.decode(2, oh), n)
+        assert bool((ops.decode(2, oh) == st).all())
+        print("   decode2 algorithmic bytes/row %d" % (294 + 24))
+    if which in ("decode3x", "small"):             # 3x3x3 EXACT one-hot -> stickers, 4 Mi rows of bf16
+        n = 4 * 2 ** 20
+        st, _, _ = ops.scramble(3, torch.randint(0, 12, (n, 25), dtype=torch.uint8, device=dev, generator=gen), want_flags=False)
+        oh = ops.encode(3, st, dtype=torch.bfloat16, encoding="exact")
+        timed("decode3x", lambda: ops.decode(3, oh, encoding="exact"), n)
+        assert bool((ops.decode(3, oh, encoding="exact") == st).all())
+        print("   decode3x algorithmic bytes/row %d" % (960 + 54))
+    if which in ("scramble_step3", "small"):       # fused scramble + step (configs[2] read literally), 8 Mi x depth 30 + 1
+        n, d = 8 * 2 ** 20, 30
+        moves = torch.randint(0, 12, (n, d), dtype=torch.uint8, device=dev, generator=gen)
+        act = torch.randint(0, 12, (n,), dtype=torch.uint8, device=dev, generator=gen)
+        st = torch.empty((n, 54), dtype=torch.uint8, device=dev)
+        so = torch.empty(n, dtype=torch.uint8, device=dev)
+        rw = torch.empty(n, dtype=torch.float32, device=dev)
+        timed("scramble_step3", lambda: ops.scramble_step(3, moves, act, out=st, solved=so, reward=rw), n * (d + 1))
+        print("   scramble_step3 algorithmic bytes/instance %d" % (d + 1 + 54 + 5))
     if which == "expand2_f32":                     # what the drop-in env / ADI feed the reference's float32 net
         n = 2 * 2 ** 20
         parents, _, _ = ops.scramble(2, torch.randint(0, 6, (n, 14), dtype=torch.uint8, device=dev, generator=gen),
