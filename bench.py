@@ -795,7 +795,7 @@ def run_b200_arm(args):
         step()
     drain()
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0, e1, ek = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     align = torch.zeros(1, dtype=torch.int32, device=dev)
     barrier()
     # The host-side barrier releases the ranks a few tens of microseconds apart, and the closing all-reduce then
@@ -806,6 +806,7 @@ def run_b200_arm(args):
     e0.record()
     for _ in range(args.steps):
         step()
+    ek.record()                                           # this rank's kernels end here, the collective follows
     totals = drain()                                      # inside the timed region
     e1.record()
     clocks.sample_now()                                   # the queued steps are still running
@@ -814,6 +815,14 @@ def run_b200_arm(args):
     clocks.__exit__(None, None, None)
     local_step_s = e0.elapsed_time(e1) * 1e-3 / args.steps
     step_s = cdist.max_over_ranks(local_step_s, dev)
+    # where a multi-GPU region's time goes: every rank's own kernels (GPUs of one box differ by ~1 %) and what
+    # follows them (waiting for the slowest rank + the all-reduce); max / min over ranks
+    kern_only_ms = e0.elapsed_time(ek) / args.steps
+    tail_ms = ek.elapsed_time(e1)
+    spread = {"kernels_ms_per_step_max": cdist.max_over_ranks(kern_only_ms, dev),
+              "kernels_ms_per_step_min": -cdist.max_over_ranks(-kern_only_ms, dev),
+              "after_last_kernel_ms_max": cdist.max_over_ranks(tail_ms, dev),
+              "after_last_kernel_ms_min": -cdist.max_over_ranks(-tail_ms, dev)}
     total_tr = world * n * depth
     value = total_tr / step_s
     solved_total, produced_total = int(totals[0]), int(totals[1])
@@ -875,7 +884,7 @@ def run_b200_arm(args):
                     "collective": ("int64[4] all-reduce(SUM) per step, asynchronous" if args.reduce_every_step else
                                    "one all-reduce(SUM) of the per-step int64[4] solved/produced counter rows at the end of "
                                    "the timed region; a device-side all-reduce in front of the start event aligns the ranks"),
-                    "host_numa_binding_rank0": numa},
+                    "timed_region_by_rank": spread, "host_numa_binding_rank0": numa},
         "solved_total": solved_total, "reward_total": 2 * solved_total - produced_total, "parity": parity,
         "e2e": e2e, "roofline": roofline, "gpu_launches": args.steps, "clocks": clocks.summary(),
     }

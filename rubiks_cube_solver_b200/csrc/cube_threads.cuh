@@ -361,24 +361,19 @@ CUBE_HD void scramble_pairs_run(CubieState (&st)[NS], const int (&rows)[NS], int
     }
 }
 
-// A SLICE of a deep scramble (depth > 320, scramble_sliced_kernel): `count` moves per instance starting at byte
-// offset off[k] of s_moves, applied to a state that is carried over from the previous slice.  Same schedule as
-// the generic path above: a fold first (the previous slice may have left a field at 30), then groups of five
-// words with a fold after each; the <= 4 words left over and the tail add <= 20 on top of <= 10.
+// A SLICE of a deep scramble (depth > 320, scramble_sliced_kernel): `len` moves per instance, applied to a state
+// that is carried over from the previous slice.  Instance k's bytes start shift[k] (0..15) bytes into the 16-byte
+// aligned slot at offset base[k] of s_moves (the slot was filled from the 16-byte boundary below the piece).  The
+// moves are read sixteen bytes at a time with 128-bit loads -- 32-bit loads would bank-conflict 4- to 8-fold,
+// because slots can only be 16-byte aligned -- and the per-row byte shift is taken out in registers: a two-level
+// word select on (shift >> 2) and a funnel shift by (shift & 3) bytes.  A fold first (the previous slice may have
+// left a twist field at 26), then one after every unit (a unit adds <= 16 to <= 10); the <= 15 moves left add <= 16.
 template <int SIZE, int NS, class TBL>
-CUBE_HD void scramble_pairs_run_at(CubieState (&st)[NS], const uint32_t (&off)[NS], int count, const uint8_t* s_moves,
-                                   const TBL& tbl, uint32_t lanereg, uint32_t roff)
+CUBE_HD void scramble_pairs_run_units(CubieState (&st)[NS], const uint32_t (&base)[NS], const uint32_t (&shift)[NS], int len,
+                                      const uint8_t* s_moves, const TBL& tbl, uint32_t lanereg, uint32_t roff)
 {
-    const uint32_t* mw = reinterpret_cast<const uint32_t*>(s_moves);
-    const int nfull = count >> 2, tail = count & 3;
     const uint32_t bias = tbl.bias();
     constexpr uint32_t K = (uint32_t)(CUBE_PAIR_BASE + 256);
-    uint32_t wi[NS], sh[NS], lo[NS];
-#pragma unroll
-    for (int k = 0; k < NS; ++k) {
-        wi[k] = off[k] >> 2; sh[k] = (off[k] & 3u) << 3;
-        lo[k] = mw[wi[k]];
-    }
     auto fold = [&]() {
 #pragma unroll
         for (int k = 0; k < NS; ++k) {
@@ -386,39 +381,77 @@ CUBE_HD void scramble_pairs_run_at(CubieState (&st)[NS], const uint32_t (&off)[N
             st[k].c1 = cubie_fold_twist(st[k].c1);
         }
     };
-    auto word = [&](int j) {
+    auto word = [&](const uint32_t (&w)[NS], bool second) {
         uint32_t y[NS];
 #pragma unroll
-        for (int k = 0; k < NS; ++k) {
-            const uint32_t hi = mw[wi[k] + j + 1];
-            y[k] = cube_funnel_r(lo[k], hi, sh[k]) * K + bias;
-            lo[k] = hi;
-        }
+        for (int k = 0; k < NS; ++k) y[k] = w[k] * K + bias;
 #pragma unroll
         for (int k = 0; k < NS; ++k) pair_apply<SIZE>(st[k], tbl, cube_prmt(y[k], lanereg, 0x5514u), roff);
-#pragma unroll
-        for (int k = 0; k < NS; ++k) pair_apply<SIZE>(st[k], tbl, cube_prmt(y[k], lanereg, 0x5534u), roff);
-    };
-    fold();
-    int j = 0;
-    for (; j + 5 <= nfull; j += 5) {
-        word(j); word(j + 1); word(j + 2); word(j + 3); word(j + 4);
-        fold();
-    }
-    for (; j < nfull; ++j) word(j);
-    if (tail) {                                          // last 1..3 moves, padded with the no-move index
-        const uint32_t keep = (1u << (8 * tail)) - 1u;
-        uint32_t y[NS];
-#pragma unroll
-        for (int k = 0; k < NS; ++k) {
-            const uint32_t w = (cube_funnel_r(lo[k], mw[wi[k] + nfull + 1], sh[k]) & keep) | (0x0c0c0c0cu & ~keep);
-            y[k] = w * K + bias;
-        }
-#pragma unroll
-        for (int k = 0; k < NS; ++k) pair_apply<SIZE>(st[k], tbl, cube_prmt(y[k], lanereg, 0x5514u), roff);
-        if (tail == 3) {
+        if (second) {
 #pragma unroll
             for (int k = 0; k < NS; ++k) pair_apply<SIZE>(st[k], tbl, cube_prmt(y[k], lanereg, 0x5534u), roff);
+        }
+    };
+    // the 16 move bytes that start `shift` bytes into the unit pair (a, b), as four words
+    auto aligned = [&](const CubeVec4& a, const CubeVec4& b, uint32_t sh, uint32_t (&o)[4]) {
+        const bool q0 = (sh & 4u) != 0, q1 = (sh & 8u) != 0;
+        const uint32_t c[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        uint32_t e[7], d[5];
+#pragma unroll
+        for (int j = 0; j < 7; ++j) e[j] = q0 ? c[j + 1] : c[j];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) d[j] = q1 ? e[j + 2] : e[j];
+        const uint32_t r = (sh & 3u) << 3;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = cube_funnel_r(d[j], d[j + 1], r);
+    };
+    fold();
+    CubeVec4 cur[NS];
+#pragma unroll
+    for (int k = 0; k < NS; ++k) cur[k] = cube_ld128(s_moves + base[k]);
+    int g = 0;
+    for (; g + 16 <= len; g += 16) {
+        CubeVec4 nxt[NS];
+        uint32_t m[NS][4], w[NS];
+#pragma unroll
+        for (int k = 0; k < NS; ++k) {
+            nxt[k] = cube_ld128(s_moves + base[k] + g + 16);
+            aligned(cur[k], nxt[k], shift[k], m[k]);
+            cur[k] = nxt[k];
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+            for (int k = 0; k < NS; ++k) w[k] = m[k][j];
+            word(w, true);
+        }
+        fold();
+    }
+    const int rem = len - g;                             // 0..15 moves left (the same for every instance)
+    if (rem) {
+        uint32_t m[NS][4], w[NS];
+#pragma unroll
+        for (int k = 0; k < NS; ++k) {
+            const CubeVec4 nxt = cube_ld128(s_moves + base[k] + g + 16);
+            aligned(cur[k], nxt, shift[k], m[k]);
+        }
+        const int nwords = rem >> 2, tail = rem & 3;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            if (j < nwords) {
+#pragma unroll
+                for (int k = 0; k < NS; ++k) w[k] = m[k][j];
+                word(w, true);
+            }
+        }
+        if (tail) {                                      // last 1..3 moves, padded with the no-move index
+            const uint32_t keep = (1u << (8 * tail)) - 1u;
+#pragma unroll
+            for (int k = 0; k < NS; ++k) {
+                const uint32_t t = nwords == 0 ? m[k][0] : nwords == 1 ? m[k][1] : nwords == 2 ? m[k][2] : m[k][3];
+                w[k] = (t & keep) | (0x0c0c0c0cu & ~keep);
+            }
+            word(w, tail == 3);
         }
     }
 }

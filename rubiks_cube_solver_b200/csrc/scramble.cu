@@ -338,30 +338,37 @@ scramble_pairs_kernel(const uint8_t* __restrict__ moves, int n_tiles, int depth_
 // ---- K1p, sliced: sequences deeper than kMaxPairDepth (test.py scrambles 1 000 deep, test.py:44) -------------
 // A tile's move bytes no longer fit in a warp's buffers, so they arrive in SLICES of kSlice moves per row while
 // the cubie state stays in registers from slice to slice.  A slice of a tile is 64 pieces of the row-major move
-// array, `depth` bytes apart: every lane fetches the pieces of its two rows with two small bulk copies from the
-// 16-byte boundary below each piece (the piece then starts (row * depth) & 15 bytes into its slot: the same
-// shift in every slice, because kSlice is a multiple of 16) and announces their bytes on the buffer's mbarrier
-// (32 arrivals).  Double-buffered across slices AND tiles.  64 small copies per 64 x 240 transitions are far
-// below the copy engine's rate of one small copy per ~20 cycles per SM.  Replaces the 3x cliff at depth 321
-// (the single-move kernel reading its moves byte by byte from global memory: 0.5e12 tr/s).
-constexpr int kSlice = 240;                       // moves per row and slice: a multiple of 16 (and of 4)
-constexpr int kSliceStride = kSlice + 32;         // bytes per row slot: shift <= 15, rounded up to 16
+// array, `depth` bytes apart and at any byte alignment: every lane fetches the pieces of its two rows (lane and
+// lane + 32) with two small bulk copies from the 16-byte boundary below each piece (the piece then starts
+// (row * depth) & 15 bytes into its slot: the same shift in every slice, because kSlice is a multiple of 16; the
+// slice runner takes it out in registers) and announces their bytes on the buffer's mbarrier (32 arrivals).
+// Slots are 17 x 16 bytes apart, so the 128-bit move loads of a quarter warp fall into eight different bank
+// groups.  Double-buffered across slices AND tiles.
+// (Tried on the way: 32-bit move loads at the per-row shift -- slots can only be 16-byte aligned, so they conflict
+// 8-fold: 0.96e12 tr/s at depth 1000; byte-coordinate copies through a 1-D tensor map, which would land every
+// piece aligned -- tensor copies want 128-byte aligned destinations, which brings the conflicts back.)
+// Slice length: moves per row and slice, a multiple of 16; a row's slot is slice + 32 bytes (shift <= 15, the
+// runner reads one unit ahead) and must be an ODD number of 16-byte units.  112 moves (144-byte slots) let 8
+// warps' double buffers fit; 240 (272-byte slots: 4 warps, one per scheduler) issued at 0.42 of a scheduler's
+// rate, single-warp latency-bound: 0.98e12 tr/s at depth 1000 (CUBE_SLICE=240 for A/B runs).
+constexpr int kSliceDefault = 112;
+__host__ __device__ constexpr int slice_stride(int slice) { return ((slice + 32) / 16) % 2 ? slice + 32 : slice + 48; }
 
 template <int SIZE>
 struct SlicedSmem {
     using G = CubeGeom<SIZE>;
     static constexpr int kOutBytes = 64 * G::S;
     static constexpr int kMovesAt = 16 + kOutBytes;                   // after the two mbarriers and the out tile
-    static constexpr int kPerWarpBytes = kMovesAt + 2 * 64 * kSliceStride;
+    __host__ __device__ static constexpr int per_warp(int slice) { return kMovesAt + 2 * 64 * slice_stride(slice); }
     static constexpr int kFixed = PairSmem<SIZE, 2>::kPerWarp;        // pair table + colour LUTs, as in K1p
-    __host__ __device__ static constexpr int bytes(int warps) { return kFixed + warps * kPerWarpBytes; }
+    __host__ __device__ static constexpr int bytes(int warps, int slice) { return kFixed + warps * per_warp(slice); }
 };
 
 template <int SIZE>
 __global__ void __launch_bounds__(8 * 32, 1)
 scramble_sliced_kernel(const uint8_t* __restrict__ moves, int n_tiles, int depth, uint8_t* __restrict__ out,
                        uint8_t* __restrict__ solved, float* __restrict__ reward, unsigned long long* __restrict__ counters,
-                       const uint8_t* __restrict__ last)
+                       const uint8_t* __restrict__ last, int kSlice)
 {
     using L = SlicedSmem<SIZE>;
     using P = PairSmem<SIZE, 2>;
@@ -373,7 +380,8 @@ scramble_sliced_kernel(const uint8_t* __restrict__ moves, int n_tiles, int depth
     const PairTableShared tbl{(bulk::smem_addr(s_ptbl) >> 8) * 0x01000100u};
     uint32_t* s_clut = reinterpret_cast<uint32_t*>(smem + P::kCornerLut);
     uint32_t* s_elut = reinterpret_cast<uint32_t*>(smem + P::kEdgeLut);
-    uint8_t* mine = smem + L::kFixed + warp * L::kPerWarpBytes;
+    const int kSliceStride = slice_stride(kSlice);
+    uint8_t* mine = smem + L::kFixed + warp * L::per_warp(kSlice);
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(mine);              // [2]: 32 arrivals each
     uint8_t* s_out = mine + 16;
     uint8_t* s_moves = mine + L::kMovesAt;                            // [2][64][kSliceStride]
@@ -385,16 +393,10 @@ scramble_sliced_kernel(const uint8_t* __restrict__ moves, int n_tiles, int depth
     __syncthreads();
 
     const int n_slices = (depth + kSlice - 1) / kSlice;
-    int rows[2];
-    rows[0] = (SIZE == 3) ? 2 * lane : lane;
-    rows[1] = (SIZE == 3) ? 2 * lane + 1 : lane + 32;
-    uint32_t shift[2], off[2];
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-        shift[k] = (uint32_t)(((long long)rows[k] * depth) & 15);
-        off[k] = (uint32_t)(rows[k] * kSliceStride) + shift[k];
-    }
-    // the lane's two pieces of slice `s` of tile `t` into buffer `b`
+    const int rows[2] = {lane, lane + 32};
+    const uint32_t shift[2] = {(uint32_t)(((long long)rows[0] * depth) & 15), (uint32_t)(((long long)rows[1] * depth) & 15)};
+    // the lane's two pieces of slice `s` of tile `t` into buffer `b`: from the 16-byte boundary below the piece to
+    // the one above its end (never past the move array: the last whole tile is left to the caller)
     auto stage = [&](int t, int s, int b) {
         const int len = depth - s * kSlice < kSlice ? depth - s * kSlice : kSlice;
         uint32_t bytes[2];
@@ -424,8 +426,8 @@ scramble_sliced_kernel(const uint8_t* __restrict__ moves, int n_tiles, int depth
             else if (tile + stride < n_tiles) stage(tile + stride, 0, buf ^ 1);
             bulk::mbar_wait(&s_bar[buf], (it >> 1) & 1u);
             const int len = depth - s * kSlice < kSlice ? depth - s * kSlice : kSlice;
-            uint32_t o[2] = {off[0] + (uint32_t)(buf * 64 * kSliceStride), off[1] + (uint32_t)(buf * 64 * kSliceStride)};
-            scramble_pairs_run_at<SIZE, 2>(st, o, len, s_moves, tbl, lanereg, roff);
+            const uint32_t base[2] = {(uint32_t)((buf * 64 + rows[0]) * kSliceStride), (uint32_t)((buf * 64 + rows[1]) * kSliceStride)};
+            scramble_pairs_run_units<SIZE, 2>(st, base, shift, len, s_moves, tbl, lanereg, roff);
         }
         if (last) {
 #pragma unroll
@@ -436,8 +438,8 @@ scramble_sliced_kernel(const uint8_t* __restrict__ moves, int n_tiles, int depth
         __syncwarp();
         bool ok[2];
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            ok[k] = scramble_pairs_finish<SIZE>(st[k], rows[k], lut, s_out);
+        for (int k = 0; k < 2; ++k) {                                 // rows lane, lane + 32: both parities in a pass (3x3x3:
+            ok[k] = scramble_pairs_finish<SIZE>(st[k], rows[k], lut, s_out);   // two half-masked store sequences, noise here)
             n_solved += ok[k] ? 1u : 0u;
         }
         bulk::fence_smem_writes();
@@ -447,7 +449,7 @@ scramble_sliced_kernel(const uint8_t* __restrict__ moves, int n_tiles, int depth
             bulk::commit();
         }
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {                                 // a deep scramble is not verdict-bound: plain stores
+        for (int k = 0; k < 2; ++k) {                                 // 32 consecutive bytes / floats per store
             if (solved) solved[(long long)tile * 64 + rows[k]] = ok[k] ? 1 : 0;
             if (reward) reward[(long long)tile * 64 + rows[k]] = ok[k] ? 1.0f : -1.0f;
         }
@@ -469,10 +471,16 @@ long long launch_sliced(const uint8_t* moves, long long n, int depth, uint8_t* o
     long long n_tiles = n / 64 - 1;
     if (n_tiles < 1) return 0;
     if (n_tiles > 0x3fffffff) n_tiles = 0x3fffffff;
-    int warps = (227 * 1024 - 256 - L::kFixed) / L::kPerWarpBytes;
+    static const int slice = [] {
+        const char* e = getenv("CUBE_SLICE");
+        const int v = e ? atoi(e) : kSliceDefault;
+        return (v >= 16 && v <= 240 && v % 16 == 0) ? v : kSliceDefault;
+    }();
+    int warps = (227 * 1024 - 256 - L::kFixed) / L::per_warp(slice);
     if (warps > 8) warps = 8;
+    if (warps >= 4) warps &= ~3;                                      // the same number on every scheduler
     if (warps < 1) return 0;
-    const int smem = L::bytes(warps) + 256 < 66048 + 256 ? 66048 + 256 : L::bytes(warps) + 256;
+    const int smem = L::bytes(warps, slice) + 256 < 66048 + 256 ? 66048 + 256 : L::bytes(warps, slice) + 256;
     auto kern = scramble_sliced_kernel<SIZE>;
     static std::atomic<int> configured_dev[64];
     std::atomic<int>& cfg = configured_dev[cube::device_slot()];
@@ -483,7 +491,7 @@ long long launch_sliced(const uint8_t* moves, long long n, int depth, uint8_t* o
     }
     long long grid = (n_tiles + warps - 1) / warps;
     if (grid > cube::persistent_ctas()) grid = cube::persistent_ctas();
-    kern<<<(unsigned)grid, warps * 32, smem, stream>>>(moves, (int)n_tiles, depth, out, solved, reward, counters, last);
+    kern<<<(unsigned)grid, warps * 32, smem, stream>>>(moves, (int)n_tiles, depth, out, solved, reward, counters, last, slice);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return -(long long)e;
     return n_tiles * 64;

@@ -210,7 +210,8 @@ class CubeEnv(_EnvBase):
             return
         batch = adi.generate_samples(self.cube_size, torch.from_numpy(moves.astype(np.uint8)).to(self._sim_device),
                                      model, temperature, model_device=self.device)
-        obs = self._obs_from_u8(batch["state"].cpu().numpy())             # 0 / 1 in the net's dtype -> the reference's dtype
+        # the parents' one-hot rows are 0 / 1 in the net's dtype: one byte per element crosses the bus
+        obs = self._obs_from_u8(batch["state"].to(torch.uint8).cpu().numpy())
         tv = batch["target_value"].cpu().tolist()           # Python floats of the float32 values, like .item()
         tp = batch["target_policy"].cpu().tolist()
         err = batch["error"].cpu().tolist()

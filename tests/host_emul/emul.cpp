@@ -36,20 +36,21 @@ void scramble_t(const uint8_t* moves, long long n, int depth, uint8_t* out, uint
 // K1p: persistent pair-table kernel, one tile of 32 * NS rows at a time with the kernel's lane -> row map
 // (rows beyond the last whole tile are left untouched: the library hands them to the tile-per-CTA kernel)
 // K1p sliced (depth > 320): the kernel's staging arithmetic -- per row and slice a copy from the 16-byte
-// boundary below the piece into a 272-byte slot, the piece starting (row * depth) & 15 bytes in -- and the
-// slice runner that carries the state over.  `moves` must be readable 16 bytes past its end (the kernel never
-// stages the last tile for that reason; the emulation stages all of them).
+// boundary below the piece into a 272-byte slot, the piece starting (row * depth) & 15 bytes in -- and the slice
+// runner that takes the shift out in registers and carries the state over.  `moves` must be readable 16 bytes
+// past its end (the kernel never stages the last tile for that reason; the emulation stages all of them).
 template <int SIZE>
-void scramble_sliced_t(const uint8_t* moves, long long n, int depth, uint8_t* out, uint8_t* solved, const uint8_t* last)
+void scramble_sliced_t(const uint8_t* moves, long long n, int depth, uint8_t* out, uint8_t* solved, const uint8_t* last,
+                       int kSlice)
 {
     using G = CubeGeom<SIZE>;
-    constexpr int kSlice = 240, kStride = 272;
+    const int kStride = ((kSlice + 32) / 16) % 2 ? kSlice + 32 : kSlice + 48;        // slice_stride() of scramble.cu
     const uint32_t* clut = SIZE == 3 ? kCornerColour3 : kCornerColour2;
     std::vector<uint8_t> tbl(65792 + 256, 0xa5);
     uint8_t* s_ptbl_mem = tbl.data() + ((16 - (reinterpret_cast<uintptr_t>(tbl.data()) & 15)) & 15);
     for (int t = 0; t < 96; ++t) pair_table_fill<SIZE>(s_ptbl_mem, t, 96);
     const PairTableHost s_ptbl{s_ptbl_mem};
-    std::vector<uint8_t> buf(64 * kStride + 16), s_out(64 * G::S);
+    std::vector<uint8_t> buf(64 * kStride + 32), s_out(64 * G::S);
     uint8_t* s_moves = buf.data() + ((16 - (reinterpret_cast<uintptr_t>(buf.data()) & 15)) & 15);
     const int n_slices = (depth + kSlice - 1) / kSlice;
     for (long long tile = 0; tile * 64 + 64 <= n; ++tile) {
@@ -64,17 +65,17 @@ void scramble_sliced_t(const uint8_t* moves, long long n, int depth, uint8_t* ou
                 std::memcpy(s_moves + row * kStride, moves + (g & ~15LL), (shift + len + 15) & ~15u);
             }
             for (int lane = 0; lane < 32; ++lane) {
-                int rows[2] = {SIZE == 3 ? 2 * lane : lane, SIZE == 3 ? 2 * lane + 1 : lane + 32};
+                const int rows[2] = {lane, lane + 32};
                 CubieState two[2] = {st[rows[0]], st[rows[1]]};
-                uint32_t off[2];
-                for (int k = 0; k < 2; ++k) off[k] = (uint32_t)(rows[k] * kStride) + (uint32_t)(((long long)rows[k] * depth) & 15);
-                scramble_pairs_run_at<SIZE, 2>(two, off, len, s_moves, s_ptbl, pair_lanereg<SIZE>(lane), pair_roff2(lane));
+                const uint32_t base[2] = {(uint32_t)(rows[0] * kStride), (uint32_t)(rows[1] * kStride)};
+                const uint32_t shift[2] = {(uint32_t)(((long long)rows[0] * depth) & 15), (uint32_t)(((long long)rows[1] * depth) & 15)};
+                scramble_pairs_run_units<SIZE, 2>(two, base, shift, len, s_moves, s_ptbl, pair_lanereg<SIZE>(lane), pair_roff2(lane));
                 st[rows[0]] = two[0]; st[rows[1]] = two[1];
             }
         }
         for (int lane = 0; lane < 32; ++lane)
             for (int k = 0; k < 2; ++k) {
-                const int row = SIZE == 3 ? 2 * lane + k : lane + 32 * k;
+                const int row = lane + 32 * k;
                 if (last) scramble_pairs_last<SIZE>(st[row], last[tile * 64 + row], s_ptbl, pair_lanereg<SIZE>(lane), pair_roff2(lane));
                 solved[tile * 64 + row] = scramble_pairs_finish<SIZE>(st[row], row, ColourLutHost{clut, kEdgeColour3}, s_out.data());
             }
@@ -299,9 +300,11 @@ void emul_scramble_step_pairs(int size, const uint8_t* moves, const uint8_t* las
     else scramble_pairs_t<2, 2>(moves, n, depth, out, solved, fix, swz, last);
 }
 // K1p sliced (deep scrambles; `last` may be null); `moves` readable 16 bytes past its end
-void emul_scramble_sliced(int size, const uint8_t* moves, const uint8_t* last, long long n, int depth, uint8_t* out, uint8_t* solved)
+void emul_scramble_sliced(int size, const uint8_t* moves, const uint8_t* last, long long n, int depth, uint8_t* out, uint8_t* solved,
+                          int slice)
 {
-    if (size == 3) scramble_sliced_t<3>(moves, n, depth, out, solved, last); else scramble_sliced_t<2>(moves, n, depth, out, solved, last);
+    if (size == 3) scramble_sliced_t<3>(moves, n, depth, out, solved, last, slice);
+    else scramble_sliced_t<2>(moves, n, depth, out, solved, last, slice);
 }
 // cube_scramble_prefixes: out [n, depth, S] cube-major, solved [n, depth]
 void emul_prefixes(int size, const uint8_t* moves, long long n, int depth, uint8_t* out, uint8_t* solved)

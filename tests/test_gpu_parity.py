@@ -1217,10 +1217,14 @@ def test_exact_3x3_encoding_roundtrip_and_reference_mode_unchanged():
     s2, _, _ = ops.scramble(2, torch.randint(0, 6, (5000, 14), dtype=torch.uint8, device=dev(), generator=gen), want_flags=False)
     assert bool((ops.encode(2, s2, dtype=torch.uint8, encoding="exact") == ops.encode(2, s2, dtype=torch.uint8)).all())
     assert bool((ops.decode(2, ops.encode(2, s2, dtype=torch.uint8), encoding="exact") == s2).all())
-    # ragged sizes of the decode kernel
+    # ragged sizes of the decode kernels, every dtype
     for m in (1, 63, 64, 65, 1000):
-        e = ops.encode(3, states[:m].contiguous(), dtype=torch.bfloat16, encoding="exact")
-        assert bool((ops.decode(3, e, encoding="exact") == states[:m]).all())
+        for dt in (torch.uint8, torch.bfloat16, torch.float32):
+            e = ops.encode(3, states[:m].contiguous(), dtype=dt, encoding="exact")
+            assert bool((ops.decode(3, e, encoding="exact") == states[:m]).all())
+            e2 = ops.encode(2, s2[:m].contiguous(), dtype=dt)
+            assert bool((ops.decode(2, e2) == s2[:m]).all())
+            assert (ops.decode(2, e2).cpu().numpy() == O.decode_2(onehot_to_u8(e2)[0])).all()
 
 
 @pytest.mark.parametrize("size", SIZES)
@@ -1235,11 +1239,11 @@ def test_scramble_step_fused_equals_scramble_then_step(size, n, depth):
     A = T.N_ACTIONS[size]
     moves = rng.randint(A, size=(n, depth)).astype(np.uint8)
     act = rng.randint(A, size=n).astype(np.uint8)
-    if depth >= 2 and depth % 2 == 1:                                   # an odd palindrome-inverse, closed by the action
+    if depth >= 2 and depth % 2 == 1:                                   # a sequence that only the action brings home
         h = depth // 2
         k = min(n, 50)
-        moves[:k, h + 1:] = moves[:k, :h][:, ::-1] ^ 1
-        act[:k] = moves[:k, h] ^ 1
+        moves[:k, h:2 * h] = moves[:k, :h][:, ::-1] ^ 1                  # solved after 2h moves, then one more move ...
+        act[:k] = moves[:k, -1] ^ 1                                     # ... which the action undoes
     counters = ops.new_counters(dev())
     states, solved, reward = ops.scramble_step(size, cu(moves), cu(act), counters=counters)
     want, ws, wr, cnt = C.scramble(size, np.concatenate((moves, act[:, None]), axis=1))

@@ -27,7 +27,7 @@ def emul():
     lib.emul_scramble.argtypes = [ctypes.c_int, vp, ll, ctypes.c_int, vp, vp]
     lib.emul_scramble_pairs.argtypes = [ctypes.c_int, vp, ll, ctypes.c_int, vp, vp, ctypes.c_int]
     lib.emul_scramble_step_pairs.argtypes = [ctypes.c_int, vp, vp, ll, ctypes.c_int, vp, vp, ctypes.c_int]
-    lib.emul_scramble_sliced.argtypes = [ctypes.c_int, vp, vp, ll, ctypes.c_int, vp, vp]
+    lib.emul_scramble_sliced.argtypes = [ctypes.c_int, vp, vp, ll, ctypes.c_int, vp, vp, ctypes.c_int]
     lib.emul_prefixes.argtypes = [ctypes.c_int, vp, ll, ctypes.c_int, vp, vp]
     lib.emul_walk_private.argtypes = [ctypes.c_int, vp, vp, ll, ctypes.c_int, vp, vp]
     lib.emul_walk.argtypes = [ctypes.c_int, vp, vp, ll, ctypes.c_int, vp, vp]
@@ -300,11 +300,13 @@ def test_scramble_step_pairs_emulation(emul, size, depth, fixed):
 
 
 @pytest.mark.parametrize("size", (2, 3))
-@pytest.mark.parametrize("depth,with_last", [(321, 0), (400, 0), (479, 1), (480, 0), (481, 0), (723, 0), (1000, 1), (241, 0), (17, 0)])
-def test_scramble_sliced_emulation(emul, size, depth, with_last):
-    """K1p sliced (deep scrambles): pieces staged from the 16-byte boundary below them into 272-byte slots, the
-    shift (row * depth) & 15 the same in every slice, the cubie state carried from slice to slice with a fold
-    at every slice start (worst case: F R F R ... piles the twists up) -- against the oracle."""
+@pytest.mark.parametrize("slice_len", (112, 240))
+@pytest.mark.parametrize("depth,with_last", [(321, 0), (400, 0), (479, 1), (480, 0), (481, 0), (482, 0), (483, 1), (495, 0), (723, 0), (1000, 1), (241, 0), (17, 0), (254, 0)])
+def test_scramble_sliced_emulation(emul, size, depth, with_last, slice_len):
+    """K1p sliced (deep scrambles): pieces staged from the 16-byte boundary below them into 272-byte slots (the
+    host harness aborts on a misaligned 128-bit load), every per-row shift 0..15 taken out by the word select +
+    funnel, slices that end in 1..15 left-over moves, the cubie state carried from slice to slice with a fold
+    at every slice start and after every unit (worst case: F R F R ... piles the twists up) -- against the oracle."""
     rng = np.random.RandomState(depth + size)
     n = 64 * 2
     A = T.N_ACTIONS[size]
@@ -317,7 +319,7 @@ def test_scramble_sliced_emulation(emul, size, depth, with_last):
     last = rng.randint(A, size=n).astype(np.uint8) if with_last else None
     out = np.empty((n, T.N_STICKERS[size]), dtype=np.uint8)
     solved = np.empty(n, dtype=np.uint8)
-    emul.emul_scramble_sliced(size, _p(moves), _p(last), n, depth, _p(out), _p(solved))
+    emul.emul_scramble_sliced(size, _p(moves), _p(last), n, depth, _p(out), _p(solved), slice_len)
     want = O.scramble(size, m2)
     if with_last:
         want = O.apply_moves(size, want, last)

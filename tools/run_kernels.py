@@ -127,6 +127,14 @@ def main():
         timed("decode3x", lambda: ops.decode(3, oh, encoding="exact"), n)
         assert bool((ops.decode(3, oh, encoding="exact") == st).all())
         print("   decode3x algorithmic bytes/row %d" % (960 + 54))
+    if which in ("scramble3_d1000", "small"):      # K1p sliced: 1 Mi instances x depth 1000 (test.py:44 scrambles that deep)
+        n, d = 2 ** 20, 1000
+        moves = torch.randint(0, 12, (n, d), dtype=torch.uint8, device=dev, generator=gen)
+        st = torch.empty((n, 54), dtype=torch.uint8, device=dev)
+        so = torch.empty(n, dtype=torch.uint8, device=dev)
+        rw = torch.empty(n, dtype=torch.float32, device=dev)
+        timed("scramble3_d1000", lambda: ops.scramble(3, moves, out=st, solved=so, reward=rw), n * d)
+        print("   scramble3_d1000 algorithmic bytes/instance %d" % (d + 54 + 5))
     if which in ("scramble_step3", "small"):       # fused scramble + step (configs[2] read literally), 8 Mi x depth 30 + 1
         n, d = 8 * 2 ** 20, 30
         moves = torch.randint(0, 12, (n, d), dtype=torch.uint8, device=dev, generator=gen)
