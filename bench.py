@@ -347,6 +347,19 @@ def measure_other_configs(torch, ops, adi, dev, peak_gbs):
 
     t = time_launches(torch, scramble_then_step, 20)
     entry("config3_3x3_scramble_then_step_8Mi", t, n * (d + 1), "transitions/s", n * (d + 54 + 5) + n * (2 * 54 + 6))
+    # ... and fused into ONE launch (cube_scramble_step): the state never leaves the registers between the two
+    t = time_launches(torch, lambda: ops.scramble_step(3, moves, act, out=st, solved=so, reward=rw), 20)
+    entry("config3_3x3_scramble_step_fused_8Mi", t, n * (d + 1), "transitions/s", n * (d + 1 + 54 + 5))
+    del moves, act, st, so, rw
+    # config 2 with its step, fused: 2x2x2, 16 Mi x (depth 20 + 1)
+    n, d = 16 * 2 ** 20, 20
+    moves = torch.randint(0, 6, (n, d), dtype=torch.uint8, device=dev, generator=gen)
+    act = torch.randint(0, 6, (n,), dtype=torch.uint8, device=dev, generator=gen)
+    st = torch.empty((n, 24), dtype=torch.uint8, device=dev)
+    so = torch.empty(n, dtype=torch.uint8, device=dev)
+    rw = torch.empty(n, dtype=torch.float32, device=dev)
+    t = time_launches(torch, lambda: ops.scramble_step(2, moves, act, out=st, solved=so, reward=rw), 10)
+    entry("config2_2x2_scramble_step_fused_16Mi", t, n * (d + 1), "transitions/s", n * (d + 1 + 24 + 5))
     del moves, act, st, so, rw
 
     # config 4: 3x3x3 ADI expansion, 4 Mi parents -> bf16 [N,12,480] + solved + reward

@@ -21,7 +21,8 @@
  *     buffer that is not 16- / 8- / 4-byte aligned takes a byte-wise kernel).
  *   - calls are asynchronous on `stream` (a cudaStream_t, may be NULL), never
  *     allocate, never synchronise, keep no state between calls and are
- *     re-entrant.  Return value: 0, a negative CUBE_ERR_*, or a positive
+ *     re-entrant (the persistent kernels' tile counters come from a ring of 1 024
+ *     slots per device: fewer than that many launches may be RUNNING at once).  Return value: 0, a negative CUBE_ERR_*, or a positive
  *     cudaError_t.  cube_last_error() describes the last non-zero return of
  *     the calling thread.
  *   - action indices are NOT range-checked on the hot path: indices A..12 are

@@ -19,7 +19,12 @@ namespace sched {
 constexpr int kClaimChunk = 2;
 constexpr int kRanges = 8;
 constexpr int kTailDiv = 4;            // the last 1/4 of the tiles is claimed dynamically (measured: 8 -> +10 %, 4 -> +13 % on K2p)
-constexpr int kSlots = 128;
+// Slots are handed out round-robin from a ring: two launches share a slot only if kSlots launches of persistent
+// kernels are in flight AT THE SAME TIME on one device (across streams, host threads and concurrently replayed
+// CUDA graphs, which bake their slot in).  A kernel holds its slot for its own duration only, launches of one
+// stream serialise, so that takes > 1024 concurrently running streams / graphs -- far beyond what fits on 148
+// SMs; the ring costs 1.2 MB of device memory.
+constexpr int kSlots = 1024;
 constexpr int kExhausted = 0x7fffff00;
 
 struct Slot { unsigned next[kRanges][32]; unsigned ctas_done; unsigned tail_div; unsigned pad[30]; };
