@@ -82,7 +82,8 @@ class BatchedMCTS(object):
         self.model, self.cube_size, self.num_sim = model, cube_size, int(num_sim)
         self.cpuct, self.loss_const, self.value_min = float(cpuct), int(virtual_loss_const), float(value_min)
         self.obs_dtype, self.model_device = obs_dtype, model_device
-        self.graph = bool(graph)      # replay simulations 2.. as ONE captured CUDA graph (the model must be capturable)
+        self.graph = bool(graph)      # replay the simulations as ONE captured CUDA graph (the model must be capturable)
+        self._ws = {}                 # cached tree store (+ graph) of the last batch shape
         self.s, self.a = ops.N_STICKERS[cube_size], ops.N_ACTIONS[cube_size]
         self.r, self.c = ops.STATE_DIM[cube_size]
         self.key_bytes = 20 if cube_size == 3 else 8
@@ -108,6 +109,41 @@ class BatchedMCTS(object):
             rows.append([rng.randint(0, action_dim - 1) for _ in range(count)])
         return torch.tensor(rows, dtype=torch.uint8)
 
+    def _workspace(self, b, dev, rand_cap):
+        """The device tree store and the per-run bookkeeping for B trees, kept between runs: a search over a batch
+        of the same shape re-arms a dozen small tensors instead of allocating and zero-filling ~8 KB per tree, and
+        (graph=True) replays the simulation graph captured by the first run."""
+        key = (b, str(dev), rand_cap)
+        ws = self._ws.get(key)
+        if ws is not None:
+            return ws
+        m, a, kb = self.num_sim + 1, self.a, self.key_bytes
+
+        def z(shape, dtype):
+            return torch.zeros(shape, dtype=dtype, device=dev)
+
+        T = dict(node_key=z((b, m, kb), torch.uint8), child_key=z((b, m, a, kb), torch.uint8),
+                 child_done=z((b, m, a), torch.uint8), P=z((b, m, a), torch.float32), W=z((b, m, a), torch.float32),
+                 N=z((b, m, a), torch.int32), L=z((b, m, a), torch.int32), n_nodes=z((b,), torch.int32),
+                 active=torch.ones(b, dtype=torch.uint8, device=dev), root_state=z((b, self.s), torch.uint8),
+                 root_key=z((b, kb), torch.uint8), rand_table=z((b, rand_cap), torch.uint8),
+                 rand_ptr=z((b,), torch.int32), path_node=z((b, self.path_cap), torch.uint8),
+                 path_action=z((b, self.path_cap), torch.uint8), path_len=z((b,), torch.int32),
+                 leaf_state=z((b, self.s), torch.uint8), flags=z((1,), torch.int32),
+                 child_slot=torch.full((b, m, a), 255, dtype=torch.uint8, device=dev),
+                 sim_counter=torch.full((1,), -1, dtype=torch.int32, device=dev))
+        ws = dict(T=T, tree=_Tree(b, m, self.path_cap, rand_cap, *[T[name].data_ptr() for name, _ in _Tree._fields_[4:]]),
+                  actions=torch.full((b, self.path_cap + 1), -1, dtype=torch.int8, device=dev), n_actions=z((b,), torch.int32),
+                  n_sims=torch.full((b,), self.num_sim, dtype=torch.int32, device=dev), still=z((self.num_sim,), torch.int32),
+                  still_host=torch.full((self.num_sim,), -1, dtype=torch.int32).pin_memory(), graph=None, keep=None)
+        self._ws.clear()                                   # one batch shape at a time: a tree store is ~8 KB per tree
+        self._ws[key] = ws
+        return ws
+
+    def release(self):
+        """Drop the cached tree store (and the captured graph)."""
+        self._ws.clear()
+
     @torch.no_grad()
     def run(self, roots, seeds=None, rand_table=None, timers=None):
         """roots: uint8 [B, S] sticker rows (CUDA).  seeds: per-tree seeds of Python's `random`
@@ -118,7 +154,7 @@ class BatchedMCTS(object):
         lib = _lib.load()
         roots = roots.contiguous()
         dev = roots.device
-        b, m, a, kb = roots.shape[0], self.num_sim + 1, self.a, self.key_bytes
+        b, m, a = roots.shape[0], self.num_sim + 1, self.a
         mdev = dev if self.model_device is None else torch.device(self.model_device)
         if rand_table is None:
             if seeds is None:
@@ -129,31 +165,27 @@ class BatchedMCTS(object):
             raise ValueError("rand_table must be [B, draws per tree]")
         if rand_table.numel() and int(rand_table.max()) >= a:
             raise IndexError("rand_table holds action indices >= %d" % a)           # they index the node's child rows
-
-        def z(shape, dtype):
-            return torch.zeros(shape, dtype=dtype, device=dev)
-
-        T = dict(node_key=z((b, m, kb), torch.uint8), child_key=z((b, m, a, kb), torch.uint8),
-                 child_done=z((b, m, a), torch.uint8), P=z((b, m, a), torch.float32), W=z((b, m, a), torch.float32),
-                 N=z((b, m, a), torch.int32), L=z((b, m, a), torch.int32), n_nodes=z((b,), torch.int32),
-                 active=torch.ones(b, dtype=torch.uint8, device=dev), root_state=roots,
-                 root_key=self._codes(ops.encode(self.cube_size, roots, dtype=torch.uint8)), rand_table=rand_table,
-                 rand_ptr=z((b,), torch.int32), path_node=z((b, self.path_cap), torch.uint8),
-                 path_action=z((b, self.path_cap), torch.uint8), path_len=z((b,), torch.int32),
-                 leaf_state=z((b, self.s), torch.uint8), flags=z((1,), torch.int32),
-                 child_slot=torch.full((b, m, a), 255, dtype=torch.uint8, device=dev),
-                 sim_counter=torch.full((1,), -1, dtype=torch.int32, device=dev))
-        tree = _Tree(b, m, self.path_cap, rand_table.shape[1], *[T[name].data_ptr() for name, _ in _Tree._fields_[4:]])
-        actions = torch.full((b, self.path_cap + 1), -1, dtype=torch.int8, device=dev)
-        n_actions = z((b,), torch.int32)
-        n_sims = torch.full((b,), self.num_sim, dtype=torch.int32, device=dev)
+        ws = self._workspace(b, dev, rand_table.shape[1])
+        T, tree, actions, n_actions, n_sims = ws["T"], ws["tree"], ws["actions"], ws["n_actions"], ws["n_sims"]
+        still, still_host = ws["still"], ws["still_host"]
+        # re-arm: only what a search reads before it writes (node rows are initialised when a node is stored)
+        T["root_state"].copy_(roots)
+        T["root_key"].copy_(self._codes(ops.encode(self.cube_size, roots, dtype=torch.uint8)))
+        T["rand_table"].copy_(rand_table)
+        for name in ("n_nodes", "rand_ptr", "path_len", "flags"):
+            T[name].zero_()
+        T["active"].fill_(1)
+        T["sim_counter"].fill_(-1)
+        actions.fill_(-1)
+        n_actions.zero_()
+        n_sims.fill_(self.num_sim)
+        still.zero_()
+        still_host.fill_(-1)
         from ._timing import Phases
         phase = Phases(timers, dev)
         # Early exit without stalling the launch queue: every update kernel counts the trees that are still
         # searching into still[sim]; the counts travel to pinned host memory behind every simulation and are
         # looked at (never waited for) a few simulations later.
-        still = z((self.num_sim,), torch.int32)
-        still_host = torch.full((self.num_sim,), -1, dtype=torch.int32).pin_memory()
         direct = self.obs_dtype in ops.ONEHOT_DTYPES
 
         def simulate():
@@ -182,7 +214,8 @@ class BatchedMCTS(object):
             return res, value, policy                                    # kept alive by the caller (graph replays reuse them)
 
         with torch.cuda.device(dev):
-            graph, keep, landed, sim = None, None, [], 0
+            landed, sim = [], 0
+            use_graph = self.graph and timers is None
             while sim < self.num_sim:
                 done = False
                 while landed and landed[0][1].query():
@@ -190,15 +223,16 @@ class BatchedMCTS(object):
                         done = True
                 if done:
                     break
-                if self.graph and sim == 1 and timers is None:
-                    # the first simulation ran eagerly (library warm-up); the rest replay one captured simulation
-                    graph = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(graph):
-                        keep = simulate()
-                if graph is not None:
-                    graph.replay()
+                if use_graph and ws["graph"] is None and sim == 1:
+                    # the very first simulation ran eagerly (library warm-up); from here on -- and in every later
+                    # run over a batch of this shape -- one captured simulation is replayed
+                    ws["graph"] = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(ws["graph"]):
+                        ws["keep"] = simulate()
+                if use_graph and ws["graph"] is not None:
+                    ws["graph"].replay()
                 else:
-                    keep = simulate()
+                    simulate()
                 ev = torch.cuda.Event()
                 ev.record(torch.cuda.current_stream(dev))
                 landed.append((sim, ev, still_host[sim:sim + 1]))

@@ -1293,3 +1293,28 @@ def test_deep_scrambles_sliced_kernel(size, depth):
     st2, so2, _ = ops.scramble_step(size, cu(moves), cu(act))
     assert (st2.cpu().numpy() == O.apply_moves(size, want, act)).all()
     assert (so2.cpu().numpy().astype(bool) == O.is_solved(size, O.apply_moves(size, want, act))).all()
+
+
+@pytest.mark.parametrize("size", SIZES)
+@pytest.mark.parametrize("graph", (False, True))
+def test_batched_mcts_reuses_its_tree_store_across_runs(size, graph):
+    """A BatchedMCTS keeps its device tree store (and, with graph=True, the captured simulation) between runs over
+    batches of the same shape: a second and third search with other roots / seeds must equal fresh searches --
+    nothing of the previous trees may leak (stale node keys, memos, counters, action lists)."""
+    from rubiks_cube_solver_b200 import mcts_batch
+    from oracle.gen_golden import ExactSearchNet
+    A = T.N_ACTIONS[size]
+    net = ExactSearchNet(T.STATE_DIM[size], A).to(dev())
+    rng = np.random.RandomState(size + 40)
+    search = mcts_batch.BatchedMCTS(net, size, num_sim=14, graph=graph)
+    for rep in range(3):
+        n = 96
+        roots = np.stack([O.scramble(size, rng.randint(A, size=(1, int(d))))[0] for d in rng.randint(1, 5, size=n)])
+        seeds = [int(x) for x in rng.randint(0, 10 ** 6, size=n)]
+        got = search.run(cu(roots), seeds=seeds)
+        want = mcts_batch.BatchedMCTS(net, size, num_sim=14).run(cu(roots), seeds=seeds)
+        for key in ("solved", "n_actions", "n_sims", "n_nodes", "root_N", "root_W", "root_L"):
+            assert bool((got[key] == want[key]).all()), (rep, key)
+        w = min(got["actions"].shape[1], want["actions"].shape[1])
+        assert bool((got["actions"][:, :w] == want["actions"][:, :w]).all())
+    search.release()
