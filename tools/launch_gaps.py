@@ -1,7 +1,7 @@
 """Per-launch gaps of chained scramble launches (events between launches break the dependent-launch
 chain on purpose): how much of a short timed region is launch latency."""
 import sys, time
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 import torch
 from rubiks_cube_solver_b200 import ops
 dev = torch.device('cuda', 0)

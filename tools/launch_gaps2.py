@@ -1,7 +1,7 @@
 """Fixed overhead of a 5-step timed region with / without the NVML sampler thread and a second sync
 (used to move the sampler thread's start-up out of bench.py's timed region)."""
 import sys, time, threading
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 import torch, bench
 from rubiks_cube_solver_b200 import ops
 dev = torch.device('cuda', 0)
