@@ -1318,3 +1318,55 @@ def test_batched_mcts_reuses_its_tree_store_across_runs(size, graph):
         w = min(got["actions"].shape[1], want["actions"].shape[1])
         assert bool((got["actions"][:, :w] == want["actions"][:, :w]).all())
     search.release()
+
+
+@pytest.mark.parametrize("size", SIZES)
+def test_adi_generate_samples_bf16_passthrough_within_tolerance(size):
+    """The ADI iteration with the net in bfloat16: K3's bf16 one-hot buffer reaches the model AS IT IS (no .float()
+    pass: the recorded input dtype is bfloat16), chunk by chunk, and the targets agree with the float32 net's within
+    bf16 tolerance -- |dV| <= 3e-2 * max(1, |V|) (8-bit mantissa through four layers) -- while everything that is
+    integer work (parents' one-hot rows, stickers, solved children, scramble counts) is identical.  The target
+    policy may differ only where the float32 values of the best two children are closer than that tolerance."""
+    A, (r, c) = T.N_ACTIONS[size], T.STATE_DIM[size]
+    nn = torch.nn
+
+    class Net(nn.Module):                                   # DeepCube's shape (model.py:7-45), small hidden sizes
+        def __init__(self):
+            super().__init__()
+            self.enc = nn.Sequential(nn.Flatten(), nn.Linear(r * c, 256), nn.ELU(), nn.Linear(256, 64), nn.ELU())
+            self.pol = nn.Sequential(nn.Linear(64, 32), nn.ELU(), nn.Linear(32, A))
+            self.val = nn.Sequential(nn.Linear(64, 32), nn.ELU(), nn.Linear(32, 1))
+            self.seen = set()
+
+        def forward(self, x):
+            self.seen.add(x.dtype)
+            if x.dim() == 2:
+                x = x.unsqueeze(0)
+            h = self.enc(x)
+            return self.val(h), self.pol(h)
+
+    torch.manual_seed(size)
+    net32 = Net().to(dev())
+    net16 = Net().to(dev())
+    net16.load_state_dict(net32.state_dict())
+    net16 = net16.to(torch.bfloat16)
+    rng = np.random.RandomState(size)
+    moves = cu(rng.randint(A, size=(700, 9)).astype(np.uint8))
+    moves[0, :2] = torch.tensor([4, 5], dtype=torch.uint8)                # back at solved after two moves
+    a32 = adi.generate_samples(size, moves, net32, 0.5, forward_chunk=1024)
+    a16 = adi.generate_samples(size, moves, net16, 0.5, forward_chunk=1024)
+    assert net32.seen == {torch.float32} and net16.seen == {torch.bfloat16}
+    assert a32["state"].dtype == torch.float32 and a16["state"].dtype == torch.bfloat16
+    assert bool((a16["state"].float() == a32["state"]).all()) and bool((a16["stickers"] == a32["stickers"]).all())
+    assert bool((a16["child_solved"] == a32["child_solved"]).all()) and bool((a16["scramble_count"] == a32["scramble_count"]).all())
+    tol = 3e-2 * torch.clamp(a32["target_value"].abs(), min=1.0)
+    assert bool(((a16["target_value"] - a32["target_value"]).abs() <= tol).all())
+    top2 = (a32["child_values"] - 1.0).topk(2, dim=1).values
+    clear = ((top2[:, 0] - top2[:, 1]) > 2 * tol) | a32["child_solved"].bool().any(dim=1)
+    assert bool((a16["target_policy"][clear] == a32["target_policy"][clear]).all()) and int(clear.sum()) > 100
+    assert bool(((a16["error"] - a32["error"]).abs() <= 2 * tol.double()).all())
+    # the oracle's rules on the float32 run (cube_env.py:239-252)
+    tv, tp, err = O.adi_targets(a32["child_values"].cpu().numpy(), a32["child_solved"].cpu().numpy().astype(bool),
+                                a32["parent_values"].cpu().numpy(), a32["scramble_count"].cpu().numpy(), 0.5)
+    assert (a32["target_value"].cpu().numpy() == tv).all() and (a32["target_policy"].cpu().numpy() == tp).all()
+    assert np.allclose(a32["error"].cpu().numpy(), err, rtol=0, atol=1e-12)
