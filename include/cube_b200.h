@@ -288,9 +288,9 @@ int cube_host_free(void* p);
 /* ---- single-cube host front end (the drop-in CubeEnv's per-call path) ---------------------
  * The reference's callers drive ONE cube per call (env.reset / env.step / get_obs:
  * cube_env.py:56-111, used by train.py:155,186-191, mcts.py:80, test.py:123).  A handle owns a
- * page of mapped pinned memory that the kernels read and write directly, so a call is one or
- * two launches and one stream synchronisation, with no copy calls: ~20 us instead of ~120 us
- * through device tensors.  Blocking; all buffers are HOST buffers; any out pointer may be NULL.
+ * page of mapped pinned memory that the kernel reads and writes directly, so a call is ONE launch
+ * of a one-cube kernel plus a wait for its completion word (polled in the page; cudaStreamSynchronize
+ * as the fallback), with no copy calls: ~20 us instead of ~120 us through device tensors.  Blocking; all buffers are HOST buffers; any out pointer may be NULL.
  * A handle is bound to the device current at creation and must not be used by two threads at once.
  *   stickers_host      [S]   uint8  in
  *   stickers_out_host  [S]   uint8  out
