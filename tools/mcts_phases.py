@@ -2,7 +2,6 @@
     python tools/mcts_phases.py [--trees 65536] [--sims 50]
 traverse / expand_codes / net / softmax glue / update, CUDA events around every phase of every simulation."""
 import argparse
-import ctypes
 import json
 import os
 import sys
@@ -13,7 +12,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 
-from rubiks_cube_solver_b200 import _lib, mcts_batch, ops
+from rubiks_cube_solver_b200 import mcts_batch, ops
 
 
 def main():
@@ -24,7 +23,6 @@ def main():
     ap.add_argument("--variants", action="store_true", help="also time graph replay and a bf16 net")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
-    import bench
     # the same net as bench.measure_mcts
     nn = torch.nn
 
