@@ -28,4 +28,9 @@ Parity pin status
   reference's ``cube_env.py`` + ``model.py`` on the restatement it solves 100 %
   of 200 scrambles at depths 1-5 and 96.5 % at depth 8, and stops solving as
   soon as a move or an encoding table is perturbed.
+* The opt-in EXACT 3x3x3 encoding (``cube_np.encode_exact`` / ``decode_exact``) is
+  not a restatement of anything in the reference -- the reference has no such
+  encoding -- but the SPEC of the library's ``CUBE_ENCODING_EXACT``: it is pinned
+  by its own properties (bijection, decode o encode = id, parities), and its edge
+  part equals the reference's edge table.
 """
