@@ -58,10 +58,11 @@ def greedy_actions(policy_logits, pre_action=None):
 
 
 @torch.no_grad()
-def greedy_solve(model, cube_size, moves, max_timesteps=200, mask_inverse=False, obs_dtype=torch.float32,
+def greedy_solve(model, cube_size, moves, max_timesteps=200, mask_inverse=False, obs_dtype=None,
                  model_device=None):
     """Scramble with `moves` ([N, depth] uint8, host or CUDA; NOOP-padded rows allowed), then follow
-    the greedy policy of `model` for at most `max_timesteps` steps.
+    the greedy policy of `model` for at most `max_timesteps` steps.  `obs_dtype` defaults to the dtype the model
+    computes in (a bfloat16 DeepCube reads the encode kernel's bf16 rows as they are, no `.float()` pass).
 
     Returns dict(solved bool [N], steps int64 [N] (time step of the first done, 0 = never),
     states uint8 [N, S] final sticker rows).
@@ -73,6 +74,10 @@ def greedy_solve(model, cube_size, moves, max_timesteps=200, mask_inverse=False,
     dev = moves.device if moves.is_cuda else torch.device("cuda", torch.cuda.current_device())
     moves = moves.to(dev).contiguous()
     mdev = dev if model_device is None else torch.device(model_device)
+    from .adi import model_dtype, param_dtype
+    if obs_dtype is None:
+        obs_dtype = model_dtype(model)
+    in_dtype = param_dtype(model)
     n = moves.shape[0]
     states, _, _ = ops.scramble(cube_size, moves, want_flags=False)
     done = torch.zeros(n, dtype=torch.bool, device=dev)
@@ -84,15 +89,18 @@ def greedy_solve(model, cube_size, moves, max_timesteps=200, mask_inverse=False,
     noop = torch.full((n,), NOOP, dtype=torch.int64, device=dev)
     for t in range(1, max_timesteps + 1):
         ops.encode(cube_size, states, dtype=obs_dtype, out=obs)
-        _, logits = model(obs.to(mdev).float())
-        action = greedy_actions(logits.to(dev), pre if mask_inverse else None)
+        x = obs.to(mdev)
+        if in_dtype is not None and x.dtype != in_dtype:
+            x = x.to(in_dtype)
+        _, logits = model(x)
+        action = greedy_actions(logits.float().to(dev), pre if mask_inverse else None)
         action = torch.where(done, noop, action)
         ops.step(cube_size, states, action.to(torch.uint8), solved=solved, reward=reward)
         newly = solved.bool() & ~done
         steps = torch.where(newly, torch.full_like(steps, t), steps)
         done |= newly
         pre = action
-        if bool(done.all()):
+        if t % 8 == 0 and bool(done.all()):               # one host synchronisation every eight time steps, not every one
             break
     return dict(solved=done, steps=steps, states=states)
 
