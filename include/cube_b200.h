@@ -120,7 +120,7 @@ int cube_scramble_step(int cube_size, const uint8_t* moves, const uint8_t* actio
  *                                        the order in which the reference appends to its replay buffer)
  *   solved     [n, depth]    uint8  out or NULL  isSolved of every prefix
  * counters[0] += solved prefixes, [1] += n * depth.  depth <= cube_scramble_prefixes_max_depth(cube_size)
- * (131 / 289: a tile of 32 cubes x depth rows is staged in shared memory), else CUBE_ERR_ARG. */
+ * (526 / 1159: a tile of 8 cubes x depth rows is staged in shared memory), else CUBE_ERR_ARG. */
 int cube_scramble_prefixes(int cube_size, const uint8_t* moves, int64_t n, int depth, uint8_t* states_out,
                            uint8_t* solved, uint64_t* counters, void* stream);
 int cube_scramble_prefixes_max_depth(int cube_size);

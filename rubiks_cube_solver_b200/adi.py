@@ -30,7 +30,7 @@ def scramble_prefixes(cube_size, moves):
     """All prefix states of every scramble, cube-major: [n, depth, S] uint8 with
     out[i, k] = state of cube i after moves[i, 0..k] (cube_env.py:187-191).
 
-    One launch (cube_scramble_prefixes) up to depth 131 (3x3x3) / 289 (2x2x2); deeper scrambles
+    One launch (cube_scramble_prefixes) up to depth 526 (3x3x3) / 1159 (2x2x2); deeper scrambles
     fall back to one cube_walk launch per level."""
     n, depth = moves.shape
     dev = moves.device

@@ -70,17 +70,26 @@ CUBE_HD bool scramble_finish(CubieState& st, int tid, const uint32_t* s_clut, co
 
 // ---- K1x: every prefix of one scramble (cube_scramble_prefixes) ---------------------------------
 // `my` = the cube's depth move bytes; row0 = index of its first row in the tile image s_img (rows are the
-// tile's output block: cube-major, depth rows per cube).  Returns the number of solved prefixes; flags (or
-// null) receives the done flag of every prefix.  The running state stays lazy (twist fields folded every 4
-// moves like the fused scramble); each level is finished on a copy.
+// tile's output block: cube-major, depth rows per cube).  The caller's lane produces the levels [k_begin, k_end)
+// only -- a cube's levels are split over several lanes, each of which first fast-forwards through the moves
+// before its share (a move is ~12 instructions, finishing a level ~100) -- and returns the number of solved
+// prefixes among them; flags (or null) receives the done flag of every produced level.  The running state stays
+// lazy (twist fields folded every 4 moves like the fused scramble); each level is finished on a copy.
 template <int SIZE>
 CUBE_HD unsigned prefix_walk(const uint8_t* my, int depth, int row0, const uint32_t* s_tbl, const uint32_t* s_clut,
-                             const uint32_t* s_elut, uint8_t* s_img, uint8_t* flags)
+                             const uint32_t* s_elut, uint8_t* s_img, uint8_t* flags, int k_begin, int k_end)
 {
     CubieState st;
     cubie_init(st);
     unsigned n_solved = 0;
-    for (int k = 0; k < depth; ++k) {
+    (void)depth;
+    // fast-forward (trip counts differ between the lanes of a warp, but the body is a dozen instructions) ...
+    for (int k = 0; k < k_begin; ++k) {
+        cubie_move<SIZE>(st, s_tbl, (uint32_t)my[k] & 0xfu);
+        if ((k & 3) == 3) { st.c0 = cubie_fold_twist(st.c0); st.c1 = cubie_fold_twist(st.c1); }
+    }
+    // ... then the lane's own levels, which the lanes of a warp produce in lockstep (their shares differ by <= 1)
+    for (int k = k_begin; k < k_end; ++k) {
         cubie_move<SIZE>(st, s_tbl, (uint32_t)my[k] & 0xfu);
         if ((k & 3) == 3) { st.c0 = cubie_fold_twist(st.c0); st.c1 = cubie_fold_twist(st.c1); }
         CubieState now = st;

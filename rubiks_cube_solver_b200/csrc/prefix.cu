@@ -4,11 +4,14 @@
 // scramble: the parents of an ADI batch are all scramble prefixes, appended cube by cube, depth by
 // depth.  This kernel writes exactly that array:
 //     states_out[i, k, :] = the sticker row after moves[i, 0..k]        (k = 0 .. depth-1)
-// A warp owns a tile of 32 cubes = one contiguous block of 32 * depth sticker rows of the output.
-// Each lane walks its cube with the fused-scramble arithmetic (five registers of cubie bytes, one
-// PRMT table row per move, cube_common.cuh) and, after every move, expands the state to its sticker
-// row in a shared-memory image of the tile's output block; the finished block leaves by one bulk
-// store (TMA), so the 54-byte rows cost no uncoalesced global stores.  Replaces one cube_walk launch
+// A warp owns a tile of 8 cubes = one contiguous block of 8 * depth sticker rows of the output, and
+// FOUR lanes share a cube: lane (part, cube) walks the cube with the fused-scramble arithmetic (five
+// registers of cubie bytes, one PRMT table row per move, cube_common.cuh), fast-forwards through the
+// moves before its quarter of the levels (a move is ~12 instructions) and expands every level of its
+// quarter to a sticker row (~100 instructions) in a shared-memory image of the tile's output block; the
+// finished block leaves by one bulk store (TMA), so the 54-byte rows cost no uncoalesced global stores.
+// (The first version gave a lane a whole cube and a warp 32 cubes: a 52 KB image per warp at depth 30,
+// 4 warps per SM, 30 dependent levels per lane: 0.095 ms for config 4's parents, occupancy 6 %.)  Replaces one cube_walk launch
 // per depth level plus the step-major -> cube-major transposes of round 1 (adi.py).
 // HBM traffic per cube: depth (moves in) + depth * (S + 1) bytes out.
 #include <atomic>
@@ -19,8 +22,9 @@
 
 namespace {
 
-constexpr int kCubesPerTile = 32;
-constexpr int kMaxWarps = 8;
+constexpr int kSplit = 4;                          // lanes per cube: the levels of a cube are split four ways
+constexpr int kCubesPerTile = 32 / kSplit;
+constexpr int kMaxWarps = 16;
 constexpr int kSmemLimit = 227 * 1024;
 
 template <int SIZE>
@@ -30,7 +34,7 @@ struct PrefixSmem {
     static constexpr int kCornerLut = kTable + G::MW * CUBE_MOVE_ROWS * 4;
     static constexpr int kEdgeLut = kCornerLut + 32 * 4;
     static constexpr int kPerWarp = (kEdgeLut + 64 * 4 + 127) & ~127;
-    __host__ __device__ static constexpr int image_bytes(int depth) { return kCubesPerTile * depth * G::S; }   // multiple of 16
+    __host__ __device__ static constexpr int image_bytes(int depth) { return (kCubesPerTile * depth * G::S + 15) & ~15; }
     __host__ __device__ static constexpr int moves_bytes(int depth) { return (kCubesPerTile * depth + 15 + 16) & ~15; }
     __host__ __device__ static constexpr int per_warp(int depth) { return image_bytes(depth) + moves_bytes(depth); }
     __host__ __device__ static constexpr int bytes(int depth, int warps) { return kPerWarp + warps * per_warp(depth); }
@@ -62,7 +66,7 @@ prefix_kernel(const uint8_t* __restrict__ moves, long long n, int depth, uint8_t
     for (long long tile = (long long)blockIdx.x * warps + warp; tile < n_tiles; tile += (long long)gridDim.x * warps) {
         const long long cube0 = tile * kCubesPerTile;
         const int cnt = (n - cube0) < kCubesPerTile ? (int)(n - cube0) : kCubesPerTile;
-        // the tile's move bytes: 32 * depth contiguous bytes, word-aligned (cube0 is a multiple of 32)
+        // the tile's move bytes: 8 * depth contiguous bytes, word-aligned (cube0 is a multiple of 8)
         const uint8_t* mv_g = moves + cube0 * depth;
         const int mv_bytes = cnt * depth;
         {
@@ -74,15 +78,21 @@ prefix_kernel(const uint8_t* __restrict__ moves, long long n, int depth, uint8_t
         }
         if (lane == 0) bulk::wait_read_all();                           // the previous tile's store has read the image
         __syncwarp();
-        if (lane < cnt)
-            n_solved += prefix_walk<SIZE>(s_mv + lane * depth, depth, lane * depth, s_tbl, s_clut, s_elut, s_img,
-                                          solved ? solved + (cube0 + lane) * depth : nullptr);
+        {
+            const int cube = lane % kCubesPerTile, part = lane / kCubesPerTile;
+            const int k_begin = part * depth / kSplit, k_end = (part + 1) * depth / kSplit;
+            if (cube < cnt && k_begin < k_end)
+                n_solved += prefix_walk<SIZE>(s_mv + cube * depth, depth, cube * depth, s_tbl, s_clut, s_elut, s_img,
+                                              solved ? solved + (cube0 + cube) * depth : nullptr, k_begin, k_end);
+        }
         bulk::fence_smem_writes();
         __syncwarp();
         uint8_t* dst_g = out + cube0 * row_bytes;
+        // a whole tile leaves by one bulk store when its block is a multiple of 16 bytes (8 * S is: any depth
+        // for 2x2x2; 8 * 54 = 432 = 27 * 16 for 3x3x3)
         if (cnt == kCubesPerTile) {
             if (lane == 0) {
-                bulk::store(dst_g, s_img, (uint32_t)L::image_bytes(depth));
+                bulk::store(dst_g, s_img, (uint32_t)(kCubesPerTile * depth * G::S));
                 bulk::commit();
             }
         } else {                                                        // ragged last tile: plain copies

@@ -135,7 +135,7 @@ def scramble_step(cube_size, moves, actions, out=None, solved=None, reward=None,
 
 
 def prefixes_max_depth(cube_size):
-    """Largest depth cube_scramble_prefixes takes (131 for 3x3x3, 289 for 2x2x2)."""
+    """Largest depth cube_scramble_prefixes takes (526 for 3x3x3, 1159 for 2x2x2)."""
     _geom(cube_size)
     return _lib.load().cube_scramble_prefixes_max_depth(cube_size)
 

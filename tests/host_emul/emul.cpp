@@ -83,19 +83,26 @@ void scramble_sliced_t(const uint8_t* moves, long long n, int depth, uint8_t* ou
     }
 }
 
-// K1x: all prefixes of every scramble, a tile of 32 cubes at a time with the kernel's tile image
+// K1x: all prefixes of every scramble, a tile of 8 cubes at a time with the kernel's tile image and its
+// four-lanes-per-cube split of the levels
 template <int SIZE>
 void prefixes_t(const uint8_t* moves, long long n, int depth, uint8_t* out, uint8_t* solved)
 {
     using G = CubeGeom<SIZE>;
+    constexpr int kSplit = 4, kCubes = 32 / kSplit;
     const uint32_t* tbl = SIZE == 3 ? kMoveWords3 : kMoveWords2;
     const uint32_t* clut = SIZE == 3 ? kCornerColour3 : kCornerColour2;
-    std::vector<uint8_t> img((size_t)32 * depth * G::S + 16);
-    for (long long cube0 = 0; cube0 < n; cube0 += 32) {
-        const int cnt = (int)((n - cube0) < 32 ? (n - cube0) : 32);
-        for (int lane = 0; lane < cnt; ++lane)
-            prefix_walk<SIZE>(moves + (cube0 + lane) * depth, depth, lane * depth, tbl, clut, kEdgeColour3, img.data(),
-                              solved + (cube0 + lane) * depth);
+    std::vector<uint8_t> img((size_t)kCubes * depth * G::S + 16);
+    for (long long cube0 = 0; cube0 < n; cube0 += kCubes) {
+        const int cnt = (int)((n - cube0) < kCubes ? (n - cube0) : kCubes);
+        std::memset(img.data(), 0xee, img.size());
+        for (int lane = 0; lane < 32; ++lane) {
+            const int cube = lane % kCubes, part = lane / kCubes;
+            const int k_begin = part * depth / kSplit, k_end = (part + 1) * depth / kSplit;
+            if (cube < cnt && k_begin < k_end)
+                prefix_walk<SIZE>(moves + (cube0 + cube) * depth, depth, cube * depth, tbl, clut, kEdgeColour3, img.data(),
+                                  solved + (cube0 + cube) * depth, k_begin, k_end);
+        }
         std::memcpy(out + cube0 * depth * G::S, img.data(), (size_t)cnt * depth * G::S);
     }
 }

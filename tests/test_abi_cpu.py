@@ -49,8 +49,8 @@ def test_argument_errors_without_cuda(lib):
     assert lib.cube_decode(3, aligned, 2, _lib.ENCODING_REFERENCE, 1, aligned, None) == _lib.CUBE_ERR_SIZE   # lossy: no inverse
     assert lib.cube_decode(3, odd, 2, _lib.ENCODING_EXACT, 1, aligned, None) == _lib.CUBE_ERR_ALIGN
     assert lib.cube_scramble_step(3, aligned, None, 1, 1, aligned, None, None, None, None) == _lib.CUBE_ERR_ARG
-    assert lib.cube_scramble_prefixes(3, aligned, 1, 132, aligned, None, None, None) == _lib.CUBE_ERR_ARG
-    assert lib.cube_scramble_prefixes_max_depth(3) == 131 and lib.cube_scramble_prefixes_max_depth(2) == 289
+    assert lib.cube_scramble_prefixes(3, aligned, 1, 527, aligned, None, None, None) == _lib.CUBE_ERR_ARG
+    assert lib.cube_scramble_prefixes_max_depth(3) == 526 and lib.cube_scramble_prefixes_max_depth(2) == 1159
     assert lib.cube_pipeline_reset_host(None, None, 1, None, None, None, None) == _lib.CUBE_ERR_ARG
     assert lib.cube_host_alloc(0, None) == _lib.CUBE_ERR_ARG and lib.cube_host_free(aligned) == _lib.CUBE_ERR_ARG
     with pytest.raises(NotImplementedError):

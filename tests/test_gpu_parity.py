@@ -1042,7 +1042,7 @@ def test_expand_codes_vs_oracle(size, n):
 
 @pytest.mark.parametrize("size", SIZES)
 @pytest.mark.parametrize("n,depth", [(1, 1), (31, 2), (32, 30), (33, 30), (1000, 7), (148 * 8 * 32 * 2 + 5, 30), (4099, 31),
-                                     (100, 131), (70, 289), (70, 290)])
+                                     (100, 131), (70, 289), (40, 526), (24, 527), (9, 1160)])
 def test_scramble_prefixes_vs_oracle(size, n, depth):
     """cube_scramble_prefixes: every prefix of every scramble in one launch, cube-major
     (get_random_samples' order, cube_env.py:187-194), with the done flag of every prefix -- against the
@@ -1066,7 +1066,7 @@ def test_scramble_prefixes_vs_oracle(size, n, depth):
         with pytest.raises(ValueError):
             ops.scramble_prefixes(size, cu(moves))
     assert (adi.scramble_prefixes(size, cu(moves)).cpu().numpy() == want).all()
-    assert ops.prefixes_max_depth(size) == (131 if size == 3 else 289)
+    assert ops.prefixes_max_depth(size) == (526 if size == 3 else 1159)
 
 
 @pytest.mark.parametrize("size", SIZES)
