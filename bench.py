@@ -569,6 +569,12 @@ def measure_mcts(torch, dev):
     mcts_batch.BatchedMCTS(gpu_net, 2, num_sim=num_sim).run(roots, rand_table=table, timers=timers)
     import copy
     dt16, res16 = timed_search(copy.deepcopy(gpu_net).to(torch.bfloat16), torch.bfloat16)
+    tf32_was = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True           # the caller's choice, like the net's dtype: float32 weights, TF32 products
+    try:
+        dt_tf32, res_tf32 = timed_search(gpu_net, torch.float32)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = tf32_was
     sims = int(res["n_sims"].sum())
     env = ScalarCubeEnv(2)
     torch.set_num_threads(1)
@@ -587,6 +593,8 @@ def measure_mcts(torch, dev):
                          "simulations_per_s": int(res16["n_sims"].sum()) / dt16,
                          "note": "the same search with the net (and the leaves' one-hot rows) in bfloat16: the float32 "
                                  "net's SIMT GEMMs are two thirds of the float32 search's time"},
+            "float32_net_tf32_matmul": {"ms": dt_tf32 * 1e3, "solved": int(res_tf32["solved"].sum()),
+                                        "simulations_per_s": int(res_tf32["n_sims"].sum()) / dt_tf32},
             "note": "one simulation = traverse + leaf expansion (6 children, net value/policy) + back-propagation "
                     "(mcts.py:36-130); 65 536 cubes scrambled 8 deep, 50 simulations each"}
 
