@@ -1096,7 +1096,7 @@ def test_batched_mcts_graph_replay_equals_eager_and_golden(size, obs_dtype):
 
 
 @pytest.mark.parametrize("size", SIZES)
-@pytest.mark.parametrize("num_sim", (1, 2, 3, 4, 30))
+@pytest.mark.parametrize("num_sim", (1, 2, 3, 4, 30, 50))
 def test_batched_mcts_short_searches_full_action_lists(size, num_sim):
     """a traversal may bounce (U then U' is back at the root's key), so a returned path can be longer
     than num_sim + 1; the action list must come back whole (n_actions <= actions.shape[1]) and equal to the
@@ -1109,11 +1109,12 @@ def test_batched_mcts_short_searches_full_action_lists(size, num_sim):
     n = 300 if num_sim < 30 else 60
     rng = np.random.RandomState(31 * num_sim + size)
     A = T.N_ACTIONS[size]
-    depths = rng.randint(1, 5, size=n)
+    depths = rng.randint(1, 5 if num_sim < 50 else 9, size=n)      # deeper roots: longer searches, more transpositions
     roots = np.stack([O.scramble(size, rng.randint(A, size=(1, int(d))))[0] for d in depths])
     gpu_net = ExactSearchNet(T.STATE_DIM[size], A).to(dev())
     cpu_net = ExactSearchNet(T.STATE_DIM[size], A)
     out = mcts_batch.BatchedMCTS(gpu_net, size, num_sim=num_sim, graph=(num_sim == 30)).run(cu(roots), seeds=list(range(n)))
+    assert num_sim < 50 or not bool(out["solved"].all())             # some trees run their whole budget
     assert int(out["n_actions"].max()) <= out["actions"].shape[1]
     env = ScalarCubeEnv(size)
     for i in range(n):
