@@ -101,13 +101,24 @@ CUBE_HD unsigned prefix_walk(const uint8_t* my, int depth, int row0, const uint3
 }
 
 // ---- K1p: fused scramble, two moves per table row --------------------------------------------
-// The pair table lives in shared memory with 256 bytes per row, every vector replicated once per
-// lane slot: 3x3x3 rows are two 16-byte vectors (P, Q) x 8 slots; 2x2x2 rows are (selectors, T0) as
-// 8 bytes x 16 slots plus T1 as 4 bytes x 32 slots.  A lane only ever reads its own slot, so the
-// 128- / 64- / 32-bit loads of a quarter / half / whole warp touch disjoint banks whatever rows the
-// lanes ask for: no bank conflicts by construction.
-// `lanereg` = the lane's slot offset in byte 0 (bytes 1..3 zero); a row address is then ONE byte
-// permute: byte 1 <- the pair index, byte 0 <- the slot offset.
+// The pair table lives in shared memory as TWO arrays of 128-byte rows (the second kPairSecond bytes behind
+// the first), every vector replicated once per lane slot: 3x3x3 rows are the two 16-byte vectors P and Q x 8
+// slots each; 2x2x2 rows are (selectors, T0) as 8 bytes x 16 slots and T1 as 4 bytes x 32 slots.  A lane only
+// ever reads its own slot, so the 128- / 64- / 32-bit loads of a quarter / half / whole warp touch disjoint
+// banks whatever rows the lanes ask for: no bank conflicts by construction.
+// `lanereg` = the address of the lane's slot in row 0 of the first array; the address of a pair's row is then
+// ONE byte dot product with the word that carries the pair indices in bytes 1 and 3 (weight 128 on the wanted
+// byte, `lanereg` as the accumulator): IDP.4A issues on the FMA pipe, which idles while PRMT / LOP3 keep the
+// ALU pipe busy.  (Until round 2 the rows were 256 bytes and the address a PRMT of the pair byte over the slot
+// byte: one more instruction on the binding pipe per pair.)
+constexpr int kPairSecond = CUBE_PAIR_ROWS * 128;
+
+template <int HALF>
+CUBE_HD uint32_t pair_addr(uint32_t y, uint32_t lanereg)        // HALF 0: the pair in byte 1 of y, 1: in byte 3
+{
+    return cube_dp4a(y, HALF ? 0x80000000u : 0x00008000u, lanereg);
+}
+
 struct CubeVec4 { uint32_t x, y, z, w; };
 
 CUBE_HD CubeVec4 cube_ld128(const uint8_t* p)
@@ -124,13 +135,11 @@ CUBE_HD CubeVec4 cube_ld128(const uint8_t* p)
 #endif
 }
 
-// Where the pair table is read from.  Host (test emulation): a plain pointer.  Device: absolute
-// 32-bit shared-window addresses -- the table sits on a 256-byte boundary of the window, so its
-// base is folded into the pair-row byte (`bias` = base >> 8 in bytes 1 and 3, added by the same
-// multiply-add that forms the row numbers) and the permute's result IS the load address.
+// Where the pair table is read from.  Host (test emulation): a plain pointer, addresses relative to it.
+// Device: absolute 32-bit shared-window addresses (`lanereg` includes the table's).
 struct PairTableHost {
     const uint8_t* base;
-    CUBE_HD uint32_t bias() const { return 0u; }
+    CUBE_HD uint32_t origin() const { return 0u; }
     CUBE_HD CubeVec4 ld(uint32_t addr, int off) const { return cube_ld128(base + addr + off); }
     CUBE_HD void ld64(uint32_t addr, uint32_t& x, uint32_t& y) const
     {
@@ -141,15 +150,15 @@ struct PairTableHost {
 };
 #if defined(__CUDACC__)
 struct PairTableShared {
-    uint32_t bias_;                                     // (base >> 8) * 0x01000100
-    __device__ __forceinline__ uint32_t bias() const { return bias_; }
+    uint32_t origin_;                                   // shared-window address of the table
+    __device__ __forceinline__ uint32_t origin() const { return origin_; }
     __device__ __forceinline__ CubeVec4 ld(uint32_t addr, int off) const
     {
         CubeVec4 v;
         if (off == 0)
             asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
         else
-            asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+128];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+            asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+%5];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr), "n"(kPairSecond));
         return v;
     }
     __device__ __forceinline__ void ld64(uint32_t addr, uint32_t& x, uint32_t& y) const
@@ -189,16 +198,16 @@ struct ColourLutShared {
 };
 #endif
 
-template <int SIZE>
-CUBE_HD uint32_t pair_lanereg(int lane)
+template <int SIZE, class TBL>
+CUBE_HD uint32_t pair_lanereg(int lane, const TBL& tbl)
 {
-    return SIZE == 3 ? (uint32_t)(lane & 7) << 4 : (uint32_t)(lane & 15) << 3;
+    return tbl.origin() + (SIZE == 3 ? (uint32_t)(lane & 7) << 4 : (uint32_t)(lane & 15) << 3);
 }
 
-// 2x2x2: the lane's T1 slot (32 x 4 bytes, bytes 128..255 of the row) relative to its (selectors, T0) slot
+// 2x2x2: the lane's T1 slot (32 x 4 bytes per row of the second array) relative to its (selectors, T0) slot
 CUBE_HD uint32_t pair_roff2(int lane)
 {
-    return 128u + (uint32_t)lane * 4u - ((uint32_t)(lane & 15) << 3);
+    return (uint32_t)kPairSecond + (uint32_t)lane * 4u - ((uint32_t)(lane & 15) << 3);
 }
 
 // fill the shared-memory image from kPairWords{3,2}; thread `t` of `nthreads`
@@ -208,14 +217,15 @@ CUBE_HD void pair_table_fill(uint8_t* s_ptbl, int t, int nthreads)
     for (int i = t; i < CUBE_PAIR_ROWS * 16; i += nthreads) {
         const int row = i >> 4, slot = i & 15;
         if (SIZE == 3) {
-            const uint32_t* v = kPairWords3 + (row * 2 + (slot >> 3)) * 4;
-            uint32_t* d = reinterpret_cast<uint32_t*>(s_ptbl) + i * 4;
+            const uint32_t* v = kPairWords3 + (row * 2 + (slot >> 3)) * 4;       // slots 0..7: P, 8..15: Q
+            uint32_t* d = reinterpret_cast<uint32_t*>(s_ptbl + (slot >> 3) * kPairSecond + row * 128 + (slot & 7) * 16);
             d[0] = v[0]; d[1] = v[1]; d[2] = v[2]; d[3] = v[3];
         } else {
             const uint32_t* v = kPairWords2 + row * 4;
-            uint32_t* d = reinterpret_cast<uint32_t*>(s_ptbl + row * 256);
+            uint32_t* d = reinterpret_cast<uint32_t*>(s_ptbl + row * 128);
+            uint32_t* d1 = reinterpret_cast<uint32_t*>(s_ptbl + kPairSecond + row * 128);
             d[2 * slot] = v[0]; d[2 * slot + 1] = v[1];
-            d[32 + 2 * slot] = v[2]; d[32 + 2 * slot + 1] = v[2];
+            d1[2 * slot] = v[2]; d1[2 * slot + 1] = v[2];
         }
     }
 }
@@ -229,7 +239,7 @@ CUBE_HD void pair_apply(CubieState& s, const TBL& tbl, uint32_t addr, uint32_t r
         const uint32_t n0 = cube_prmt(s.c0, s.c1, P.x) + P.y;
         const uint32_t n1 = cube_prmt(s.c0, s.c1, cube_hi16(P.x)) + P.z;
         s.c0 = n0; s.c1 = n1;
-        const CubeVec4 Q = tbl.ld(addr, 128);
+        const CubeVec4 Q = tbl.ld(addr, kPairSecond);
         const uint32_t t0 = cube_prmt(s.e1, s.e2, Q.x);
         const uint32_t t1 = cube_prmt(s.e0, s.e2, Q.y);
         const uint32_t t2 = cube_prmt(s.e0, s.e1, Q.z);
@@ -264,16 +274,16 @@ CUBE_HD constexpr int pair_static_shift(int k)
                      : (DEPTH % 4 == 0 ? 0 : -1);
 }
 
-// pair rows (bytes 1 and 3) of the next four moves: (move word) * 269 + bias.  With a static shift
+// pair rows (bytes 1 and 3) of the next four moves: (move word) * 269.  With a static shift
 // the funnel shift (ALU pipe) is folded into multiply-adds (FMA pipe):
 //   shift 0: lo * 269;   shift 16: (lo >> 16) * 269 + hi * (269 << 16)   (mod 2^32, like the product)
 template <int SSH>
-CUBE_HD uint32_t pair_rows_word(uint32_t lo, uint32_t hi, uint32_t sh, uint32_t bias)
+CUBE_HD uint32_t pair_rows_word(uint32_t lo, uint32_t hi, uint32_t sh)
 {
     constexpr uint32_t K = (uint32_t)(CUBE_PAIR_BASE + 256);
-    if (SSH == 0) return lo * K + bias;
-    if (SSH == 16) return hi * (K << 16) + (cube_hi16(lo) * K + bias);
-    return cube_funnel_r(lo, hi, sh) * K + bias;
+    if (SSH == 0) return lo * K;
+    if (SSH == 16) return hi * (K << 16) + cube_hi16(lo) * K;
+    return cube_funnel_r(lo, hi, sh) * K;
 }
 
 template <int SIZE, int DEPTH, int NS, class TBL>
@@ -284,7 +294,6 @@ CUBE_HD void scramble_pairs_run(CubieState (&st)[NS], const int (&rows)[NS], int
     const int depth = DEPTH > 0 ? DEPTH : depth_rt;
     const uint32_t* mw = reinterpret_cast<const uint32_t*>(s_moves);
     const int nfull = depth >> 2, tail = depth & 3;
-    const uint32_t bias = tbl.bias();
     uint32_t wi[NS], sh[NS], lo[NS];
 #pragma unroll
     for (int k = 0; k < NS; ++k) {
@@ -303,7 +312,7 @@ CUBE_HD void scramble_pairs_run(CubieState (&st)[NS], const int (&rows)[NS], int
 #pragma unroll
                 for (int h = 0; h < NS; h += 2) {
                     const uint32_t hi = (s0 == 0) ? 0u : mw[wi[h] + j + 1];
-                    y[h] = pair_rows_word<s0>(lo[h], hi, sh[h], bias);              // bytes 1, 3 = pair rows
+                    y[h] = pair_rows_word<s0>(lo[h], hi, sh[h]);              // bytes 1, 3 = pair rows
                     lo[h] = (s0 == 0) ? mw[wi[h] + j + 1] : hi;
                 }
             }
@@ -312,7 +321,7 @@ CUBE_HD void scramble_pairs_run(CubieState (&st)[NS], const int (&rows)[NS], int
 #pragma unroll
                 for (int h = 1; h < NS; h += 2) {
                     const uint32_t hi = (s1 == 0) ? 0u : mw[wi[h] + j + 1];
-                    y[h] = pair_rows_word<s1>(lo[h], hi, sh[h], bias);
+                    y[h] = pair_rows_word<s1>(lo[h], hi, sh[h]);
                     lo[h] = (s1 == 0) ? mw[wi[h] + j + 1] : hi;
                 }
             }
@@ -321,14 +330,14 @@ CUBE_HD void scramble_pairs_run(CubieState (&st)[NS], const int (&rows)[NS], int
 #pragma unroll
             for (int k = 0; k < NS; ++k) {
                 const uint32_t hi = (s == 0) ? 0u : mw[wi[k] + j + 1];
-                y[k] = pair_rows_word<s>(lo[k], hi, sh[k], bias);
+                y[k] = pair_rows_word<s>(lo[k], hi, sh[k]);
                 lo[k] = (s == 0) ? mw[wi[k] + j + 1] : hi;
             }
         }
 #pragma unroll
-        for (int k = 0; k < NS; ++k) pair_apply<SIZE>(st[k], tbl, cube_prmt(y[k], lanereg, 0x5514u), roff);
+        for (int k = 0; k < NS; ++k) pair_apply<SIZE>(st[k], tbl, pair_addr<0>(y[k], lanereg), roff);
 #pragma unroll
-        for (int k = 0; k < NS; ++k) pair_apply<SIZE>(st[k], tbl, cube_prmt(y[k], lanereg, 0x5534u), roff);
+        for (int k = 0; k < NS; ++k) pair_apply<SIZE>(st[k], tbl, pair_addr<1>(y[k], lanereg), roff);
     };
     auto fold = [&]() {
 #pragma unroll
@@ -359,13 +368,13 @@ CUBE_HD void scramble_pairs_run(CubieState (&st)[NS], const int (&rows)[NS], int
 #pragma unroll
         for (int k = 0; k < NS; ++k) {
             const uint32_t w = (cube_funnel_r(lo[k], mw[wi[k] + nfull + 1], sh[k]) & keep) | (0x0c0c0c0cu & ~keep);
-            y[k] = w * (uint32_t)(CUBE_PAIR_BASE + 256) + bias;
+            y[k] = w * (uint32_t)(CUBE_PAIR_BASE + 256);
         }
 #pragma unroll
-        for (int k = 0; k < NS; ++k) pair_apply<SIZE>(st[k], tbl, cube_prmt(y[k], lanereg, 0x5514u), roff);
+        for (int k = 0; k < NS; ++k) pair_apply<SIZE>(st[k], tbl, pair_addr<0>(y[k], lanereg), roff);
         if (tail == 3) {
 #pragma unroll
-            for (int k = 0; k < NS; ++k) pair_apply<SIZE>(st[k], tbl, cube_prmt(y[k], lanereg, 0x5534u), roff);
+            for (int k = 0; k < NS; ++k) pair_apply<SIZE>(st[k], tbl, pair_addr<1>(y[k], lanereg), roff);
         }
     }
 }
@@ -381,7 +390,6 @@ template <int SIZE, int NS, class TBL>
 CUBE_HD void scramble_pairs_run_units(CubieState (&st)[NS], const uint32_t (&base)[NS], const uint32_t (&shift)[NS], int len,
                                       const uint8_t* s_moves, const TBL& tbl, uint32_t lanereg, uint32_t roff)
 {
-    const uint32_t bias = tbl.bias();
     constexpr uint32_t K = (uint32_t)(CUBE_PAIR_BASE + 256);
     auto fold = [&]() {
 #pragma unroll
@@ -393,12 +401,12 @@ CUBE_HD void scramble_pairs_run_units(CubieState (&st)[NS], const uint32_t (&bas
     auto word = [&](const uint32_t (&w)[NS], bool second) {
         uint32_t y[NS];
 #pragma unroll
-        for (int k = 0; k < NS; ++k) y[k] = w[k] * K + bias;
+        for (int k = 0; k < NS; ++k) y[k] = w[k] * K;
 #pragma unroll
-        for (int k = 0; k < NS; ++k) pair_apply<SIZE>(st[k], tbl, cube_prmt(y[k], lanereg, 0x5514u), roff);
+        for (int k = 0; k < NS; ++k) pair_apply<SIZE>(st[k], tbl, pair_addr<0>(y[k], lanereg), roff);
         if (second) {
 #pragma unroll
-            for (int k = 0; k < NS; ++k) pair_apply<SIZE>(st[k], tbl, cube_prmt(y[k], lanereg, 0x5534u), roff);
+            for (int k = 0; k < NS; ++k) pair_apply<SIZE>(st[k], tbl, pair_addr<1>(y[k], lanereg), roff);
         }
     };
     // the 16 move bytes that start `shift` bytes into the unit pair (a, b), as four words
@@ -472,8 +480,8 @@ CUBE_HD void scramble_pairs_last(CubieState& st, uint32_t action, const TBL& tbl
 {
     st.c0 = cubie_fold_twist(st.c0);
     st.c1 = cubie_fold_twist(st.c1);
-    const uint32_t y = (action | 0x0c0c0c00u) * (uint32_t)(CUBE_PAIR_BASE + 256) + tbl.bias();
-    pair_apply<SIZE>(st, tbl, cube_prmt(y, lanereg, 0x5514u), roff);
+    const uint32_t y = (action | 0x0c0c0c00u) * (uint32_t)(CUBE_PAIR_BASE + 256);
+    pair_apply<SIZE>(st, tbl, pair_addr<0>(y, lanereg), roff);
 }
 
 // Swizzled move tile.  In the flat tile image a lane's move words are `rows * depth` bytes apart: when
@@ -492,17 +500,16 @@ template <int SIZE, int NS, class TBL>
 CUBE_HD void scramble_pairs_run_swizzled(CubieState (&st)[NS], const uint8_t* tile, int lane, int depth, const TBL& tbl,
                                          uint32_t lanereg, uint32_t roff)
 {
-    const uint32_t bias = tbl.bias();
     constexpr uint32_t K = (uint32_t)(CUBE_PAIR_BASE + 256);
     static_assert(SIZE == 2 || NS == 2, "3x3x3: two rows per lane");
     auto word = [&](const uint32_t (&w)[NS]) {
         uint32_t y[NS];
 #pragma unroll
-        for (int k = 0; k < NS; ++k) y[k] = w[k] * K + bias;
+        for (int k = 0; k < NS; ++k) y[k] = w[k] * K;
 #pragma unroll
-        for (int k = 0; k < NS; ++k) pair_apply<SIZE>(st[k], tbl, cube_prmt(y[k], lanereg, 0x5514u), roff);
+        for (int k = 0; k < NS; ++k) pair_apply<SIZE>(st[k], tbl, pair_addr<0>(y[k], lanereg), roff);
 #pragma unroll
-        for (int k = 0; k < NS; ++k) pair_apply<SIZE>(st[k], tbl, cube_prmt(y[k], lanereg, 0x5534u), roff);
+        for (int k = 0; k < NS; ++k) pair_apply<SIZE>(st[k], tbl, pair_addr<1>(y[k], lanereg), roff);
     };
     auto fold = [&]() {
 #pragma unroll

@@ -196,7 +196,7 @@ struct PairSmem {
         return moves_at(swz) + 2 * move_stride(depth, swz);
     }
     // never below 65 792 + 256 bytes: a garbage move byte (> 12) makes a garbage pair row (<= 255) whose
-    // two vectors must still be inside the CTA's allocation (255 * 256 + 240 + 128 + 16)
+    // two vectors must still be inside the CTA's allocation (169 * 128 + 255 * 128 + 128 = 54 400 would do)
     __host__ __device__ static constexpr int bytes(int depth, int warps, bool priv = false)
     {
         return kPerWarp + warps * per_warp(depth, priv) < 66048 ? 66048 : kPerWarp + warps * per_warp(depth, priv);
@@ -219,11 +219,11 @@ scramble_pairs_kernel(const uint8_t* __restrict__ moves, int n_tiles, int depth_
     constexpr bool kPriv = DEPTH < 0;
     constexpr uint32_t kAlign = kPriv ? 1024u : 256u;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // everything is laid out from a 256-byte boundary of the shared window (see PairTableShared)
+    // everything is laid out from a 256-byte boundary of the shared window (table rows on 128-byte boundaries)
     const uint32_t window = bulk::smem_addr(smem_raw);
     uint8_t* smem = smem_raw + ((kAlign - (window & (kAlign - 1u))) & (kAlign - 1u));
     uint8_t* s_ptbl = smem + L::kTable;
-    const PairTableShared tbl{(bulk::smem_addr(s_ptbl) >> 8) * 0x01000100u};
+    const PairTableShared tbl{bulk::smem_addr(s_ptbl)};
     uint32_t* s_clut = reinterpret_cast<uint32_t*>(smem + L::kCornerLut);
     uint32_t* s_elut = reinterpret_cast<uint32_t*>(smem + L::kEdgeLut);
     uint8_t* mine = smem + L::kPerWarp + warp * L::per_warp(depth, kPriv);
@@ -261,7 +261,7 @@ scramble_pairs_kernel(const uint8_t* __restrict__ moves, int n_tiles, int depth_
     int rows[NS];
 #pragma unroll
     for (int k = 0; k < NS; ++k) rows[k] = (SIZE == 3) ? 64 * (k >> 1) + 2 * lane + (k & 1) : lane + 32 * k;
-    const uint32_t lanereg = pair_lanereg<SIZE>(lane), roff = pair_roff2(lane);
+    const uint32_t lanereg = pair_lanereg<SIZE>(lane, tbl), roff = pair_roff2(lane);
     const ColourLutShared lut{bulk::smem_addr(s_clut), bulk::smem_addr(s_elut)};
     unsigned n_solved = 0;
 
@@ -377,7 +377,7 @@ scramble_sliced_kernel(const uint8_t* __restrict__ moves, int n_tiles, int depth
     const uint32_t window = bulk::smem_addr(smem_raw);
     uint8_t* smem = smem_raw + ((256u - (window & 255u)) & 255u);     // the pair table on a 256-byte boundary
     uint8_t* s_ptbl = smem + P::kTable;
-    const PairTableShared tbl{(bulk::smem_addr(s_ptbl) >> 8) * 0x01000100u};
+    const PairTableShared tbl{bulk::smem_addr(s_ptbl)};
     uint32_t* s_clut = reinterpret_cast<uint32_t*>(smem + P::kCornerLut);
     uint32_t* s_elut = reinterpret_cast<uint32_t*>(smem + P::kEdgeLut);
     const int kSliceStride = slice_stride(kSlice);
@@ -409,7 +409,7 @@ scramble_sliced_kernel(const uint8_t* __restrict__ moves, int n_tiles, int depth
             bulk::load(s_moves + (b * 64 + rows[k]) * kSliceStride, moves + (g & ~15LL), bytes[k], &s_bar[b]);
         }
     };
-    const uint32_t lanereg = pair_lanereg<SIZE>(lane), roff = pair_roff2(lane);
+    const uint32_t lanereg = pair_lanereg<SIZE>(lane, tbl), roff = pair_roff2(lane);
     const ColourLutShared lut{bulk::smem_addr(s_clut), bulk::smem_addr(s_elut)};
     unsigned n_solved = 0;
     const int stride = (int)gridDim.x * warps;

@@ -69,14 +69,14 @@ void scramble_sliced_t(const uint8_t* moves, long long n, int depth, uint8_t* ou
                 CubieState two[2] = {st[rows[0]], st[rows[1]]};
                 const uint32_t base[2] = {(uint32_t)(rows[0] * kStride), (uint32_t)(rows[1] * kStride)};
                 const uint32_t shift[2] = {(uint32_t)(((long long)rows[0] * depth) & 15), (uint32_t)(((long long)rows[1] * depth) & 15)};
-                scramble_pairs_run_units<SIZE, 2>(two, base, shift, len, s_moves, s_ptbl, pair_lanereg<SIZE>(lane), pair_roff2(lane));
+                scramble_pairs_run_units<SIZE, 2>(two, base, shift, len, s_moves, s_ptbl, pair_lanereg<SIZE>(lane, s_ptbl), pair_roff2(lane));
                 st[rows[0]] = two[0]; st[rows[1]] = two[1];
             }
         }
         for (int lane = 0; lane < 32; ++lane)
             for (int k = 0; k < 2; ++k) {
                 const int row = lane + 32 * k;
-                if (last) scramble_pairs_last<SIZE>(st[row], last[tile * 64 + row], s_ptbl, pair_lanereg<SIZE>(lane), pair_roff2(lane));
+                if (last) scramble_pairs_last<SIZE>(st[row], last[tile * 64 + row], s_ptbl, pair_lanereg<SIZE>(lane, s_ptbl), pair_roff2(lane));
                 solved[tile * 64 + row] = scramble_pairs_finish<SIZE>(st[row], row, ColourLutHost{clut, kEdgeColour3}, s_out.data());
             }
         std::memcpy(out + tile * 64 * G::S, s_out.data(), (size_t)64 * G::S);
@@ -135,8 +135,8 @@ void scramble_pairs_t(const uint8_t* moves, long long n, int depth, uint8_t* out
                 rows[k] = (SIZE == 3) ? 64 * (k >> 1) + 2 * lane + (k & 1) : lane + 32 * k;
                 cubie_init(st[k]);
             }
-            const uint32_t lr = pair_lanereg<SIZE>(lane);
             const PairTableHost s_ptbl{s_ptbl_mem};
+            const uint32_t lr = pair_lanereg<SIZE>(lane, s_ptbl);
             if constexpr (SIZE == 2 || NS == 2) {
                 if (priv) scramble_pairs_run_swizzled<SIZE, NS>(st, s_priv.data(), lane, depth, s_ptbl, lr, pair_roff2(lane));
             }

@@ -1,15 +1,20 @@
 """A/B timing of the fused scramble (config 3, 8 Mi x depth 30) in back-to-back launches, as bench.py's timed loop
-runs it:  CUBE_EARLY_WAIT=0|1 python tools/ab_k1p.py"""
+runs it.  AB_LIB=<path to another build of libcube_b200.so> times that build instead of the tree's (same box, same
+process layout): e.g. a build of HEAD exported with `git archive` next to the working tree's."""
 import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
+from rubiks_cube_solver_b200 import _lib
+
+if os.environ.get("AB_LIB"):
+    _lib.LIB_PATH = os.environ["AB_LIB"]
 from rubiks_cube_solver_b200 import ops
 
 dev = torch.device("cuda", 0)
-n, d = 8 * 2 ** 20, 30
+n, d = 8 * 2 ** 20, int(os.environ.get("AB_DEPTH", "30"))
 moves = torch.randint(0, 12, (n, d), dtype=torch.uint8, device=dev, generator=torch.Generator(device=dev).manual_seed(1234))
 st = torch.empty((n, 54), dtype=torch.uint8, device=dev)
 so = torch.empty(n, dtype=torch.uint8, device=dev)
@@ -27,5 +32,6 @@ for rep in range(5):
     torch.cuda.synchronize()
     best.append(e0.elapsed_time(e1) / 200)
 ms = sorted(best)[len(best) // 2]
-print("CUBE_EARLY_WAIT=%s  median %.5f ms  min %.5f  %.4e tr/s  frac %.4f" % (
-    os.environ.get("CUBE_EARLY_WAIT", "1"), ms, min(best), n * d / ms * 1e3, n * 89 / ms / 1e6 / 6553.3))
+print("lib=%s NBUF=%s depth %d  median %.5f ms  min %.5f  %.4e tr/s  frac %.4f" % (
+    os.environ.get("AB_LIB", "tree"), os.environ.get("CUBE_PAIR_NBUF", "-"), d, ms, min(best), n * d / ms * 1e3,
+    n * (d + 59) / ms / 1e6 / 6553.3))
