@@ -49,6 +49,13 @@ __device__ __forceinline__ void load(void* dst_smem, const void* src_gmem, uint3
                  : "memory");
 }
 
+// hint: bring [src, src + bytes) into L2.  No architectural effect, so it may be issued BEFORE a dependency wait
+// (griddepcontrol.wait): the data is only read after the wait, from wherever its latest copy is
+__device__ __forceinline__ void prefetch_l2(const void* src_gmem, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
+}
+
 // global -> shared through a 2-D tensor map (box at element coordinates {c0, c1}; the map fixes the box,
 // the swizzle and the byte count), completion counted on `bar`
 __device__ __forceinline__ void load_tile_2d(void* dst_smem, const void* tensor_map, int c0, int c1, uint64_t* bar)

@@ -16,7 +16,7 @@
 
 namespace sched {
 
-constexpr int kClaimChunk = 2;
+constexpr int kClaimChunk = 2;         // tiles per claim (the default; a kernel with long tiles claims one at a time)
 constexpr int kRanges = 8;
 constexpr int kTailDiv = 4;            // the last 1/4 of the tiles is claimed dynamically (measured: 8 -> +10 %, 4 -> +13 % on K2p)
 // Slots are handed out round-robin from a ring: two launches share a slot only if kSlots launches of persistent
@@ -39,8 +39,9 @@ struct WarpTiles {
     Slot* slot;
     int n_tiles, total_warps, tail0;   // tiles [tail0, n_tiles) are dynamic
     int next_static;
-    int r, visited;                    // tail sub-range being worked on, sub-ranges given up so far
+    int r, visited;                    // tail sub-range being worked on; visited == kRanges: nothing left anywhere
     int cur, end;                      // the claimed chunk in hand
+    int chunk;                         // tiles per claim
     unsigned pending;                  // lane 0: raw result of the claim issued ahead in sub-range r
 
     __device__ __forceinline__ int lo(int range) const
@@ -49,12 +50,13 @@ struct WarpTiles {
     }
     __device__ __forceinline__ void claim_ahead(int lane)
     {
-        if (lane == 0) pending = atomicAdd(&slot->next[r][0], (unsigned)kClaimChunk);
+        if (lane == 0) pending = atomicAdd(&slot->next[r][0], (unsigned)chunk);
     }
 
-    __device__ __forceinline__ void init(Slot* s, int n, int warps_per_cta, int warp, int lane, int tail_div)
+    __device__ __forceinline__ void init(Slot* s, int n, int warps_per_cta, int warp, int lane, int tail_div,
+                                         int claim_chunk = kClaimChunk)
     {
-        slot = s; n_tiles = n; total_warps = (int)gridDim.x * warps_per_cta;
+        slot = s; n_tiles = n; total_warps = (int)gridDim.x * warps_per_cta; chunk = claim_chunk;
         const int gid = (int)blockIdx.x * warps_per_cta + warp;
         tail0 = tail_div > 0 ? n - n / tail_div : n;
         next_static = gid;
@@ -78,12 +80,20 @@ struct WarpTiles {
             const long long base = (long long)lo(r) + got;
             if (base < hi) {
                 cur = (int)base;
-                end = cur + kClaimChunk < hi ? cur + kClaimChunk : hi;
-            } else {                                                  // sub-range used up: move on (steal)
-                r = (r + 1) % kRanges;
-                ++visited;
+                end = cur + chunk < hi ? cur + chunk : hi;
+            } else {
+                // sub-range used up: look at ALL counters at once (lanes 0..7, one round trip) and move to the
+                // next one that still has tiles; none left = done.  (Probing them one claim after the other cost
+                // up to kRanges atomic round trips per warp at the end of a kernel: ~8 us during which the CTA
+                // holds its SM and the next launch of the stream waits for the grid to complete.)
+                bool left = false;
+                if (lane < kRanges) left = lo(lane) + (long long)__ldcg(&slot->next[lane][0]) < lo(lane + 1);
+                const unsigned open = __ballot_sync(0xffffffffu, left) & ((1u << kRanges) - 1u);
+                if (open == 0) { visited = kRanges; return kExhausted; }
+                const unsigned rot = (open >> (r + 1)) | (open << (kRanges - r - 1));     // bit 0 = range r + 1
+                r = (r + 1 + (__ffs(rot & ((1u << kRanges) - 1u)) - 1)) % kRanges;
             }
-            if (visited < kRanges) claim_ahead(lane);
+            claim_ahead(lane);
         }
         return cur++;
     }
