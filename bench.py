@@ -785,6 +785,21 @@ def run_b200_arm(args):
     cbuf = torch.zeros((n_rows, 4), dtype=torch.int64, device=dev)
     pending = []
     state = {"i": 0, "reduced": 0}
+    # the closing all-reduce: one small kernel per rank over NVLink peer memory (csrc/peer.cu) instead of an
+    # ncclAllReduce of the same few hundred bytes -- the collective's cost is latency only
+    peer, collective = None, "none" if world == 1 else "nccl"
+    if world > 1 and args.collective == "peer" and not args.reduce_every_step:
+        try:
+            peer = cdist.PeerCounters(capacity=4 * n_rows)
+            collective = "peer"
+        except Exception as e:                            # no symmetric memory on this box: NCCL, and say so
+            collective = "nccl (peer exchange unavailable: %s)" % (str(e).splitlines()[0][:120] if str(e) else type(e).__name__)
+        flag = torch.tensor([1 if peer is not None else 0], dtype=torch.int64, device=dev)
+        torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN)
+        if int(flag[0]) == 0:                             # all ranks or none
+            peer = None
+            if collective == "peer":
+                collective = "nccl (peer exchange unavailable on another rank)"
 
     def step():
         k = state["i"]
@@ -801,7 +816,10 @@ def run_b200_arm(args):
                 h.wait()
             del pending[:]
         elif state["i"] > state["reduced"]:
-            cdist.reduce_counters(cbuf[state["reduced"]:state["i"]])
+            if peer is not None:
+                peer.allreduce_(cbuf[state["reduced"]:state["i"]])
+            else:
+                cdist.reduce_counters(cbuf[state["reduced"]:state["i"]])
             state["reduced"] = state["i"]
         return cbuf[state["i"] - 1]
 
@@ -905,7 +923,7 @@ def run_b200_arm(args):
                     "collective": ("int64[4] all-reduce(SUM) per step, asynchronous" if args.reduce_every_step else
                                    "one all-reduce(SUM) of the per-step int64[4] solved/produced counter rows at the end of "
                                    "the timed region; a device-side all-reduce in front of the start event aligns the ranks"),
-                    "timed_region_by_rank": spread, "host_numa_binding_rank0": numa},
+                    "timed_region_by_rank": spread, "closing_collective": collective, "host_numa_binding_rank0": numa},
         "solved_total": solved_total, "reward_total": 2 * solved_total - produced_total, "parity": parity,
         "e2e": e2e, "roofline": roofline, "gpu_launches": args.steps, "clocks": clocks.summary(),
     }
@@ -957,6 +975,9 @@ def main():
     ap.add_argument("--cpu-cubes-per-proc", type=int, default=15000)
     ap.add_argument("--ref-seconds", type=float, default=60.0)
     ap.add_argument("--reduce-every-step", action="store_true")
+    ap.add_argument("--collective", choices=("peer", "nccl"), default="peer",
+                    help="N > 1: the counters' closing all-reduce as the library's one-kernel exchange over NVLink peer "
+                         "memory (cube_peer_allreduce_i64; falls back to nccl when symmetric memory is unavailable) or as ncclAllReduce")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-other", action="store_true")
     ap.add_argument("--no-numa-bind", action="store_true", help="N > 1: do not pin each rank to its GPU's NUMA node")

@@ -84,6 +84,26 @@ int cube_sm_count(void);
  * efficiency either way), so nothing sets it by default. */
 int cube_set_reserved_sms(int n);
 
+/* Multi-GPU: the path's only collective -- the SUM of the solved / produced counters over the ranks of ONE box
+ * (the reference is single-process, its counterpart is the `solved` tally of a test loop,
+ * test.py:52-60) -- as a one-shot all-reduce over NVLink peer memory: one small kernel per rank stores its values
+ * into its slot of EVERY rank's exchange buffer, raises a flag there and sums all slots of its own buffer once
+ * every flag has arrived (csrc/peer.cu).  Every rank gets the same totals, in place.
+ *   peer_buffers [world]  uint64  host  device addresses, valid on THIS device, of all ranks' exchange
+ *                                        buffers in rank order (own buffer included; e.g. torch symmetric memory's
+ *                                        buffer_ptrs), each cube_peer_buffer_bytes(capacity) bytes, 128-byte
+ *                                        aligned, zero-filled before the first call
+ *   values       [n]      int64   device in/out, n <= capacity (the same n and capacity on every rank)
+ *   epoch                 uint32         call number: 1 for the first call on a set of buffers, then 2, 3, ...
+ *                                        -- the same on every rank (nothing is ever reset; slots alternate with
+ *                                        the epoch's parity, so consecutive calls may overlap across ranks)
+ * All ranks must make the call (it waits for every rank's flag: a missing rank hangs the kernel, like any
+ * collective); world <= CUBE_PEER_MAX_RANKS.  Measured against ncclAllReduce of the same 640 bytes: DESIGN.md 6. */
+#define CUBE_PEER_MAX_RANKS 8
+int64_t cube_peer_buffer_bytes(int capacity);
+int cube_peer_allreduce_i64(int world, int rank, const uint64_t* peer_buffers, int64_t* values, int n, int capacity,
+                            uint32_t epoch, void* stream);
+
 /* Identically seeded scrambles -- the move indices reset(seed, k) draws (cube_env.py:62-65):
  *   moves_out[i, :] = np.random.RandomState(seeds[i]).randint(A, size=depth)      (bit for bit)
  * generated on the device (MT19937 seeded by init_genrand, masked rejection sampling like NumPy's

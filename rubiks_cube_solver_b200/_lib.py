@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_PKG, "libcube_b200.so")
 SYMBOLS = (
     "cube_abi_version", "cube_last_error", "cube_sm_count", "cube_set_reserved_sms", "cube_moves_from_seeds", "cube_scramble", "cube_scramble_step", "cube_scramble_prefixes", "cube_scramble_prefixes_max_depth", "cube_step", "cube_walk",
     "cube_solved", "cube_encode", "cube_expand", "cube_expand_codes", "cube_adi_targets", "cube_mcts_traverse", "cube_mcts_update", "cube_decode", "cube_validate_actions",
+    "cube_peer_buffer_bytes", "cube_peer_allreduce_i64",
     "cube_pipeline_create", "cube_pipeline_destroy", "cube_pipeline_scramble_host", "cube_pipeline_reset_host", "cube_host_alloc", "cube_host_free",
     "cube_env_host_create", "cube_env_host_destroy", "cube_env_host_step", "cube_env_host_scramble", "cube_env_host_encode",
 )
@@ -71,6 +72,9 @@ def load():
     lib.cube_mcts_update.argtypes = [ci, vp, vp, vp, vp, vp, vp, ctypes.c_float, ci, vp, vp, vp, vp, vp]
     lib.cube_decode.argtypes = [ci, vp, ci, ci, i64, vp, vp]
     lib.cube_validate_actions.argtypes = [ci, vp, i64, vp, vp]
+    lib.cube_peer_buffer_bytes.argtypes = [ci]
+    lib.cube_peer_buffer_bytes.restype = i64
+    lib.cube_peer_allreduce_i64.argtypes = [ci, ci, vp, vp, ci, ci, ctypes.c_uint32, vp]
     lib.cube_pipeline_create.argtypes = [ci, ci, i64, ci, ctypes.POINTER(vp)]
     lib.cube_pipeline_destroy.argtypes = [vp]
     lib.cube_pipeline_scramble_host.argtypes = [vp, vp, i64, vp, vp, vp, ctypes.POINTER(i64)]

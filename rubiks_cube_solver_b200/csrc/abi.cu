@@ -259,6 +259,26 @@ int cube_decode(int cube_size, const void* onehot, int dtype, int encoding, int6
     CUBE_DONE("cube_decode", cube::launch_decode2(onehot, dtype, n, states_out, (cudaStream_t)stream));
 }
 
+int64_t cube_peer_buffer_bytes(int capacity)
+{
+    if (capacity < 1) return fail(CUBE_ERR_ARG, "cube_peer_buffer_bytes");
+    return (int64_t)cube::peer_buffer_bytes(capacity);
+}
+
+int cube_peer_allreduce_i64(int world, int rank, const uint64_t* peer_buffers, int64_t* values, int n, int capacity,
+                            uint32_t epoch, void* stream)
+{
+    if (world < 1 || world > CUBE_PEER_MAX_RANKS || rank < 0 || rank >= world || n < 0 || capacity < 1 || n > capacity ||
+        epoch == 0 || !peer_buffers || (n > 0 && !values))
+        return fail(CUBE_ERR_ARG, "cube_peer_allreduce_i64");
+    for (int p = 0; p < world; ++p)
+        if (!peer_buffers[p] || (peer_buffers[p] & 127u)) return fail(CUBE_ERR_ALIGN, "cube_peer_allreduce_i64");
+    if (reinterpret_cast<uintptr_t>(values) & 7u) return fail(CUBE_ERR_ALIGN, "cube_peer_allreduce_i64");
+    if (n == 0) return CUBE_OK;
+    CUBE_DONE("cube_peer_allreduce_i64", cube::launch_peer_allreduce_i64(world, rank, peer_buffers, (long long*)values, n,
+                                                                         capacity, epoch, (cudaStream_t)stream));
+}
+
 int cube_validate_actions(int cube_size, const uint8_t* actions, int64_t count, uint64_t* counters, void* stream)
 {
     CUBE_CHECK_SIZE("cube_validate_actions");

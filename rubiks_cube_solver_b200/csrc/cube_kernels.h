@@ -73,6 +73,11 @@ int launch_decode2(const void* onehot, int dtype, long long n, uint8_t* out, cud
 // 3x3x3 one-hot rows in the EXACT encoding -> sticker rows
 int launch_decode3_exact(const void* onehot, int dtype, long long n, uint8_t* out, cudaStream_t stream);
 
+// one-shot SUM all-reduce of int64 values over peer-mapped exchange buffers (peer.cu)
+size_t peer_buffer_bytes(int cap);
+int launch_peer_allreduce_i64(int world, int rank, const uint64_t* peer_bufs, long long* values, int n, int cap,
+                              unsigned epoch, cudaStream_t stream);
+
 int sm_count();
 // index of the current device for per-device launch state (cudaFuncSetAttribute is per device), 0..63
 int device_slot();

@@ -46,6 +46,62 @@ def reduce_counters_async(counters):
     return None
 
 
+class PeerCounters:
+    """The counters' SUM all-reduce over NVLink peer memory (C ABI cube_peer_allreduce_i64, csrc/peer.cu) for the
+    ranks of one box: every rank's exchange buffer is torch symmetric memory, mapped by all ranks once, here; an
+    all-reduce is then ONE small kernel per rank on the current stream (no NCCL call, no host synchronisation).
+
+        peer = PeerCounters(capacity=256)        # collective: every rank constructs it
+        peer.allreduce_(counters)                # int64 CUDA tensor, <= capacity elements, in place
+
+    Raises RuntimeError when symmetric memory cannot be set up (no process group, no peer access); callers fall
+    back to reduce_counters (NCCL) -- both give the same totals."""
+
+    def __init__(self, capacity=256, group=None):
+        import ctypes
+
+        import torch.distributed._symmetric_memory as symm_mem
+
+        from . import _lib
+
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("PeerCounters needs an initialised process group")
+        group = group if group is not None else dist.group.WORLD
+        self._lib = _lib
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.capacity = int(capacity)
+        nbytes = int(_lib.load().cube_peer_buffer_bytes(self.capacity))
+        if nbytes <= 0:
+            raise RuntimeError("cube_peer_buffer_bytes(%d) failed" % self.capacity)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.buffer = symm_mem.empty(nbytes // 8, dtype=torch.int64, device=dev)
+        self.buffer.zero_()
+        self.handle = symm_mem.rendezvous(self.buffer, group)
+        ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        if len(ptrs) != self.world:
+            raise RuntimeError("symmetric memory returned %d buffer pointers for %d ranks" % (len(ptrs), self.world))
+        off = self.buffer.data_ptr() - ptrs[self.rank]    # the tensor's offset inside the (symmetric) allocation
+        self._ptrs = (ctypes.c_uint64 * self.world)(*[p + off for p in ptrs])
+        self.epoch = 0
+        torch.cuda.synchronize(dev)                       # every buffer is zero ...
+        dist.barrier(group)                               # ... before any rank's first flag can arrive
+
+    def allreduce_(self, values):
+        import ctypes
+
+        if values.dtype != torch.int64 or not values.is_cuda or not values.is_contiguous():
+            raise TypeError("values must be a contiguous int64 CUDA tensor")
+        n = values.numel()
+        if n > self.capacity:
+            raise ValueError("%d values exceed the exchange buffer's capacity %d" % (n, self.capacity))
+        self.epoch += 1
+        lib = self._lib.load()
+        stream = ctypes.c_void_p(torch.cuda.current_stream(values.device).cuda_stream)
+        self._lib.check(lib.cube_peer_allreduce_i64(self.world, self.rank, self._ptrs, ctypes.c_void_p(values.data_ptr()), n,
+                                                    self.capacity, self.epoch, stream), "cube_peer_allreduce_i64")
+        return values
+
+
 def reward_total(counters):
     """Exact sum of the +-1 rewards behind the counters: 2*solved - produced."""
     return 2 * int(counters[0]) - int(counters[1])

@@ -25,7 +25,7 @@ def lib():
 
 def test_header_symbols_exported(lib):
     header = open(os.path.join(ROOT, "include", "cube_b200.h")).read()
-    declared = set(re.findall(r"^(?:int|const char\*)\s+(cube_\w+)\s*\(", header, flags=re.M))
+    declared = set(re.findall(r"^(?:int|int64_t|const char\*)\s+(cube_\w+)\s*\(", header, flags=re.M))
     assert declared == set(_lib.SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), name
@@ -53,6 +53,12 @@ def test_argument_errors_without_cuda(lib):
     assert lib.cube_scramble_prefixes_max_depth(3) == 526 and lib.cube_scramble_prefixes_max_depth(2) == 1159
     assert lib.cube_pipeline_reset_host(None, None, 1, None, None, None, None) == _lib.CUBE_ERR_ARG
     assert lib.cube_host_alloc(0, None) == _lib.CUBE_ERR_ARG and lib.cube_host_free(aligned) == _lib.CUBE_ERR_ARG
+    one = (ctypes.c_uint64 * 1)(1 << 20)
+    assert lib.cube_peer_buffer_bytes(64) == 8 * 32 * 4 + 2 * 8 * 64 * 8 and lib.cube_peer_buffer_bytes(0) == _lib.CUBE_ERR_ARG
+    assert lib.cube_peer_allreduce_i64(9, 0, one, aligned, 1, 64, 1, None) == _lib.CUBE_ERR_ARG       # > CUBE_PEER_MAX_RANKS
+    assert lib.cube_peer_allreduce_i64(1, 0, one, aligned, 65, 64, 1, None) == _lib.CUBE_ERR_ARG
+    assert lib.cube_peer_allreduce_i64(1, 0, one, aligned, 1, 64, 0, None) == _lib.CUBE_ERR_ARG       # epochs start at 1
+    assert lib.cube_peer_allreduce_i64(1, 0, (ctypes.c_uint64 * 1)((1 << 20) + 64), aligned, 1, 64, 1, None) == _lib.CUBE_ERR_ALIGN
     with pytest.raises(NotImplementedError):
         _lib.check(_lib.CUBE_ERR_SIZE, "x")
     with pytest.raises(IndexError):

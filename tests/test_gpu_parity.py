@@ -3,6 +3,7 @@ golden vectors generated from the reference.  Bit-exact everywhere (integer / by
 Run on the B200 box:  python -m pytest tests -m gpu -x -q
 """
 import copy
+import os
 import ctypes
 
 import numpy as np
@@ -740,6 +741,55 @@ def test_new_entry_points_edge_cases():
     assert lib.cube_adi_targets(3, None, None, None, None, None, 0, 7, None, None, None, None) == _lib.CUBE_ERR_ARG
     assert lib.cube_mcts_traverse(3, None, ctypes.c_float(1.0), 150, None) == _lib.CUBE_ERR_ARG
     assert lib.cube_set_reserved_sms(-1) == _lib.CUBE_ERR_ARG and lib.cube_set_reserved_sms(0) == 0
+
+
+def test_peer_allreduce_single_rank_and_argument_checks():
+    """C ABI cube_peer_allreduce_i64 with a world of one (the exchange buffer is plain device memory): the sum of
+    one rank's values is the values, call after call (epochs 1, 2, 3: both slot parities), and the argument checks."""
+    lib = _lib.load()
+    dev = torch.device("cuda", 0)
+    cap = 64
+    nbytes = lib.cube_peer_buffer_bytes(cap)
+    assert nbytes > 0 and nbytes % 128 == 0 and lib.cube_peer_buffer_bytes(0) == _lib.CUBE_ERR_ARG
+    buf = torch.zeros(nbytes // 8, dtype=torch.int64, device=dev)
+    ptrs = (ctypes.c_uint64 * 1)(buf.data_ptr())
+    stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    for epoch in (1, 2, 3):
+        v = torch.arange(-5, cap - 5, dtype=torch.int64, device=dev) * (2 ** 33 + epoch)
+        want = v.clone()
+        assert lib.cube_peer_allreduce_i64(1, 0, ptrs, ctypes.c_void_p(v.data_ptr()), cap, cap, epoch, stream) == 0
+        assert torch.equal(v, want)
+    v = torch.ones(8, dtype=torch.int64, device=dev)
+    p = ctypes.c_void_p(v.data_ptr())
+    E = _lib.CUBE_ERR_ARG
+    assert lib.cube_peer_allreduce_i64(0, 0, ptrs, p, 8, cap, 4, stream) == E          # world
+    assert lib.cube_peer_allreduce_i64(9, 0, ptrs, p, 8, cap, 4, stream) == E
+    assert lib.cube_peer_allreduce_i64(1, 1, ptrs, p, 8, cap, 4, stream) == E          # rank
+    assert lib.cube_peer_allreduce_i64(1, 0, ptrs, p, cap + 1, cap, 4, stream) == E    # n > capacity
+    assert lib.cube_peer_allreduce_i64(1, 0, ptrs, p, 8, cap, 0, stream) == E          # epoch 0
+    assert lib.cube_peer_allreduce_i64(1, 0, None, p, 8, cap, 4, stream) == E
+    odd = (ctypes.c_uint64 * 1)(buf.data_ptr() + 8)
+    assert lib.cube_peer_allreduce_i64(1, 0, odd, p, 8, cap, 4, stream) == _lib.CUBE_ERR_ALIGN
+    assert lib.cube_peer_allreduce_i64(1, 0, ptrs, p, 0, cap, 4, stream) == 0          # nothing to do
+    torch.cuda.synchronize()
+
+
+def test_peer_allreduce_two_ranks():
+    """The peer-memory all-reduce against torch.distributed's on two GPUs (tools/peer_allreduce_check.py under
+    torchrun: 200 calls with rank-dependent delays + three unsynchronised calls in a row)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533",
+                          os.path.join(root, "tools", "peer_allreduce_check.py")],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["world"] == 2 and line["mismatching_calls"] == 0
 
 
 def test_two_devices_in_one_process():
