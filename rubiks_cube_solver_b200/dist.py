@@ -74,8 +74,18 @@ class PeerCounters:
         if nbytes <= 0:
             raise RuntimeError("cube_peer_buffer_bytes(%d) failed" % self.capacity)
         dev = torch.device("cuda", torch.cuda.current_device())
-        self.buffer = symm_mem.empty(nbytes // 8, dtype=torch.int64, device=dev)
-        self.buffer.zero_()
+        # the allocation is local and may fail on one rank only; the rendezvous behind it is a collective, so the
+        # ranks first agree that every one of them got its buffer (all of them raise, or none)
+        err = None
+        try:
+            self.buffer = symm_mem.empty(nbytes // 8, dtype=torch.int64, device=dev)
+            self.buffer.zero_()
+        except Exception as e:                            # noqa: BLE001 - reported below, on every rank
+            err = e
+        ok = torch.tensor([0 if err is not None else 1], dtype=torch.int64, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok[0]) == 0:
+            raise RuntimeError("symmetric memory allocation failed on %s: %s" % ("this rank" if err is not None else "another rank", err))
         self.handle = symm_mem.rendezvous(self.buffer, group)
         ptrs = [int(p) for p in self.handle.buffer_ptrs]
         if len(ptrs) != self.world:
