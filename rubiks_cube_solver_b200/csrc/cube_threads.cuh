@@ -177,12 +177,17 @@ struct PairTableShared {
 // Colour LUT access of the finishing pass.  Host: pointers.  Device: "base + 4 * cubie byte q" is ONE
 // dot-product instruction (weights 4 << 8q, accumulator = the LUT's shared-window address): byte
 // extraction, scaling and address arithmetic on the FMA pipe instead of PRMT + shift on the ALU pipe.
+// Edges have one 32-entry LUT PER SLOT (kEdgeColourSlot3: bytes 2, 3 carry the centre colours of the slot's
+// faces for the row assembly); the slot's LUT is an immediate offset of the load.
 struct ColourLutHost {
     const uint32_t* c;
-    const uint32_t* e;
+    const uint32_t* e;                                  // [12][32]
     // x = four cubie bytes; entry of byte q
     CUBE_HD uint32_t corner(uint32_t x, int q) const { return cube_lut_at(c, cube_dp4a(x, 4u << (8 * q), 0u)); }
-    CUBE_HD uint32_t edge(uint32_t x, int q) const { return cube_lut_at(e, cube_dp4a(x, 4u << (8 * q), 0u)); }
+    template <int SLOT> CUBE_HD uint32_t edge(uint32_t x) const
+    {
+        return cube_lut_at(e + 32 * SLOT, cube_dp4a(x, 4u << (8 * (SLOT & 3)), 0u));
+    }
 };
 #if defined(__CUDACC__)
 struct ColourLutShared {
@@ -194,7 +199,12 @@ struct ColourLutShared {
         return v;
     }
     __device__ __forceinline__ uint32_t corner(uint32_t x, int q) const { return lds32(cube_dp4a(x, 4u << (8 * q), cbase)); }
-    __device__ __forceinline__ uint32_t edge(uint32_t x, int q) const { return lds32(cube_dp4a(x, 4u << (8 * q), ebase)); }
+    template <int SLOT> __device__ __forceinline__ uint32_t edge(uint32_t x) const
+    {
+        uint32_t v;
+        asm("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(cube_dp4a(x, 4u << (8 * (SLOT & 3)), ebase)), "n"(128 * SLOT));
+        return v;
+    }
 };
 #endif
 
@@ -605,12 +615,9 @@ CUBE_HD bool scramble_pairs_finish(CubieState& st, int row, const LUT& lut, uint
     if (SIZE == 3) {
         const uint32_t f0 = cubie_canonical_flip(st.e0), f1 = cubie_canonical_flip(st.e1), f2 = cubie_canonical_flip(st.e2);
         ok = ok && ((f0 == 0x03020100u) & (f1 == 0x07060504u) & (f2 == 0x0b0a0908u));
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            L[8 + q] = lut.edge(f0, q);
-            L[12 + q] = lut.edge(f1, q);
-            L[16 + q] = lut.edge(f2, q);
-        }
+        L[8] = lut.template edge<0>(f0);   L[9] = lut.template edge<1>(f0);   L[10] = lut.template edge<2>(f0);  L[11] = lut.template edge<3>(f0);
+        L[12] = lut.template edge<4>(f1);  L[13] = lut.template edge<5>(f1);  L[14] = lut.template edge<6>(f1);  L[15] = lut.template edge<7>(f1);
+        L[16] = lut.template edge<8>(f2);  L[17] = lut.template edge<9>(f2);  L[18] = lut.template edge<10>(f2); L[19] = lut.template edge<11>(f2);
         uint32_t w[13], h;
         uint8_t* rowp = s_out + 54 * row;
         if (row & 1) {

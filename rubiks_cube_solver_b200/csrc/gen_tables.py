@@ -313,6 +313,14 @@ C_LUT_3 = colour_lut(CORNER_SLOTS_3, 9, 3)
 _E_LUT_32 = colour_lut(EDGE_SLOTS_3, 9, 2)
 E_LUT_3 = [_E_LUT_32[(i & 15) | ((((i >> 4) ^ (i >> 5)) & 1) << 4)] for i in range(64)]
 C_LUT_2 = colour_lut(CORNER_SLOTS_2, 4, 3)
+# K1p's finishing pass reads the edge colours from one LUT PER SLOT (32 canonical entries each: piece | flip << 4).
+# Bytes 0, 1 are the two colours as above; bytes 2, 3 are the CENTRE colours of the faces that the slot's sticker
+# positions 0 and 1 lie on -- constants of the slot.  A centre sticker always shares its output word with an edge
+# sticker of its own face, so the row assembly takes it from that edge's LUT word instead of from an immediate:
+# one source register fewer, i.e. one byte permute fewer, in six words of a row.
+E_LUT_SLOT_3 = [[_E_LUT_32[i] | (st[0] // 9) << 16 | (st[1] // 9) << 24 for i in range(32)] for st in EDGE_SLOTS_3]
+CENTRE_ALTERNATIVES_3 = {f: [(8 + s_, 2 + k) for s_, st in enumerate(EDGE_SLOTS_3) for k in range(2) if st[k] // 9 == f]
+                         for f in range(6)}
 
 
 def sticker_sources(slots_list, n_stickers, centres):
@@ -449,20 +457,30 @@ def _prmt_expr(ops):
             % (lo_pair[0], lo_pair[1], sel(lo_pair, lo), hi_pair[0], hi_pair[1], sel(hi_pair, hi), final)), 3
 
 
-def assemble_row_fn(name, src, first, n_words, half_at):
+def assemble_row_fn(name, src, first, n_words, half_at, centre_alt=None):
     """Straight-line code for one alignment of a 54-byte row in shared memory: w[j] = stickers
-    first+4j .. first+4j+3 and *h = the two stickers half_at, half_at+1 (low 16 bits)."""
-    def op(s_):
-        if src[s_][0] == "const":
-            return ("0x%02xu" % src[s_][1], 0)
-        return ("L[%d]" % src[s_][0], src[s_][1])
+    first+4j .. first+4j+3 and *h = the two stickers half_at, half_at+1 (low 16 bits).
+    centre_alt[f] = [(L index, byte), ...]: LUT words that also carry the centre colour of face f; a centre is
+    taken from one that the word reads anyway, else from an immediate."""
+    def ops_of(positions):
+        regs = {src[s_][0] for s_ in positions if s_ is not None and src[s_][0] != "const"}
+        out = []
+        for s_ in positions:
+            if s_ is None:
+                out.append(None)
+            elif src[s_][0] == "const":
+                alt = [a for a in (centre_alt or {}).get(src[s_][1], []) if a[0] in regs]
+                out.append(("L[%d]" % alt[0][0], alt[0][1]) if alt else ("0x%02xu" % src[s_][1], 0))
+            else:
+                out.append(("L[%d]" % src[s_][0], src[s_][1]))
+        return out
     lines = ["CUBE_HD void %s(const uint32_t* L, uint32_t* w, uint32_t* h)\n{\n" % name]
     total = 0
     for j in range(n_words):
-        e, k = _prmt_expr([op(first + 4 * j + b) for b in range(4)])
+        e, k = _prmt_expr(ops_of([first + 4 * j + b for b in range(4)]))
         total += k
         lines.append("    w[%d] = %s;\n" % (j, e))
-    e, k = _prmt_expr([op(half_at), op(half_at + 1), None, None])
+    e, k = _prmt_expr(ops_of([half_at, half_at + 1, None, None]))
     total += k
     lines.append("    *h = %s;\n}   // %d byte permutes\n\n" % (e, total))
     return "".join(lines)
@@ -544,6 +562,8 @@ def render():
     o.append("// colour LUTs: index = cubie byte (piece | twist << 3 corners; piece | a << 4 | b << 5 edges, flip = a ^ b)\n")
     o.append(_c_array("uint32_t", "kCornerColour3", C_LUT_3))
     o.append(_c_array("uint32_t", "kEdgeColour3", E_LUT_3))
+    o.append("// K1p finishing pass: one 32-entry edge LUT per slot, bytes 2 / 3 = the centre colours of the slot's two faces\n")
+    o.append(_c_array("uint32_t", "kEdgeColourSlot3", [v for lut in E_LUT_SLOT_3 for v in lut]))
     o.append(_c_array("uint32_t", "kCornerColour2", C_LUT_2))
     src3 = sticker_sources([CORNER_SLOTS_3, EDGE_SLOTS_3], 54, {4 + 9 * f: f for f in range(6)})
     src2 = sticker_sources([CORNER_SLOTS_2], 24, {})
@@ -553,8 +573,8 @@ def render():
     o.append(assemble_fn("cube_assemble2", src2, 6))
     o.append("// the same row for the two alignments of a 54-byte row on the word grid (K1p): even rows start on\n"
              "// a word (13 words + trailing half), odd rows two bytes later (leading half + 13 words)\n")
-    o.append(assemble_row_fn("cube_assemble3_even", src3, 0, 13, 52))
-    o.append(assemble_row_fn("cube_assemble3_odd", src3, 2, 13, 0))
+    o.append(assemble_row_fn("cube_assemble3_even", src3, 0, 13, 52, CENTRE_ALTERNATIVES_3))
+    o.append(assemble_row_fn("cube_assemble3_odd", src3, 2, 13, 0, CENTRE_ALTERNATIVES_3))
     o.append("// sticker positions of 2x2x2 slot `pos` (py222 pieceDefs), usable as compile-time constants\n")
     o.append("CUBE_HD constexpr int cube_piece_def2(int pos, int k)\n{\n    constexpr int t[21] = {%s};\n"
              "    return t[pos * 3 + k];\n}\n\n" % ", ".join(str(v) for r in PIECE_DEFS_2 for v in r))

@@ -180,8 +180,8 @@ struct PairSmem {
     static constexpr int kPairTile = 32 * NS;
     static constexpr int kTable = 0;                                  // + up to 255 bytes: 256-byte aligned in the window
     static constexpr int kCornerLut = kPairTableBytes + 256;          // (relative to the aligned table start: + 0)
-    static constexpr int kEdgeLut = kCornerLut + 256;
-    static constexpr int kPerWarp = kEdgeLut + 256;
+    static constexpr int kEdgeLut = kCornerLut + 256;                 // 3x3x3: one 32-entry LUT per edge slot (1 536 bytes)
+    static constexpr int kPerWarp = (kEdgeLut + 1536 + 1023) / 1024 * 1024;      // the swizzled move tiles want 1 KB boundaries
     static constexpr int kOutBytes = kPairTile * G::S;                // 3456 / 3072: multiples of 16
     // flat tile image (+16: the last row's word loads run past it), or the swizzled tile (`swz`: the copy
     // engine's 128-byte swizzle wants 1024-byte aligned buffers)
@@ -248,7 +248,7 @@ scramble_pairs_kernel(const uint8_t* __restrict__ moves, int n_tiles, int depth_
     asm volatile("griddepcontrol.launch_dependents;");
     pair_table_fill<SIZE>(s_ptbl, tid, blockDim.x);
     if (tid < 32) s_clut[tid] = (SIZE == 3) ? kCornerColour3[tid] : kCornerColour2[tid];
-    if (tid >= 64 && tid < 96) s_elut[tid - 64] = (SIZE == 3) ? kEdgeColour3[tid - 64] : 0u;   // canonical flips: 32 entries
+    if (SIZE == 3) for (int i = tid; i < 12 * 32; i += blockDim.x) s_elut[i] = kEdgeColourSlot3[i];   // canonical flips: 32 entries per slot
     if (lane == 0) { bulk::mbar_init(&s_bar[0], 1); bulk::mbar_init(&s_bar[1], 1); }
     // the warp's first two tiles (its static share starts at its global warp index) are hinted into L2 while the
     // previous grid of the stream drains: after the wait 3 552 warps fetch their first tile at once, and a tile
@@ -402,7 +402,7 @@ scramble_sliced_kernel(const uint8_t* __restrict__ moves, int n_tiles, int depth
 
     pair_table_fill<SIZE>(s_ptbl, tid, blockDim.x);
     if (tid < 32) s_clut[tid] = (SIZE == 3) ? kCornerColour3[tid] : kCornerColour2[tid];
-    if (tid >= 64 && tid < 96) s_elut[tid - 64] = (SIZE == 3) ? kEdgeColour3[tid - 64] : 0u;
+    if (SIZE == 3) for (int i = tid; i < 12 * 32; i += blockDim.x) s_elut[i] = kEdgeColourSlot3[i];
     if (lane == 0) { bulk::mbar_init(&s_bar[0], 32); bulk::mbar_init(&s_bar[1], 32); }
     __syncthreads();
 

@@ -77,7 +77,7 @@ void scramble_sliced_t(const uint8_t* moves, long long n, int depth, uint8_t* ou
             for (int k = 0; k < 2; ++k) {
                 const int row = lane + 32 * k;
                 if (last) scramble_pairs_last<SIZE>(st[row], last[tile * 64 + row], s_ptbl, pair_lanereg<SIZE>(lane, s_ptbl), pair_roff2(lane));
-                solved[tile * 64 + row] = scramble_pairs_finish<SIZE>(st[row], row, ColourLutHost{clut, kEdgeColour3}, s_out.data());
+                solved[tile * 64 + row] = scramble_pairs_finish<SIZE>(st[row], row, ColourLutHost{clut, kEdgeColourSlot3}, s_out.data());
             }
         std::memcpy(out + tile * 64 * G::S, s_out.data(), (size_t)64 * G::S);
     }
@@ -148,7 +148,7 @@ void scramble_pairs_t(const uint8_t* moves, long long n, int depth, uint8_t* out
             if (last)
                 for (int k = 0; k < NS; ++k) scramble_pairs_last<SIZE>(st[k], last[base + rows[k]], s_ptbl, lr, pair_roff2(lane));
             for (int k = 0; k < NS; ++k)
-                ok[k] |= (uint32_t)scramble_pairs_finish<SIZE>(st[k], rows[k], ColourLutHost{clut, kEdgeColour3}, s_out.data()) << lane;
+                ok[k] |= (uint32_t)scramble_pairs_finish<SIZE>(st[k], rows[k], ColourLutHost{clut, kEdgeColourSlot3}, s_out.data()) << lane;
         }
         if (SIZE == 3) {
             for (int k = 0; k < T / 4; ++k) {                        // the kernel's verdict exchange
