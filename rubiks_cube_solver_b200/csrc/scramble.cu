@@ -181,7 +181,7 @@ struct PairSmem {
     static constexpr int kTable = 0;                                  // + up to 255 bytes: 256-byte aligned in the window
     static constexpr int kCornerLut = kPairTableBytes + 256;          // (relative to the aligned table start: + 0)
     static constexpr int kEdgeLut = kCornerLut + 256;                 // 3x3x3: one 32-entry LUT per edge slot (1 536 bytes)
-    static constexpr int kPerWarp = (kEdgeLut + 1536 + 1023) / 1024 * 1024;      // the swizzled move tiles want 1 KB boundaries
+    static constexpr int kPerWarp = (kEdgeLut + (SIZE == 3 ? 1536 : 256) + 1023) / 1024 * 1024;   // swizzled move tiles: 1 KB boundaries
     static constexpr int kOutBytes = kPairTile * G::S;                // 3456 / 3072: multiples of 16
     // flat tile image (+16: the last row's word loads run past it), or the swizzled tile (`swz`: the copy
     // engine's 128-byte swizzle wants 1024-byte aligned buffers)
