@@ -203,7 +203,9 @@ struct PairSmem {
     }
 };
 
-template <int SIZE, int DEPTH, int NS>
+// PLAIN: the common call -- solved and reward arrays present, no trailing action -- with the per-tile null
+// checks and the action fetch compiled out (~18 of a tile's ~1 080 instructions)
+template <int SIZE, int DEPTH, int NS, bool PLAIN>
 __global__ void __launch_bounds__(PairCfg<SIZE, NS>::kMaxWarps * 32, 1)
 scramble_pairs_kernel(const uint8_t* __restrict__ moves, int n_tiles, int depth_rt, uint8_t* __restrict__ out,
                       uint8_t* __restrict__ solved, float* __restrict__ reward, unsigned long long* __restrict__ counters,
@@ -278,7 +280,8 @@ scramble_pairs_kernel(const uint8_t* __restrict__ moves, int n_tiles, int depth_
     const uint32_t lanereg = pair_lanereg<SIZE>(lane, tbl), roff = pair_roff2(lane);
     const ColourLutShared lut{bulk::smem_addr(s_clut), bulk::smem_addr(s_elut)};
     unsigned n_solved = 0;
-
+    const bool has_last = !PLAIN && last != nullptr;
+    const bool has_solved = PLAIN || solved != nullptr, has_reward = PLAIN || reward != nullptr;
     for (int it = 0; tile < n_tiles; ++it) {
         const int buf = it & 1;
         const int next = tiles.pop(lane);
@@ -286,7 +289,7 @@ scramble_pairs_kernel(const uint8_t* __restrict__ moves, int n_tiles, int depth_
         // cube_scramble_step: the trailing action of every instance (rows 2l, 2l+1 are neighbours: one 16-bit load;
         // 2x2x2 rows l + 32k: 32 consecutive bytes per load), fetched before the walk so its latency is hidden
         uint32_t last_w[NS];
-        if (last) {
+        if (has_last) {
             if (SIZE == 3) {
 #pragma unroll
                 for (int h = 0; h < NS; h += 2) {
@@ -305,7 +308,7 @@ scramble_pairs_kernel(const uint8_t* __restrict__ moves, int n_tiles, int depth_
         for (int k = 0; k < NS; ++k) cubie_init(st[k]);
         if constexpr (kPriv) scramble_pairs_run_swizzled<SIZE, NS>(st, s_moves + buf * mstride, lane, depth, tbl, lanereg, roff);
         else scramble_pairs_run<SIZE, (DEPTH > 0 ? DEPTH : 0), NS>(st, rows, depth, s_moves + buf * mstride, tbl, lanereg, roff);
-        if (last) {                                                   // cube_scramble_step: one more face turn
+        if (has_last) {                                               // cube_scramble_step: one more face turn
 #pragma unroll
             for (int k = 0; k < NS; ++k) scramble_pairs_last<SIZE>(st[k], last_w[k], tbl, lanereg, roff);
         }
@@ -329,14 +332,14 @@ scramble_pairs_kernel(const uint8_t* __restrict__ moves, int n_tiles, int depth_
 #pragma unroll
             for (int h = 0; h < NS; h += 2) {
                 const long long r0 = (long long)tile * kPairTile + 32 * h + 2 * lane;
-                if (solved) *reinterpret_cast<uint16_t*>(solved + r0) = (uint16_t)((ok[h] ? 1u : 0u) | (ok[h + 1] ? 0x100u : 0u));
-                if (reward) *reinterpret_cast<float2*>(reward + r0) = make_float2(ok[h] ? 1.0f : -1.0f, ok[h + 1] ? 1.0f : -1.0f);
+                if (has_solved) *reinterpret_cast<uint16_t*>(solved + r0) = (uint16_t)((ok[h] ? 1u : 0u) | (ok[h + 1] ? 0x100u : 0u));
+                if (has_reward) *reinterpret_cast<float2*>(reward + r0) = make_float2(ok[h] ? 1.0f : -1.0f, ok[h + 1] ? 1.0f : -1.0f);
             }
         } else {                                                      // rows l + 32k: 32 in a row per store
 #pragma unroll
             for (int k = 0; k < NS; ++k) {
-                if (solved) solved[(long long)tile * kPairTile + 32 * k + lane] = ok[k] ? 1 : 0;
-                if (reward) reward[(long long)tile * kPairTile + 32 * k + lane] = ok[k] ? 1.0f : -1.0f;
+                if (has_solved) solved[(long long)tile * kPairTile + 32 * k + lane] = ok[k] ? 1 : 0;
+                if (has_reward) reward[(long long)tile * kPairTile + 32 * k + lane] = ok[k] ? 1.0f : -1.0f;
             }
         }
         tile = next;
@@ -661,11 +664,15 @@ long long launch_pairs(const uint8_t* moves, long long n, int depth, uint8_t* ou
     if (warps < min_warps) return 0;
     const int smem = L::bytes(depth, warps, priv) + slack;
     // straight-line specialisations: the reference's default depth (config.yaml:7) and BASELINE config 2's
-    auto kern = depth == 30 ? scramble_pairs_kernel<SIZE, 30, NS>
-              : depth == 20 ? scramble_pairs_kernel<SIZE, 20, NS>
-              : priv ? scramble_pairs_kernel<SIZE, (kCanSwizzle ? -1 : 0), NS> : scramble_pairs_kernel<SIZE, 0, NS>;
-    static std::atomic<int> configured_smem[64][4];       // per device and kernel, 0 = never configured
-    std::atomic<int>& cfg = configured_smem[cube::device_slot()][depth == 30 ? 1 : depth == 20 ? 2 : priv ? 3 : 0];
+    const bool plain = solved && reward && !last;
+    auto kern = plain ? (depth == 30 ? scramble_pairs_kernel<SIZE, 30, NS, true>
+                         : depth == 20 ? scramble_pairs_kernel<SIZE, 20, NS, true>
+                         : priv ? scramble_pairs_kernel<SIZE, (kCanSwizzle ? -1 : 0), NS, true> : scramble_pairs_kernel<SIZE, 0, NS, true>)
+                      : (depth == 30 ? scramble_pairs_kernel<SIZE, 30, NS, false>
+                         : depth == 20 ? scramble_pairs_kernel<SIZE, 20, NS, false>
+                         : priv ? scramble_pairs_kernel<SIZE, (kCanSwizzle ? -1 : 0), NS, false> : scramble_pairs_kernel<SIZE, 0, NS, false>);
+    static std::atomic<int> configured_smem[64][8];       // per device and kernel, 0 = never configured
+    std::atomic<int>& cfg = configured_smem[cube::device_slot()][(depth == 30 ? 1 : depth == 20 ? 2 : priv ? 3 : 0) + (plain ? 4 : 0)];
     if (smem > cfg.load(std::memory_order_relaxed)) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return -(long long)e;
