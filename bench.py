@@ -901,7 +901,7 @@ def run_b200_arm(args):
                 traffic_note = "profiles/scramble3_dram_bytes_per_launch.json is from other sources (stale): not quoted"
         except Exception:                                   # noqa: BLE001
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "scramble_pairs_kernel<3,30,2>", "achieved": alg_bytes / kern_s / 1e9,
+    roofline = {"bound": "hbm", "kernel": "scramble_pairs_kernel<3,30,2,plain>", "achieved": alg_bytes / kern_s / 1e9,
                 "peak": peak_gbs, "unit": "GB/s", "frac": alg_bytes / kern_s / 1e9 / peak_gbs, "traffic": traffic,
                 "traffic_source": traffic_note,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,

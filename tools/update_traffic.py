@@ -19,14 +19,14 @@ def main():
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, data = rows[0], rows[1], rows[2:]
     col = {h: i for i, h in enumerate(hdr)}
-    row = [r for r in data if "scramble_pairs_kernel<3, 30, 2>" in r[col["Kernel Name"]]][-1]
+    row = [r for r in data if "scramble_pairs_kernel<3, 30, 2, 1>" in r[col["Kernel Name"]]][-1]
 
     def nbytes(key):
         v, u = float(row[col[key]]), units[col[key]].lower()
         return int(round(v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}[u]))
 
     rd, wr = nbytes("dram__bytes_read.sum"), nbytes("dram__bytes_write.sum")
-    rec = {"kernel": "scramble_pairs_kernel<3,30,2>", "instances_per_launch": 8 * 2 ** 20, "depth": 30,
+    rec = {"kernel": "scramble_pairs_kernel<3,30,2,plain>", "instances_per_launch": 8 * 2 ** 20, "depth": 30,
            "dram_bytes_read": rd, "dram_bytes_write": wr, "dram_bytes_per_launch": rd + wr,
            "algorithmic_bytes_per_launch": 8 * 2 ** 20 * 89,
            "from": "ncu --set full --clock-control none on `python tools/run_kernels.py scramble3 --iters 3` (%s)" % os.path.basename(rep),
