@@ -41,6 +41,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
     while (!mbar_try_wait(bar, parity)) {}
 }
 
+// one lane of the (converged) warp, chosen by the hardware: code under it is known to run in a single thread, which
+// spares the copy instructions' uniform operands the compiler's "which active lane?" loop
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // global -> shared, completion counted on `bar`
 __device__ __forceinline__ void load(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar)
 {

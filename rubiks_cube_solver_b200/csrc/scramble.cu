@@ -237,7 +237,7 @@ scramble_pairs_kernel(const uint8_t* __restrict__ moves, int n_tiles, int depth_
     // stage tile `t`'s move bytes in buffer `b` (warp-uniform arguments): one 1-D bulk copy for the flat
     // image, one 2-D tensor copy (rows of 128 bytes, 128-byte swizzle) for the swizzled tile
     auto stage = [&](int t, int b) {
-        if (lane == 0) {
+        if (bulk::elect_one()) {
             bulk::mbar_expect_tx(&s_bar[b], move_bytes);
             if (!kPriv) bulk::load(s_moves + b * mstride, moves + (long long)t * move_bytes, move_bytes, &s_bar[b]);
             else bulk::load_tile_2d(s_moves + b * mstride, &move_map, 0, t * (kPairTile * depth >> 7), &s_bar[b]);
@@ -312,7 +312,7 @@ scramble_pairs_kernel(const uint8_t* __restrict__ moves, int n_tiles, int depth_
 #pragma unroll
             for (int k = 0; k < NS; ++k) scramble_pairs_last<SIZE>(st[k], last_w[k], tbl, lanereg, roff);
         }
-        if (lane == 0) bulk::wait_read_all();                         // the previous store has released the out tile
+        if (bulk::elect_one()) bulk::wait_read_all();                 // the previous store has released the out tile (elect.sync picks the same lane every time)
         __syncwarp();
         bool ok[NS];
 #pragma unroll
@@ -323,7 +323,7 @@ scramble_pairs_kernel(const uint8_t* __restrict__ moves, int n_tiles, int depth_
 
         bulk::fence_smem_writes();                                    // rows -> visible to the copy engine
         __syncwarp();
-        if (lane == 0) {
+        if (bulk::elect_one()) {
             bulk::store(out + (long long)tile * L::kOutBytes, s_out, (uint32_t)L::kOutBytes);
             bulk::commit();
         }
@@ -347,7 +347,8 @@ scramble_pairs_kernel(const uint8_t* __restrict__ moves, int n_tiles, int depth_
     n_solved = __reduce_add_sync(0xffffffffu, n_solved);
     if (lane == 0 && n_solved && counters) atomicAdd(&counters[0], (unsigned long long)n_solved);
     if (blockIdx.x == 0 && tid == 0 && counters) atomicAdd(&counters[1], (unsigned long long)n_tiles * kPairTile);
-    if (lane == 0) bulk::wait_read_all();                             // shared memory must outlive the copies' reads
+    __syncwarp();
+    if (bulk::elect_one()) bulk::wait_read_all();                     // shared memory must outlive the copies' reads
     __syncthreads();
     sched::release(slot);
 }
