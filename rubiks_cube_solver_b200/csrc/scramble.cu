@@ -203,9 +203,10 @@ struct PairSmem {
     }
 };
 
-// PLAIN: the common call -- solved and reward arrays present, no trailing action -- with the per-tile null
-// checks and the action fetch compiled out (~18 of a tile's ~1 080 instructions)
-template <int SIZE, int DEPTH, int NS, bool PLAIN>
+// MODE 1: the common call -- solved and reward arrays present, no trailing action -- with the per-tile null
+// checks and the action fetch compiled out (~18 of a tile's ~1 080 instructions); MODE 2: the same with the
+// trailing action of cube_scramble_step; MODE 0: any combination, decided at run time
+template <int SIZE, int DEPTH, int NS, int MODE>
 __global__ void __launch_bounds__(PairCfg<SIZE, NS>::kMaxWarps * 32, 1)
 scramble_pairs_kernel(const uint8_t* __restrict__ moves, int n_tiles, int depth_rt, uint8_t* __restrict__ out,
                       uint8_t* __restrict__ solved, float* __restrict__ reward, unsigned long long* __restrict__ counters,
@@ -280,8 +281,8 @@ scramble_pairs_kernel(const uint8_t* __restrict__ moves, int n_tiles, int depth_
     const uint32_t lanereg = pair_lanereg<SIZE>(lane, tbl), roff = pair_roff2(lane);
     const ColourLutShared lut{bulk::smem_addr(s_clut), bulk::smem_addr(s_elut)};
     unsigned n_solved = 0;
-    const bool has_last = !PLAIN && last != nullptr;
-    const bool has_solved = PLAIN || solved != nullptr, has_reward = PLAIN || reward != nullptr;
+    const bool has_last = MODE == 2 || (MODE == 0 && last != nullptr);
+    const bool has_solved = MODE != 0 || solved != nullptr, has_reward = MODE != 0 || reward != nullptr;
     for (int it = 0; tile < n_tiles; ++it) {
         const int buf = it & 1;
         const int next = tiles.pop(lane);
@@ -665,15 +666,17 @@ long long launch_pairs(const uint8_t* moves, long long n, int depth, uint8_t* ou
     if (warps < min_warps) return 0;
     const int smem = L::bytes(depth, warps, priv) + slack;
     // straight-line specialisations: the reference's default depth (config.yaml:7) and BASELINE config 2's
-    const bool plain = solved && reward && !last;
-    auto kern = plain ? (depth == 30 ? scramble_pairs_kernel<SIZE, 30, NS, true>
-                         : depth == 20 ? scramble_pairs_kernel<SIZE, 20, NS, true>
-                         : priv ? scramble_pairs_kernel<SIZE, (kCanSwizzle ? -1 : 0), NS, true> : scramble_pairs_kernel<SIZE, 0, NS, true>)
-                      : (depth == 30 ? scramble_pairs_kernel<SIZE, 30, NS, false>
-                         : depth == 20 ? scramble_pairs_kernel<SIZE, 20, NS, false>
-                         : priv ? scramble_pairs_kernel<SIZE, (kCanSwizzle ? -1 : 0), NS, false> : scramble_pairs_kernel<SIZE, 0, NS, false>);
-    static std::atomic<int> configured_smem[64][8];       // per device and kernel, 0 = never configured
-    std::atomic<int>& cfg = configured_smem[cube::device_slot()][(depth == 30 ? 1 : depth == 20 ? 2 : priv ? 3 : 0) + (plain ? 4 : 0)];
+    const int mode = (solved && reward) ? (last ? 2 : 1) : 0;
+    const int variant = depth == 30 ? 1 : depth == 20 ? 2 : priv ? 3 : 0;
+    using Kern = decltype(&scramble_pairs_kernel<SIZE, 0, NS, 0>);
+    constexpr int kSwz = kCanSwizzle ? -1 : 0;
+    static const Kern kerns[3][4] = {
+        {scramble_pairs_kernel<SIZE, 0, NS, 0>, scramble_pairs_kernel<SIZE, 30, NS, 0>, scramble_pairs_kernel<SIZE, 20, NS, 0>, scramble_pairs_kernel<SIZE, kSwz, NS, 0>},
+        {scramble_pairs_kernel<SIZE, 0, NS, 1>, scramble_pairs_kernel<SIZE, 30, NS, 1>, scramble_pairs_kernel<SIZE, 20, NS, 1>, scramble_pairs_kernel<SIZE, kSwz, NS, 1>},
+        {scramble_pairs_kernel<SIZE, 0, NS, 2>, scramble_pairs_kernel<SIZE, 30, NS, 2>, scramble_pairs_kernel<SIZE, 20, NS, 2>, scramble_pairs_kernel<SIZE, kSwz, NS, 2>}};
+    const Kern kern = kerns[mode][variant];
+    static std::atomic<int> configured_smem[64][12];      // per device and kernel, 0 = never configured
+    std::atomic<int>& cfg = configured_smem[cube::device_slot()][variant + 4 * mode];
     if (smem > cfg.load(std::memory_order_relaxed)) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return -(long long)e;
