@@ -3,6 +3,7 @@ csrc/cube_threads.cuh as plain C++) against the oracle.  Catches table / selecto
 bugs without a GPU; the product library never contains this code path."""
 import ctypes
 import os
+import re
 import subprocess
 
 import numpy as np
@@ -327,3 +328,25 @@ def test_scramble_sliced_emulation(emul, size, depth, with_last, slice_len):
     assert (solved.astype(bool) == O.is_solved(size, want)).all()
     if depth % 2 == 0 and not with_last:
         assert solved[8:24].all()
+
+
+def test_row_assembly_takes_the_centres_from_edge_lut_words():
+    """K1p's finishing pass (gen_tables.py: E_LUT_SLOT_3, assemble_row_fn): every edge slot's LUT carries the centre
+    colours of the slot's two faces in bytes 2 and 3, both alignments of the row assembly need 32 byte permutes
+    (38 with the centres as immediates), and no centre immediate is left in the generated code."""
+    g = _gen_tables()
+    assert len(g.E_LUT_SLOT_3) == 12 and all(len(lut) == 32 for lut in g.E_LUT_SLOT_3)
+    for slot, lut in zip(g.EDGE_SLOTS_3, g.E_LUT_SLOT_3):
+        for i, v in enumerate(lut):
+            assert v & 0xffff == g._E_LUT_32[i] & 0xffff                      # the two colours, as in the shared LUT
+            assert (v >> 16) & 0xff == slot[0] // 9 and v >> 24 == slot[1] // 9
+    for f in range(6):                                                        # four edge stickers per face
+        assert len(g.CENTRE_ALTERNATIVES_3[f]) == 4
+    src3 = g.sticker_sources([g.CORNER_SLOTS_3, g.EDGE_SLOTS_3], 54, {4 + 9 * f: f for f in range(6)})
+    for first, half_at in ((0, 52), (2, 0)):
+        with_alt = g.assemble_row_fn("f", src3, first, 13, half_at, g.CENTRE_ALTERNATIVES_3)
+        without = g.assemble_row_fn("f", src3, first, 13, half_at)
+        assert "// 32 byte permutes" in with_alt and "// 38 byte permutes" in without
+        # no immediate operand (a centre constant) remains: operands are L[..] words and nested permutes only
+        body = with_alt.split("{", 1)[1]
+        assert not re.search(r"cube_prmt\((0x[0-9a-f]{2}u)|, (0x[0-9a-f]{2}u),", body)
