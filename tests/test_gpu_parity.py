@@ -1421,3 +1421,22 @@ def test_adi_generate_samples_bf16_passthrough_within_tolerance(size):
                                 a32["parent_values"].cpu().numpy(), a32["scramble_count"].cpu().numpy(), 0.5)
     assert (a32["target_value"].cpu().numpy() == tv).all() and (a32["target_policy"].cpu().numpy() == tp).all()
     assert np.allclose(a32["error"].cpu().numpy(), err, rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("switch", ["CUBE_PAIR_SWIZZLE=0", "CUBE_PAIR_FOUR=0", "CUBE_SCRAMBLE_CLASSIC=1", "CUBE_TAIL_DIV=1"])
+def test_fallback_paths_under_ab_switches(switch):
+    """The library reads its A/B switches once per process, so every fallback path gets its own
+    interpreter: the depth / boundary / garbage-byte scramble tests again, with the switch set.  (The default paths
+    are what the rest of this file runs; all switches x the whole scramble / step / walk selection were run by hand
+    on the final tree)"""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    name, value = switch.split("=")
+    env = dict(os.environ, **{name: value})
+    k = ("test_scramble_vs_oracle_depths or test_scramble_tile_and_depth_boundaries or "
+         "test_garbage_action_bytes_are_memory_safe_scramble or test_scramble_swizzled_move_tiles")
+    out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-m", "gpu", "-x", "-q",
+                          "-p", "no:cacheprovider", "-k", k], capture_output=True, text=True, timeout=600, env=env, cwd=root)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
+    assert " passed" in out.stdout and " failed" not in out.stdout
